@@ -1,0 +1,321 @@
+// oracle_radtool.hpp - CPU restatement of the reference's radtool/ layer.
+//
+// TEST INFRASTRUCTURE ONLY.  This is the parity oracle for the CUDA path; it
+// is never linked into, imported by, or called from the product library.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load it.
+//
+// Parity status: "parity unpinned" by exact goldens - the reference ships no
+// expected outputs and cannot be compiled here (no Fortran
+// compiler).  The restatement follows the Fortran operation-for-operation and
+// is cross-checked by tests/test_oracle_*.py (brute-force matrix exponential,
+// dense inverse, doc budget table to 3 d.p., designed-to-agree fixture pairs).
+//
+// Every routine cites the reference file:line it follows
+// (paths relative to the reference root).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <limits>
+
+namespace orc {
+
+// One dense matrix of ONE spectral interval.  The reference stores
+// (nmat, i, j) with the spectral index fastest (radtool_matrix.F90:18-24) and
+// loops it innermost; no operation mixes spectral intervals, so looping the
+// interval outermost gives identical arithmetic per interval.
+struct Mat {
+  int r = 0, c = 0;
+  std::vector<double> a;
+  Mat() {}
+  Mat(int r_, int c_) : r(r_), c(c_), a((size_t)r_ * c_, 0.0) {}
+  double &operator()(int i, int j) { return a[(size_t)i + (size_t)r * j]; }
+  double operator()(int i, int j) const { return a[(size_t)i + (size_t)r * j]; }
+  void zero() { std::fill(a.begin(), a.end(), 0.0); }
+};
+typedef std::vector<double> Vec;
+
+inline Mat operator+(const Mat &A, const Mat &B) {
+  Mat C(A.r, A.c);
+  for (size_t k = 0; k < A.a.size(); ++k) C.a[k] = A.a[k] + B.a[k];
+  return C;
+}
+inline Mat operator-(const Mat &A, const Mat &B) {
+  Mat C(A.r, A.c);
+  for (size_t k = 0; k < A.a.size(); ++k) C.a[k] = A.a[k] - B.a[k];
+  return C;
+}
+inline Mat neg(const Mat &A) {
+  Mat C(A.r, A.c);
+  for (size_t k = 0; k < A.a.size(); ++k) C.a[k] = -A.a[k];
+  return C;
+}
+inline Vec operator+(const Vec &a, const Vec &b) {
+  Vec c(a.size());
+  for (size_t k = 0; k < a.size(); ++k) c[k] = a[k] + b[k];
+  return c;
+}
+inline Vec operator-(const Vec &a, const Vec &b) {
+  Vec c(a.size());
+  for (size_t k = 0; k < a.size(); ++k) c[k] = a[k] - b[k];
+  return c;
+}
+
+// Sub-block copy / paste helpers for the "clear-only" / "veg-only" branches
+// (radsurf_urban_sw.F90:512-583 pass array sections).
+inline Mat sub(const Mat &A, int i0, int ni, int j0, int nj) {
+  Mat B(ni, nj);
+  for (int j = 0; j < nj; ++j)
+    for (int i = 0; i < ni; ++i) B(i, j) = A(i0 + i, j0 + j);
+  return B;
+}
+inline void paste(Mat &A, int i0, int j0, const Mat &B) {
+  for (int j = 0; j < B.c; ++j)
+    for (int i = 0; i < B.r; ++i) A(i0 + i, j0 + j) = B(i, j);
+}
+
+// mat_x_vec / rect_mat_x_vec / singlemat_x_vec / rect_singlemat_x_vec
+// radtool_matrix.F90:71-118,125-159,166-199,206-240: y(j1) = sum_j2 A(j1,j2) b(j2),
+// accumulated from zero in ascending j2.
+inline Vec matvec(const Mat &A, const Vec &b) {
+  Vec y(A.r, 0.0);
+  for (int j1 = 0; j1 < A.r; ++j1)
+    for (int j2 = 0; j2 < A.c; ++j2) y[j1] = y[j1] + A(j1, j2) * b[j2];
+  return y;
+}
+
+// mat_x_mat / rect_mat_x_mat / rect_mat_x_singlemat
+// radtool_matrix.F90:248-328,335-371,462-497: C(j1,j2) = sum_j3 A(j1,j3) B(j3,j2),
+// accumulated from zero in ascending j3 (dense pattern only; the
+// IMatrixPatternShortwave branch has no callers).
+inline Mat matmul(const Mat &A, const Mat &B) {
+  Mat C(A.r, B.c);
+  for (int j2 = 0; j2 < B.c; ++j2)
+    for (int j3 = 0; j3 < A.c; ++j3) {
+      const double b = B(j3, j2);
+      for (int j1 = 0; j1 < A.r; ++j1) C(j1, j2) = C(j1, j2) + A(j1, j3) * b;
+    }
+  return C;
+}
+
+// rect_expandedmat_x_mat radtool_matrix.F90:505-549: (A (x) I_s) * B, A is
+// m-by-o, zero entries of A skipped.
+inline Mat expandedmat_x_mat(int m, int o, int s, const Mat &A, const Mat &B) {
+  const int p = B.c;
+  Mat C(m * s, p);
+  for (int j1 = 0; j1 < m; ++j1)
+    for (int j3 = 0; j3 < o; ++j3)
+      if (A(j1, j3) != 0.0) {
+        const int offset2 = (j3 - j1) * s;
+        for (int jj2 = 0; jj2 < p; ++jj2)
+          for (int jj1 = j1 * s; jj1 < (j1 + 1) * s; ++jj1)
+            C(jj1, jj2) = C(jj1, jj2) + A(j1, j3) * B(jj1 + offset2, jj2);
+      }
+  return C;
+}
+
+// rect_mat_x_expandedmat radtool_matrix.F90:556-599: A * (B (x) I_s), B is
+// m-by-o, A is p-by-(m*s).
+inline Mat mat_x_expandedmat(int m, int o, int s, const Mat &A, const Mat &B) {
+  const int p = A.r;
+  Mat C(p, o * s);
+  for (int j2 = 0; j2 < o; ++j2)
+    for (int j3 = 0; j3 < m; ++j3)
+      if (B(j3, j2) != 0.0) {
+        const int offset3 = (j3 - j2) * s;
+        for (int jj1 = 0; jj1 < p; ++jj1)
+          for (int jj2 = j2 * s; jj2 < (j2 + 1) * s; ++jj2)
+            C(jj1, jj2) = C(jj1, jj2) + A(jj1, jj2 + offset3) * B(j3, j2);
+      }
+  return C;
+}
+
+// rect_expandedmat_x_vec radtool_matrix.F90:608-648.
+inline Vec expandedmat_x_vec(int m, int k, int s, const Mat &A, const Vec &b) {
+  Vec y((size_t)m * s, 0.0);
+  for (int j1 = 0; j1 < m; ++j1)
+    for (int j3 = 0; j3 < k; ++j3)
+      if (A(j1, j3) != 0.0) {
+        const int offset2 = (j3 - j1) * s;
+        for (int jj1 = j1 * s; jj1 < (j1 + 1) * s; ++jj1)
+          y[jj1] = y[jj1] + A(j1, j3) * b[jj1 + offset2];
+      }
+  return y;
+}
+
+// identity_minus_mat_x_mat radtool_matrix.F90:655-691.
+inline Mat identity_minus_mat_x_mat(const Mat &A, const Mat &B) {
+  Mat C = matmul(A, B);
+  for (size_t k = 0; k < C.a.size(); ++k) C.a[k] = -C.a[k];
+  for (int j = 0; j < C.r; ++j) C(j, j) = 1.0 + C(j, j);
+  return C;
+}
+
+// lu_factorization radtool_matrix.F90:982-1017: Crout-style, NO pivoting.
+inline Mat lu_factorization(const Mat &A) {
+  const int m = A.r;
+  Mat LU = A;
+  for (int j2 = 0; j2 < m; ++j2) {
+    for (int j1 = 0; j1 < j2; ++j1) {
+      double s = LU(j1, j2);
+      for (int j3 = 0; j3 < j1; ++j3) s = s - LU(j1, j3) * LU(j3, j2);
+      LU(j1, j2) = s;
+    }
+    for (int j1 = j2; j1 < m; ++j1) {
+      double s = LU(j1, j2);
+      for (int j3 = 0; j3 < j2; ++j3) s = s - LU(j1, j3) * LU(j3, j2);
+      LU(j1, j2) = s;
+    }
+    if (j2 != m - 1) {
+      const double s = 1.0 / LU(j2, j2);
+      for (int j1 = j2 + 1; j1 < m; ++j1) LU(j1, j2) = LU(j1, j2) * s;
+    }
+  }
+  return LU;
+}
+
+// lu_substitution radtool_matrix.F90:1024-1049.
+inline Vec lu_substitution(const Mat &LU, const Vec &b) {
+  const int m = LU.r;
+  Vec x(b.begin(), b.begin() + m);
+  for (int j2 = 1; j2 < m; ++j2)
+    for (int j1 = 0; j1 < j2; ++j1) x[j2] = x[j2] - x[j1] * LU(j2, j1);
+  for (int j2 = m - 1; j2 >= 0; --j2) {
+    for (int j1 = j2 + 1; j1 < m; ++j1) x[j2] = x[j2] - x[j1] * LU(j2, j1);
+    x[j2] = x[j2] / LU(j2, j2);
+  }
+  return x;
+}
+
+// lu_invert radtool_matrix.F90:1057-1090 (identity right-hand sides).
+inline Mat lu_invert(const Mat &LU) {
+  const int m = LU.r;
+  Mat X(m, m);
+  for (int j3 = 0; j3 < m; ++j3) {
+    X(j3, j3) = 1.0;
+    for (int j2 = 1; j2 < m; ++j2)
+      for (int j1 = 0; j1 < j2; ++j1) X(j2, j3) = X(j2, j3) - X(j1, j3) * LU(j2, j1);
+    for (int j2 = m - 1; j2 >= 0; --j2) {
+      for (int j1 = j2 + 1; j1 < m; ++j1) X(j2, j3) = X(j2, j3) - X(j1, j3) * LU(j2, j1);
+      X(j2, j3) = X(j2, j3) / LU(j2, j2);
+    }
+  }
+  return X;
+}
+
+// solve_rect_mat radtool_matrix.F90:1119-1135 (always general LU).
+inline Mat solve_rect_mat(const Mat &A, const Mat &B) {
+  Mat LU = lu_factorization(A);
+  Mat X(A.r, B.c);
+  Vec col(A.r);
+  for (int j = 0; j < B.c; ++j) {
+    for (int i = 0; i < A.r; ++i) col[i] = B(i, j);
+    Vec x = lu_substitution(LU, col);
+    for (int i = 0; i < A.r; ++i) X(i, j) = x[i];
+  }
+  return X;
+}
+
+// solve_vec radtool_matrix.F90:1143-1169 with solve_vec_2 (:779-795, Cramer)
+// and solve_vec_3 (:827-864, explicit LU); re-factorises on every call.
+inline Vec solve_vec(const Mat &A, const Vec &b) {
+  const int m = A.r;
+  if (m == 2) {
+    const double inv_det = 1.0 / (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
+    Vec x(2);
+    x[0] = inv_det * (A(1, 1) * b[0] - A(0, 1) * b[1]);
+    x[1] = inv_det * (A(0, 0) * b[1] - A(1, 0) * b[0]);
+    return x;
+  } else if (m == 3) {
+    const double L21 = A(1, 0) / A(0, 0);
+    const double L31 = A(2, 0) / A(0, 0);
+    const double U22 = A(1, 1) - L21 * A(0, 1);
+    const double U23 = A(1, 2) - L21 * A(0, 2);
+    const double L32 = (A(2, 1) - L31 * A(0, 1)) / U22;
+    const double U33 = A(2, 2) - L31 * A(0, 2) - L32 * U23;
+    const double y2 = b[1] - L21 * b[0];
+    const double y3 = b[2] - L31 * b[0] - L32 * y2;
+    Vec x(3);
+    x[2] = y3 / U33;
+    x[1] = (y2 - U23 * x[2]) / U22;
+    x[0] = (b[0] - A(0, 1) * x[1] - A(0, 2) * x[2]) / A(0, 0);
+    return x;
+  }
+  return lu_substitution(lu_factorization(A), b);
+}
+
+// solve_mat radtool_matrix.F90:1175-1197 with solve_mat_2 (:801-821),
+// solve_mat_3 (:870-906), solve_mat_n (:1096-1113).
+inline Mat solve_mat(const Mat &A, const Mat &B) {
+  const int m = A.r;
+  Mat X(m, m);
+  if (m == 2) {
+    const double inv_det = 1.0 / (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
+    X(0, 0) = inv_det * (A(1, 1) * B(0, 0) - A(0, 1) * B(1, 0));
+    X(1, 0) = inv_det * (A(0, 0) * B(1, 0) - A(1, 0) * B(0, 0));
+    X(0, 1) = inv_det * (A(1, 1) * B(0, 1) - A(0, 1) * B(1, 1));
+    X(1, 1) = inv_det * (A(0, 0) * B(1, 1) - A(1, 0) * B(0, 1));
+    return X;
+  } else if (m == 3) {
+    const double L21 = A(1, 0) / A(0, 0);
+    const double L31 = A(2, 0) / A(0, 0);
+    const double U22 = A(1, 1) - L21 * A(0, 1);
+    const double U23 = A(1, 2) - L21 * A(0, 2);
+    const double L32 = (A(2, 1) - L31 * A(0, 1)) / U22;
+    const double U33 = A(2, 2) - L31 * A(0, 2) - L32 * U23;
+    for (int j = 0; j < 3; ++j) {
+      const double y2 = B(1, j) - L21 * B(0, j);
+      const double y3 = B(2, j) - L31 * B(0, j) - L32 * y2;
+      X(2, j) = y3 / U33;
+      X(1, j) = (y2 - U23 * X(2, j)) / U22;
+      X(0, j) = (B(0, j) - A(0, 1) * X(1, j) - A(0, 2) * X(2, j)) / A(0, 0);
+    }
+    return X;
+  }
+  return solve_rect_mat(A, B);
+}
+
+// invert radtool_matrix.F90:1203-1235 (general LU for every order).
+inline Mat invert(const Mat &A) { return lu_invert(lu_factorization(A)); }
+
+// Column scaling A * diag(d): the `A * spread(d,2,n)` idiom
+// (radtool_calc_matrices_sw_eig.F90:194,205-206).
+inline Mat scale_cols(const Mat &A, const Vec &d) {
+  Mat B(A.r, A.c);
+  for (int j = 0; j < A.c; ++j)
+    for (int i = 0; i < A.r; ++i) B(i, j) = A(i, j) * d[j];
+  return B;
+}
+
+struct LegendreGauss {
+  int nstream = 0;
+  Vec mu, sin_ang, tan_ang, weight, hweight, vweight;
+  double vadjustment = 1.0, vadjustment2 = 1.0;
+};
+
+void calc_legendre_gauss(int nnode, double x1, double x2, Vec &xnode, Vec &weight);
+void legendre_gauss_initialize(LegendreGauss &lg, int nstream);
+
+// Returns number of failures (0 or 1) like the optional nerror argument.
+int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &eigenvector);
+
+void schur_invert_sw(const Mat &g0, const Mat &g1, const Mat &g2, const Mat &g3, Mat &g0i,
+                     Mat &g1i, Mat &g2i, Mat &g3i);
+
+void calc_matrices_sw_eig(int ndiff, int ndir, double dz, double mu0, const Mat &gamma0,
+                          const Mat &gamma1, const Mat &gamma2, const Mat &gamma3,
+                          Mat &reflectance, Mat &transmittance, Mat &s_up, Mat &s_dn,
+                          Mat &trans_dir, Mat &int_dir, Mat &int_diff, Mat &int_dir_diff);
+
+void calc_matrices_lw_eig(int norder, double dz, const Mat &gamma1, const Mat &gamma2,
+                          const Vec &emiss_rate, Mat &reflectance, Mat &transmittance,
+                          Vec &source, Mat &int_flux, Vec &int_flux_source);
+
+// Instrumented flop counter (SURVEY.md App. C asks the oracle to publish a
+// measured constant next to the closed-form estimate).  Counted analytically
+// per call from the loop bounds; disabled unless enabled by the test.
+extern thread_local double g_flops;
+
+} // namespace orc
