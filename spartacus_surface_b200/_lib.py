@@ -1,0 +1,64 @@
+"""Loader of the product C-ABI library (csrc/libspartacus_b200.so).
+
+There is no CPU fallback: if the library is missing this raises, and every
+solve entry point of the library itself returns SSB200_ERR_NOGPU when no CUDA
+device is visible.
+"""
+import ctypes as C
+import os
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libspartacus_b200.so")
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    P = C.POINTER
+    lib.ssb200_version.restype = C.c_char_p
+    lib.ssb200_last_error.restype = C.c_char_p
+    lib.ssb200_device_count.restype = C.c_int
+    lib.ssb200_set_device.argtypes = [C.c_int]
+    lib.ssb200_legendre_gauss_init.argtypes = [C.c_int32, P(_abi.LegendreGauss)]
+    radsurf_args = [P(_abi.Config), P(_abi.CanopyProperties), P(_abi.SwSpectralProperties),
+                    P(_abi.LwSpectralProperties), P(_abi.BoundaryCondsOut), C.c_int32, C.c_int32,
+                    P(_abi.CanopyFlux), P(_abi.CanopyFlux), P(_abi.CanopyFlux), P(_abi.CanopyFlux)]
+    lib.ssb200_radsurf.argtypes = radsurf_args
+    lib.ssb200_radsurf.restype = C.c_int
+    lib.ssb200_radsurf_device.argtypes = radsurf_args + [C.c_void_p, P(C.c_int32)]
+    lib.ssb200_radsurf_device.restype = C.c_int
+    lib.ssb200_kernel_launch_count.restype = C.c_int64
+    lib.ssb200_set_profiling.argtypes = [C.c_int]
+    lib.ssb200_last_kernel_times_ms.argtypes = [P(C.c_double)]
+    lib.ssb200_release.restype = C.c_int
+    lib.ssb200_canopy_flux_scale_device.argtypes = [P(_abi.CanopyFlux), P(C.c_int32), P(C.c_int32),
+                                                    C.c_void_p, C.c_void_p]
+    lib.ssb200_canopy_flux_sum_device.argtypes = [P(_abi.CanopyFlux), P(_abi.CanopyFlux),
+                                                  P(_abi.CanopyFlux), C.c_void_p]
+    lib.ssb200_canopy_flux_check_device.argtypes = [P(_abi.CanopyFlux), P(_abi.CanopyProperties),
+                                                    C.c_void_p, C.c_void_p]
+    lib.ssb200_measure_fp64_peak_tflops.argtypes = [C.c_int]
+    lib.ssb200_measure_fp64_peak_tflops.restype = C.c_double
+    return lib
+
+
+def load():
+    """Return the ctypes handle of libspartacus_b200.so (built by __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        _lib = _declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def last_error():
+    return load().ssb200_last_error().decode()

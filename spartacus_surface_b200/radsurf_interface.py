@@ -1,0 +1,67 @@
+"""radsurf: the public entry of the path (radsurf/radsurf_interface.F90:20-25).
+
+Same argument list and meaning as the reference subroutine; the body is the
+B200 library (ssb200_radsurf for host arrays, ssb200_radsurf_device when the
+members are torch CUDA tensors).  The reference aborts on error
+(utilities/radiation_io.F90:46-54); here errors raise RadsurfError.
+"""
+import ctypes as C
+
+from ._arrays import is_torch
+from ._lib import load, last_error
+
+
+class RadsurfError(RuntimeError):
+    pass
+
+
+def marshal(config, canopy_props, sw_spectral_props, lw_spectral_props, bc_out,
+            sw_norm_dir=None, sw_norm_diff=None, lw_internal=None, lw_norm=None):
+    """Build the C structs of include/spartacus_b200.h from the API objects.
+
+    Returned objects own no array memory: the caller's arrays must outlive
+    the call (same ownership rule as the Fortran allocatables).
+    """
+    structs = dict(
+        config=config.as_struct(),
+        canopy=canopy_props.as_struct(),
+        sw=sw_spectral_props.as_struct() if sw_spectral_props is not None else None,
+        lw=lw_spectral_props.as_struct() if lw_spectral_props is not None else None,
+        bc=bc_out.as_struct(),
+        sw_norm_dir=sw_norm_dir.as_struct() if sw_norm_dir is not None else None,
+        sw_norm_diff=sw_norm_diff.as_struct() if sw_norm_diff is not None else None,
+        lw_internal=lw_internal.as_struct() if lw_internal is not None else None,
+        lw_norm=lw_norm.as_struct() if lw_norm is not None else None,
+    )
+    return structs
+
+
+def _ref(s):
+    return C.byref(s) if s is not None else None
+
+
+def call_radsurf(fn, structs, istartcol, iendcol, extra=()):
+    s = structs
+    return fn(_ref(s["config"]), _ref(s["canopy"]), _ref(s["sw"]), _ref(s["lw"]), _ref(s["bc"]),
+              int(istartcol or 0), int(iendcol or 0), _ref(s["sw_norm_dir"]), _ref(s["sw_norm_diff"]),
+              _ref(s["lw_internal"]), _ref(s["lw_norm"]), *extra)
+
+
+def radsurf(config, canopy_props, sw_spectral_props, lw_spectral_props, bc_out,
+            istartcol=None, iendcol=None, sw_norm_dir=None, sw_norm_diff=None,
+            lw_internal=None, lw_norm=None, stream=None):
+    """Solve columns istartcol..iendcol (1-based inclusive, default all)."""
+    lib = load()
+    structs = marshal(config, canopy_props, sw_spectral_props, lw_spectral_props, bc_out,
+                      sw_norm_dir, sw_norm_diff, lw_internal, lw_norm)
+    device = is_torch(canopy_props.dz) if canopy_props.dz is not None else is_torch(bc_out.sw_albedo
+                                                                                    if bc_out.sw_albedo is not None
+                                                                                    else bc_out.lw_emissivity)
+    if device:
+        rc = call_radsurf(lib.ssb200_radsurf_device, structs, istartcol, iendcol,
+                          extra=(C.c_void_p(stream or 0), None))
+    else:
+        rc = call_radsurf(lib.ssb200_radsurf, structs, istartcol, iendcol)
+    if rc < 0:
+        raise RadsurfError(f"ssb200_radsurf failed (rc={rc}): {last_error()}")
+    return rc
