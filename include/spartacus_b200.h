@@ -146,6 +146,12 @@ typedef struct ssb200_boundary_conds_out {
 /* Library / build identification string. */
 const char *ssb200_version(void);
 
+/* sizeof() of the ABI structs in declaration order (legendre_gauss, config,
+ * canopy_properties, sw_spectral_properties, lw_spectral_properties,
+ * canopy_flux, boundary_conds_out): lets a foreign-language binding verify its
+ * mirror of this header at load time. */
+int ssb200_abi_sizes(int64_t out[7]);
+
 /* Text of the last error raised on the calling thread ("" if none). */
 const char *ssb200_last_error(void);
 
@@ -211,6 +217,12 @@ int64_t ssb200_kernel_launch_count(void);
  * events and synchronises at the end of the call). */
 int ssb200_set_profiling(int enable);
 int ssb200_last_kernel_times_ms(double out[5]);
+
+/* Tuning knobs: "scratch_budget_bytes" (device scratch per launch chunk;
+ * 0 = automatic: half of the free memory, at most 24 GiB) and "fast_kernels"
+ * (1 = use the sub-warp kernels where a configuration has one, 0 = generic
+ * one-thread-per-problem kernels everywhere; results agree to rounding). */
+int ssb200_set_option(const char *name, int64_t value);
 
 /* Release cached plans, scratch and pinned staging buffers. */
 int ssb200_release(void);

@@ -23,6 +23,7 @@ def _declare(lib):
     P = C.POINTER
     lib.ssb200_version.restype = C.c_char_p
     lib.ssb200_last_error.restype = C.c_char_p
+    lib.ssb200_abi_sizes.argtypes = [P(C.c_int64)]
     lib.ssb200_device_count.restype = C.c_int
     lib.ssb200_set_device.argtypes = [C.c_int]
     lib.ssb200_legendre_gauss_init.argtypes = [C.c_int32, P(_abi.LegendreGauss)]
@@ -37,6 +38,7 @@ def _declare(lib):
     lib.ssb200_set_profiling.argtypes = [C.c_int]
     lib.ssb200_last_kernel_times_ms.argtypes = [P(C.c_double)]
     lib.ssb200_release.restype = C.c_int
+    lib.ssb200_set_option.argtypes = [C.c_char_p, C.c_int64]
     lib.ssb200_canopy_flux_scale_device.argtypes = [P(_abi.CanopyFlux), P(C.c_int32), P(C.c_int32),
                                                     C.c_void_p, C.c_void_p]
     lib.ssb200_canopy_flux_sum_device.argtypes = [P(_abi.CanopyFlux), P(_abi.CanopyFlux),
@@ -56,7 +58,15 @@ def load():
             raise LibraryMissing(
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback)")
-        _lib = _declare(C.CDLL(LIB_PATH))
+        lib = _declare(C.CDLL(LIB_PATH))
+        sizes = (C.c_int64 * 7)()
+        lib.ssb200_abi_sizes(sizes)
+        mirror = [C.sizeof(t) for t in (_abi.LegendreGauss, _abi.Config, _abi.CanopyProperties,
+                                       _abi.SwSpectralProperties, _abi.LwSpectralProperties,
+                                       _abi.CanopyFlux, _abi.BoundaryCondsOut)]
+        if list(sizes) != mirror:
+            raise RuntimeError(f"ctypes mirror out of date: library {list(sizes)} vs _abi.py {mirror}")
+        _lib = lib
     return _lib
 
 

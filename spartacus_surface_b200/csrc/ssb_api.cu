@@ -1,0 +1,819 @@
+// ssb_api.cu - kernels and C-ABI entry points of libspartacus_b200.so
+// (include/spartacus_b200.h).  sm_100a only; there is no CPU fallback: every
+// solve entry returns SSB200_ERR_NOGPU when no CUDA device is present.
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "ssb_driver.hpp"
+#include "ssb_fast.cuh"
+#include "ssb_launch.hpp"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::mutex g_mutex;
+long long g_launches = 0;
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define SSB_CUDA(call)                                                                           \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(SSB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+// Flat tiles and single-layer urban models (the generic kernels live in ssb_k_ns*_*.cu)
+__global__ void k_surface(ssb::SurfaceArgs s, int nsw_threads, int nlw_threads) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nsw_threads) ssb::surface_column_sw(s, t / s.nsw, t % s.nsw);
+  if (t < nlw_threads) ssb::surface_column_lw(s, t / s.nlw, t % s.nlw);
+}
+
+// ---------------------------------------------------------------------------
+// canopy_flux_type%scale / %sum / %check on device
+// ---------------------------------------------------------------------------
+struct FieldList {
+  double *p[32];
+  const double *a[32], *b[32];
+  int per_layer[32];  // 1: (nspec, ntotlay), 0: (nspec, ncol)
+  int spectral[32];
+  int n;
+};
+
+__global__ void k_scale(FieldList fl, const double *factor, const int *lay2col, int nspec, long ncol, long ntotlay) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  for (int f = 0; f < fl.n; ++f) {
+    const long cnt = (fl.per_layer[f] ? ntotlay : ncol) * nspec;
+    if (t < cnt) {
+      const long idx = t / nspec;
+      const int g = (int)(t % nspec);
+      const long col = fl.per_layer[f] ? lay2col[idx] : idx;
+      fl.p[f][t] = factor[g + (long)nspec * col] * fl.p[f][t];
+    }
+  }
+}
+
+__global__ void k_sum(FieldList fl, int nspec, long ncol, long ntotlay) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  for (int f = 0; f < fl.n; ++f) {
+    const long cnt = (fl.per_layer[f] ? ntotlay : ncol) * (fl.spectral[f] ? nspec : 1);
+    if (t < cnt) fl.p[f][t] = fl.a[f][t] + fl.b[f][t];
+  }
+}
+
+__global__ void k_check(ssb200_canopy_flux f, const int *nlay, const int *istartlay, const int *irep, int ncol,
+                        double *residual) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  const int ns = f.nspec;
+  const int l1 = istartlay[col] - 1, nl = nlay[col], rep = irep[col];
+  auto sum_col = [&](const double *p) {
+    double s = 0.0;
+    for (int g = 0; g < ns; ++g) s += p[g + (size_t)ns * col];
+    return s;
+  };
+  auto sum_lay = [&](const double *p) {
+    double s = 0.0;
+    if (p)
+      for (int l = 0; l < nl; ++l)
+        for (int g = 0; g < ns; ++g) s += p[g + (size_t)ns * (l1 + l)];
+    return s;
+  };
+  const double ground_net = sum_col(f.ground_net), top_net = sum_col(f.top_net);
+  const double clear = (rep != SSB200_TILE_FLAT) ? sum_lay(f.clear_air_abs) : 0.0;
+  double roof = 0.0, wall = 0.0, veg = 0.0, vegair = 0.0;
+  if (rep == SSB200_TILE_URBAN || rep == SSB200_TILE_VEGETATED_URBAN || rep == SSB200_TILE_SIMPLE_URBAN ||
+      rep == SSB200_TILE_INFINITE_STREET) {
+    roof = sum_lay(f.roof_net);
+    wall = sum_lay(f.wall_net);
+  }
+  if (rep == SSB200_TILE_FOREST || rep == SSB200_TILE_VEGETATED_URBAN) {
+    veg = sum_lay(f.veg_abs);
+    vegair = sum_lay(f.veg_air_abs);
+  }
+  residual[col] = ground_net + clear + wall + roof + veg + vegair - top_net;
+}
+
+// register-resident independent DFMA chains: FP64 roofline denominator
+__global__ void k_fp64_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c);
+    a1 = fma(a1, m, c);
+    a2 = fma(a2, m, c);
+    a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c);
+    a5 = fma(a5, m, c);
+    a6 = fma(a6, m, c);
+    a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------
+// Context: cached device buffers, plan, scratch
+// ---------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+struct Context {
+  ssb::Plan plan;
+  bool plan_uploaded = false;
+  long uploaded_generation = -1;
+  DevBuf d_nlay, d_istart, d_irep, d_cols, d_scratch, d_status, d_lay2col;
+  std::vector<DevBuf> stage;  // staging mirrors of host arrays for ssb200_radsurf
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  size_t budget_doubles = 0;
+  bool profiling = false;
+  double times_ms[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaError_t first_error = cudaSuccess;
+  int fast_mode = 1;
+};
+Context g_ctx;
+
+struct CudaBackend {
+  Context &cx;
+  explicit CudaBackend(Context &c) : cx(c) {}
+  const int *dev_cols(const ssb::Plan &, size_t off) { return (const int *)cx.d_cols.p + off; }
+  const int *dev_nlay() { return (const int *)cx.d_nlay.p; }
+  const int *dev_istartlay() { return (const int *)cx.d_istart.p; }
+  const int *dev_irep() { return (const int *)cx.d_irep.p; }
+  int *dev_status() { return (int *)cx.d_status.p; }
+  size_t scratch_budget_doubles() { return cx.budget_doubles; }
+  double *scratch(size_t n) {
+    cudaError_t e = cx.d_scratch.reserve(n * sizeof(double));
+    if (e != cudaSuccess && cx.first_error == cudaSuccess) cx.first_error = e;
+    return (double *)cx.d_scratch.p;
+  }
+  void tick(int family, bool start) {
+    if (!cx.profiling) return;
+    if (start) {
+      cudaEventRecord(cx.ev0, cx.stream);
+    } else {
+      cudaEventRecord(cx.ev1, cx.stream);
+      cudaEventSynchronize(cx.ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, cx.ev0, cx.ev1);
+      cx.times_ms[family] += ms;
+    }
+  }
+  void check_launch() {
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && cx.first_error == cudaSuccess) cx.first_error = e;
+  }
+  template <class F>
+  void launch(F launcher, const ssb::ClassArgs &a, long nt, int family) {
+    if (nt <= 0 || cx.first_error != cudaSuccess) return;
+    tick(family, true);
+    launcher(a, nt, cx.stream);
+    check_launch();
+    tick(family, false);
+  }
+  template <int NS>
+  void layer_sw(const ssb::ClassArgs &a, long nt) {
+    if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
+      tick(0, true);
+      const bool done = ssb::fast_layer_sw<NS>(a, nt, cx.stream);
+      if (done) check_launch();
+      tick(0, false);
+      if (done) return;
+    }
+    launch(ssb::launch_layer_sw<NS>, a, nt, 0);
+  }
+  template <int NS>
+  void layer_lw(const ssb::ClassArgs &a, long nt) {
+    if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
+      tick(2, true);
+      const bool done = ssb::fast_layer_lw<NS>(a, nt, cx.stream);
+      if (done) check_launch();
+      tick(2, false);
+      if (done) return;
+    }
+    launch(ssb::launch_layer_lw<NS>, a, nt, 2);
+  }
+  template <int NS>
+  void sweeps_sw(const ssb::ClassArgs &a, long nt) {
+    launch(ssb::launch_sweeps_sw<NS>, a, nt, 1);
+  }
+  template <int NS>
+  void sweeps_lw(const ssb::ClassArgs &a, long nt) {
+    launch(ssb::launch_sweeps_lw<NS>, a, nt, 3);
+  }
+  void surface(const ssb::SurfaceArgs &s, int nsw_threads, int nlw_threads) {
+    const int nt = nsw_threads > nlw_threads ? nsw_threads : nlw_threads;
+    if (nt <= 0 || cx.first_error != cudaSuccess) return;
+    tick(4, true);
+    k_surface<<<(nt + 127) / 128, 128, 0, cx.stream>>>(s, nsw_threads, nlw_threads);
+    check_launch();
+    tick(4, false);
+  }
+};
+
+int ensure_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(SSB200_ERR_NOGPU, "no CUDA device visible: libspartacus_b200 has no CPU fallback");
+  }
+  return 0;
+}
+
+int upload_plan(Context &cx, const ssb200_canopy_properties &cp) {
+  const size_t ncol = (size_t)cp.ncol;
+  SSB_CUDA(cx.d_nlay.reserve(sizeof(int) * (ncol + 1)));
+  SSB_CUDA(cx.d_istart.reserve(sizeof(int) * (ncol + 1)));
+  SSB_CUDA(cx.d_irep.reserve(sizeof(int) * (ncol + 1)));
+  SSB_CUDA(cx.d_cols.reserve(sizeof(int) * (cx.plan.all_cols.size() + 1)));
+  SSB_CUDA(cudaMemcpyAsync(cx.d_nlay.p, cx.plan.nlay.data(), sizeof(int) * ncol, cudaMemcpyHostToDevice, cx.stream));
+  SSB_CUDA(cudaMemcpyAsync(cx.d_istart.p, cx.plan.istartlay.data(), sizeof(int) * ncol, cudaMemcpyHostToDevice,
+                           cx.stream));
+  SSB_CUDA(cudaMemcpyAsync(cx.d_irep.p, cx.plan.irep.data(), sizeof(int) * ncol, cudaMemcpyHostToDevice, cx.stream));
+  SSB_CUDA(cudaMemcpyAsync(cx.d_cols.p, cx.plan.all_cols.data(), sizeof(int) * cx.plan.all_cols.size(),
+                           cudaMemcpyHostToDevice, cx.stream));
+  // the host vectors must stay unchanged until the copies are done
+  SSB_CUDA(cudaStreamSynchronize(cx.stream));
+  cx.plan_uploaded = true;
+  cx.uploaded_generation = cx.plan.generation;
+  return 0;
+}
+
+// Core of both entry points; all double arrays are device pointers here.
+int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, int iendcol, cudaStream_t stream,
+                          int32_t *status_out) {
+  std::string err;
+  int rc = ssb::validate_call(ca, err);
+  if (rc) return fail(rc, err);
+  const ssb200_canopy_properties &cp = *ca.cp;
+  int c1 = istartcol > 0 ? istartcol : 1;
+  int c2 = iendcol > 0 ? iendcol : cp.ncol;
+  if (c2 > cp.ncol) c2 = cp.ncol;
+  if (c1 > c2) return 0;
+  cx.stream = stream;
+  cx.first_error = cudaSuccess;
+  rc = ssb::build_plan(*ca.config, cp, c1 - 1, c2 - 1, cx.plan, err);
+  if (rc) {
+    cx.plan.valid = false;
+    return fail(rc, err);
+  }
+  if (cx.plan.generation != cx.uploaded_generation) cx.plan_uploaded = false;
+  if (!cx.plan_uploaded) {
+    rc = upload_plan(cx, cp);
+    if (rc) return rc;
+  }
+  SSB_CUDA(cx.d_status.reserve(sizeof(int)));
+  SSB_CUDA(cudaMemsetAsync(cx.d_status.p, 0, sizeof(int), stream));
+  if (cx.budget_doubles == 0) {
+    size_t free_b = 0, total_b = 0;
+    SSB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t b = (free_b + cx.d_scratch.bytes) / 2;
+    const size_t cap = (size_t)24 << 30;
+    if (b > cap) b = cap;
+    cx.budget_doubles = b / sizeof(double);
+  }
+  if (cx.profiling) {
+    if (!cx.ev0) {
+      cudaEventCreate(&cx.ev0);
+      cudaEventCreate(&cx.ev1);
+    }
+    for (double &t : cx.times_ms) t = 0.0;
+  }
+  CudaBackend be(cx);
+  ssb::Dispatcher<CudaBackend> disp(be);
+  rc = disp.run(ca, cx.plan, err);
+  if (rc) return fail(rc, err);
+  if (cx.first_error != cudaSuccess)
+    return fail(SSB200_ERR_CUDA, std::string("kernel launch / scratch allocation: ") + cudaGetErrorString(cx.first_error));
+  if (status_out)
+    SSB_CUDA(cudaMemcpyAsync(status_out, cx.d_status.p, sizeof(int), cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}
+
+// --- host-pointer staging --------------------------------------------------
+struct Stager {
+  Context &cx;
+  cudaStream_t stream;
+  int next = 0;
+  int rc = 0;
+  struct Out {
+    double *host;
+    double *dev;
+    size_t off, cnt;
+  };
+  std::vector<Out> outs;
+  Stager(Context &c, cudaStream_t s) : cx(c), stream(s) {}
+  // mirror `host[0 .. total)` on the device, copying only [off, off+cnt)
+  double *mirror(const double *host, size_t total, size_t off, size_t cnt, bool upload, bool download) {
+    if (!host || rc) return nullptr;
+    if ((size_t)next >= cx.stage.size()) cx.stage.resize((size_t)next + 16);
+    DevBuf &b = cx.stage[next++];
+    cudaError_t e = b.reserve((total > 0 ? total : 1) * sizeof(double));
+    if (e != cudaSuccess) {
+      rc = fail(SSB200_ERR_CUDA, std::string("staging allocation: ") + cudaGetErrorString(e));
+      return nullptr;
+    }
+    double *d = (double *)b.p;
+    if (upload && cnt > 0) {
+      e = cudaMemcpyAsync(d + off, host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, stream);
+      if (e != cudaSuccess) rc = fail(SSB200_ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+    }
+    if (download && cnt > 0) outs.push_back(Out{const_cast<double *>(host), d, off, cnt});
+    return d;
+  }
+  int download_all() {
+    for (const Out &o : outs) {
+      cudaError_t e = cudaMemcpyAsync(o.host + o.off, o.dev + o.off, o.cnt * sizeof(double), cudaMemcpyDeviceToHost, stream);
+      if (e != cudaSuccess) return fail(SSB200_ERR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+    }
+    return 0;
+  }
+};
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char *ssb200_version(void) { return "spartacus_surface_b200 0.1 (sm_100a, generic + sub-warp kernels)"; }
+
+const char *ssb200_last_error(void) { return g_last_error.c_str(); }
+
+int ssb200_abi_sizes(int64_t out[7]) {
+  if (!out) return fail(SSB200_ERR_ARG, "NULL argument");
+  out[0] = sizeof(ssb200_legendre_gauss);
+  out[1] = sizeof(ssb200_config);
+  out[2] = sizeof(ssb200_canopy_properties);
+  out[3] = sizeof(ssb200_sw_spectral_properties);
+  out[4] = sizeof(ssb200_lw_spectral_properties);
+  out[5] = sizeof(ssb200_canopy_flux);
+  out[6] = sizeof(ssb200_boundary_conds_out);
+  return 0;
+}
+
+int ssb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int ssb200_set_device(int device) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  SSB_CUDA(cudaSetDevice(device));
+  return 0;
+}
+
+// legendre_gauss_type%initialize (radtool/radtool_legendre_gauss.F90:52-100,119-170):
+// Newton iteration for the Legendre nodes mapped to [0,1]; host side, once per config.
+int ssb200_legendre_gauss_init(int32_t nstream, ssb200_legendre_gauss *lg) {
+  if (!lg || nstream < 1 || nstream > SSB200_MAX_NSTREAM) return fail(SSB200_ERR_ARG, "nstream outside 1..16");
+  const int n = nstream;
+  const double pi = SSB_PI, eps = SSB_EPS;
+  double y[SSB200_MAX_NSTREAM], y0[SSB200_MAX_NSTREAM], dp[SSB200_MAX_NSTREAM];
+  double P[SSB200_MAX_NSTREAM + 1][SSB200_MAX_NSTREAM];
+  const float c027 = 0.27f / (float)n;  // single-precision constant expression in the reference (:142)
+  for (int k = 1; k <= n; ++k) {
+    y[k - 1] = cos((2 * (k - 1) + 1) * pi / (2 * n)) + (double)c027 * sin(pi * (-1.0 + 2.0 * k) / (n + 1));
+    y0[k - 1] = 2.0;
+  }
+  for (;;) {
+    double md = 0.0;
+    for (int i = 0; i < n; ++i) md = fmax(md, fabs(y[i] - y0[i]));
+    if (!(md > eps)) break;
+    for (int i = 0; i < n; ++i) {
+      P[0][i] = 1.0;
+      P[1][i] = y[i];
+    }
+    for (int k = 2; k <= n; ++k)
+      for (int i = 0; i < n; ++i) P[k][i] = ((2 * k - 1) * y[i] * P[k - 1][i] - (k - 1) * P[k - 2][i]) / k;
+    for (int i = 0; i < n; ++i) dp[i] = (n + 1) * (P[n - 1][i] - y[i] * P[n][i]) / (1.0 - y[i] * y[i]);
+    for (int i = 0; i < n; ++i) {
+      y0[i] = y[i];
+      y[i] = y0[i] - P[n][i] / dp[i];
+    }
+  }
+  memset(lg, 0, sizeof(*lg));
+  lg->nstream = n;
+  double sh = 0.0, sv = 0.0, s2 = 0.0;
+  for (int i = 0; i < n; ++i) {
+    lg->mu[i] = 0.5 * (0.0 * (1.0 - y[i]) + 1.0 * (1.0 - y[i]));  // map as written in the reference (:165)
+    lg->weight[i] = (((n + 1) * (n + 1)) / (double)(n * n)) * (1.0 - 0.0) / ((1.0 - y[i] * y[i]) * dp[i] * dp[i]);
+    lg->sin_ang[i] = sqrt(1.0 - lg->mu[i] * lg->mu[i]);
+    lg->tan_ang[i] = lg->sin_ang[i] / lg->mu[i];
+    lg->hweight[i] = lg->weight[i] * lg->mu[i];
+    lg->vweight[i] = lg->weight[i] * lg->sin_ang[i];
+  }
+  for (int i = 0; i < n; ++i) {
+    sh += lg->hweight[i];
+    sv += lg->vweight[i];
+  }
+  for (int i = 0; i < n; ++i) {
+    lg->hweight[i] = lg->hweight[i] / sh;
+    lg->vweight[i] = lg->vweight[i] / sv;
+  }
+  lg->vadjustment = 1.0;
+  for (int i = 0; i < n; ++i) s2 += lg->weight[i] * lg->sin_ang[i];
+  lg->vadjustment2 = (pi / 4.0) / s2;
+  return 0;
+}
+
+int ssb200_radsurf_device(const ssb200_config *config, const ssb200_canopy_properties *canopy_props,
+                          const ssb200_sw_spectral_properties *sw, const ssb200_lw_spectral_properties *lw,
+                          ssb200_boundary_conds_out *bc_out, int32_t istartcol, int32_t iendcol,
+                          ssb200_canopy_flux *sw_norm_dir, ssb200_canopy_flux *sw_norm_diff,
+                          ssb200_canopy_flux *lw_internal, ssb200_canopy_flux *lw_norm, void *stream,
+                          int32_t *status_out) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  ssb::CallArgs ca{config, canopy_props, sw, lw, bc_out, sw_norm_dir, sw_norm_diff, lw_internal, lw_norm};
+  return radsurf_device_locked(g_ctx, ca, istartcol, iendcol, (cudaStream_t)stream, status_out);
+}
+
+int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *cp,
+                   const ssb200_sw_spectral_properties *sw, const ssb200_lw_spectral_properties *lw,
+                   ssb200_boundary_conds_out *bc, int32_t istartcol, int32_t iendcol, ssb200_canopy_flux *sw_dir,
+                   ssb200_canopy_flux *sw_diff, ssb200_canopy_flux *lw_int, ssb200_canopy_flux *lw_norm) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  Context &cx = g_ctx;
+  {
+    ssb::CallArgs probe{config, cp, sw, lw, bc, sw_dir, sw_diff, lw_int, lw_norm};
+    std::string err;
+    rc = ssb::validate_call(probe, err);
+    if (rc) return fail(rc, err);
+  }
+  if (!cx.own_stream) SSB_CUDA(cudaStreamCreateWithFlags(&cx.own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = cx.own_stream;
+  int c1 = istartcol > 0 ? istartcol : 1, c2 = iendcol > 0 ? iendcol : cp->ncol;
+  if (c2 > cp->ncol) c2 = cp->ncol;
+  if (c1 > c2) return 0;
+  const size_t ncol = (size_t)cp->ncol, ntot = (size_t)cp->ntotlay;
+  // packed layer range touched by the columns of this call; check that it is
+  // contiguous so that per-layer outputs need no upload
+  size_t l1 = ntot, l2 = 0;
+  bool contiguous = true;
+  size_t expect = 0;
+  bool first = true;
+  for (int j = c1 - 1; j < c2; ++j) {
+    if (cp->i_representation[j] == SSB200_TILE_FLAT || cp->nlay[j] <= 0) continue;
+    const size_t s = (size_t)cp->istartlay[j] - 1, e = s + (size_t)cp->nlay[j];
+    if (cp->istartlay[j] < 1 || e > ntot) return fail(SSB200_ERR_SHAPE, "layer range outside 1..ntotlay");
+    if (!first && s != expect) contiguous = false;
+    first = false;
+    expect = e;
+    if (s < l1) l1 = s;
+    if (e > l2) l2 = e;
+  }
+  if (l2 < l1) l1 = l2 = 0;
+  const size_t cO = (size_t)(c1 - 1), cN = (size_t)(c2 - c1 + 1), lN = l2 - l1;
+  Stager sg(cx, st);
+  ssb200_canopy_properties dcp = *cp;
+  auto lay1 = [&](const double *h) { return (const double *)sg.mirror(h, ntot, l1, lN, true, false); };
+  dcp.cos_sza = sg.mirror(cp->cos_sza, ncol, cO, cN, true, false);
+  dcp.dz = lay1(cp->dz);
+  dcp.building_fraction = lay1(cp->building_fraction);
+  dcp.building_scale = lay1(cp->building_scale);
+  dcp.veg_fraction = lay1(cp->veg_fraction);
+  dcp.veg_scale = lay1(cp->veg_scale);
+  dcp.veg_ext = lay1(cp->veg_ext);
+  dcp.veg_fsd = lay1(cp->veg_fsd);
+  dcp.veg_contact_fraction = lay1(cp->veg_contact_fraction);
+  ssb200_sw_spectral_properties dsw;
+  ssb200_lw_spectral_properties dlw;
+  memset(&dsw, 0, sizeof(dsw));
+  memset(&dlw, 0, sizeof(dlw));
+  if (config->do_sw) {
+    const size_t g = (size_t)config->nsw;
+    auto L = [&](const double *h) { return (const double *)sg.mirror(h, ntot * g, l1 * g, lN * g, true, false); };
+    auto Cc = [&](const double *h) { return (const double *)sg.mirror(h, ncol * g, cO * g, cN * g, true, false); };
+    dsw.nspec = sw->nspec;
+    dsw.air_ext = L(sw->air_ext);
+    dsw.air_ssa = L(sw->air_ssa);
+    dsw.veg_ssa = L(sw->veg_ssa);
+    dsw.ground_albedo = Cc(sw->ground_albedo);
+    dsw.roof_albedo = L(sw->roof_albedo);
+    dsw.wall_albedo = L(sw->wall_albedo);
+    dsw.wall_specular_frac = L(sw->wall_specular_frac);
+    dsw.ground_albedo_dir = Cc(sw->ground_albedo_dir);
+    dsw.roof_albedo_dir = L(sw->roof_albedo_dir);
+  }
+  if (config->do_lw) {
+    const size_t g = (size_t)config->nlw;
+    auto L = [&](const double *h) { return (const double *)sg.mirror(h, ntot * g, l1 * g, lN * g, true, false); };
+    auto Cc = [&](const double *h) { return (const double *)sg.mirror(h, ncol * g, cO * g, cN * g, true, false); };
+    dlw.nspec = lw->nspec;
+    dlw.air_ext = L(lw->air_ext);
+    dlw.air_ssa = L(lw->air_ssa);
+    dlw.clear_air_planck = L(lw->clear_air_planck);
+    dlw.veg_ssa = L(lw->veg_ssa);
+    dlw.veg_planck = L(lw->veg_planck);
+    dlw.veg_air_planck = L(lw->veg_air_planck);
+    dlw.ground_emissivity = Cc(lw->ground_emissivity);
+    dlw.ground_emission = Cc(lw->ground_emission);
+    dlw.roof_emissivity = L(lw->roof_emissivity);
+    dlw.wall_emissivity = L(lw->wall_emissivity);
+    dlw.roof_emission = L(lw->roof_emission);
+    dlw.wall_emission = L(lw->wall_emission);
+  }
+  // outputs: per-column members are uploaded first (Flat tiles and night-time
+  // columns leave some of them untouched); per-layer members are fully
+  // rewritten by the kernels when the layer range is contiguous
+  ssb200_boundary_conds_out dbc;
+  memset(&dbc, 0, sizeof(dbc));
+  {
+    const size_t gs = (size_t)config->nsw, gl = (size_t)config->nlw;
+    if (config->do_sw) {
+      dbc.sw_albedo = sg.mirror(bc->sw_albedo, ncol * gs, cO * gs, cN * gs, true, true);
+      dbc.sw_albedo_dir = sg.mirror(bc->sw_albedo_dir, ncol * gs, cO * gs, cN * gs, true, true);
+    }
+    if (config->do_lw) {
+      dbc.lw_emissivity = sg.mirror(bc->lw_emissivity, ncol * gl, cO * gl, cN * gl, true, true);
+      dbc.lw_emission = sg.mirror(bc->lw_emission, ncol * gl, cO * gl, cN * gl, true, true);
+    }
+  }
+  auto stage_flux = [&](const ssb200_canopy_flux *h, ssb200_canopy_flux &d) {
+    d = *h;
+    const size_t g = (size_t)h->nspec;
+    auto Cc = [&](double *p) { return sg.mirror(p, ncol * g, cO * g, cN * g, true, true); };
+    auto L = [&](double *p) { return sg.mirror(p, ntot * g, l1 * g, lN * g, !contiguous, true); };
+    auto C1 = [&](double *p) { return sg.mirror(p, ncol, cO, cN, true, true); };
+    auto L1 = [&](double *p) { return sg.mirror(p, ntot, l1, lN, !contiguous, true); };
+    d.ground_dn = Cc(h->ground_dn);
+    d.ground_net = Cc(h->ground_net);
+    d.ground_vertical_diff = Cc(h->ground_vertical_diff);
+    d.top_dn = Cc(h->top_dn);
+    d.top_net = Cc(h->top_net);
+    d.ground_dn_dir = Cc(h->ground_dn_dir);
+    d.top_dn_dir = Cc(h->top_dn_dir);
+    d.ground_sunlit_frac = C1(h->ground_sunlit_frac);
+    d.roof_in = L(h->roof_in);
+    d.roof_net = L(h->roof_net);
+    d.wall_in = L(h->wall_in);
+    d.wall_net = L(h->wall_net);
+    d.roof_in_dir = L(h->roof_in_dir);
+    d.wall_in_dir = L(h->wall_in_dir);
+    d.roof_sunlit_frac = L1(h->roof_sunlit_frac);
+    d.wall_sunlit_frac = L1(h->wall_sunlit_frac);
+    d.clear_air_abs = L(h->clear_air_abs);
+    d.veg_abs = L(h->veg_abs);
+    d.veg_air_abs = L(h->veg_air_abs);
+    d.veg_abs_dir = L(h->veg_abs_dir);
+    d.veg_sunlit_frac = L1(h->veg_sunlit_frac);
+    d.flux_dn_layer_top = L(h->flux_dn_layer_top);
+    d.flux_up_layer_top = L(h->flux_up_layer_top);
+    d.flux_dn_layer_base = L(h->flux_dn_layer_base);
+    d.flux_up_layer_base = L(h->flux_up_layer_base);
+    d.flux_dn_dir_layer_top = L(h->flux_dn_dir_layer_top);
+    d.flux_dn_dir_layer_base = L(h->flux_dn_dir_layer_base);
+  };
+  ssb200_canopy_flux d1, d2, d3, d4;
+  if (config->do_sw) {
+    stage_flux(sw_dir, d1);
+    stage_flux(sw_diff, d2);
+  }
+  if (config->do_lw) {
+    stage_flux(lw_int, d3);
+    stage_flux(lw_norm, d4);
+  }
+  if (sg.rc) return sg.rc;
+  ssb::CallArgs ca{config, &dcp, config->do_sw ? &dsw : nullptr, config->do_lw ? &dlw : nullptr, &dbc,
+                   config->do_sw ? &d1 : nullptr, config->do_sw ? &d2 : nullptr,
+                   config->do_lw ? &d3 : nullptr, config->do_lw ? &d4 : nullptr};
+  rc = radsurf_device_locked(cx, ca, c1, c2, st, nullptr);
+  if (rc) return rc;
+  rc = sg.download_all();
+  if (rc) return rc;
+  int status = 0;
+  SSB_CUDA(cudaMemcpyAsync(&status, cx.d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SSB_CUDA(cudaStreamSynchronize(st));
+  return status;
+}
+
+int64_t ssb200_kernel_launch_count(void) { return (int64_t)g_launches; }
+
+int ssb200_set_profiling(int enable) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  g_ctx.profiling = enable != 0;
+  return 0;
+}
+
+int ssb200_last_kernel_times_ms(double out[5]) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  for (int i = 0; i < 5; ++i) out[i] = g_ctx.times_ms[i];
+  return 0;
+}
+
+int ssb200_set_option(const char *name, int64_t value) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  const std::string n(name ? name : "");
+  if (n == "scratch_budget_bytes") {
+    g_ctx.budget_doubles = (size_t)value / sizeof(double);
+    return 0;
+  }
+  if (n == "fast_kernels") {
+    g_ctx.fast_mode = value != 0;
+    return 0;
+  }
+  return fail(SSB200_ERR_ARG, "unknown option " + n);
+}
+
+int ssb200_release(void) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  Context &cx = g_ctx;
+  if (ssb200_device_count() > 0) {
+    cudaDeviceSynchronize();
+    for (DevBuf *b : {&cx.d_nlay, &cx.d_istart, &cx.d_irep, &cx.d_cols, &cx.d_scratch, &cx.d_status, &cx.d_lay2col})
+      b->release();
+    for (DevBuf &b : cx.stage) b.release();
+  }
+  cx.plan = ssb::Plan();
+  cx.plan_uploaded = false;
+  cx.budget_doubles = 0;
+  return 0;
+}
+
+static int collect_fields(ssb200_canopy_flux *o, const ssb200_canopy_flux *a, const ssb200_canopy_flux *b,
+                          FieldList &fl, bool with_sunlit) {
+  fl.n = 0;
+  auto add = [&](double *p, const double *pa, const double *pb, int per_layer, int spectral) {
+    if (!p) return;
+    if (a && (!pa || !pb)) return;
+    fl.p[fl.n] = p;
+    fl.a[fl.n] = pa;
+    fl.b[fl.n] = pb;
+    fl.per_layer[fl.n] = per_layer;
+    fl.spectral[fl.n] = spectral;
+    ++fl.n;
+  };
+#define F(m, pl, sp) add(o->m, a ? a->m : nullptr, b ? b->m : nullptr, pl, sp)
+  F(ground_dn, 0, 1);
+  F(ground_net, 0, 1);
+  F(ground_vertical_diff, 0, 1);
+  F(top_dn, 0, 1);
+  F(top_net, 0, 1);
+  F(ground_dn_dir, 0, 1);
+  F(top_dn_dir, 0, 1);
+  F(roof_in, 1, 1);
+  F(roof_net, 1, 1);
+  F(wall_in, 1, 1);
+  F(wall_net, 1, 1);
+  F(roof_in_dir, 1, 1);
+  F(wall_in_dir, 1, 1);
+  F(clear_air_abs, 1, 1);
+  F(veg_abs, 1, 1);
+  F(veg_air_abs, 1, 1);
+  F(veg_abs_dir, 1, 1);
+  F(flux_dn_layer_top, 1, 1);
+  F(flux_up_layer_top, 1, 1);
+  F(flux_dn_layer_base, 1, 1);
+  F(flux_up_layer_base, 1, 1);
+  F(flux_dn_dir_layer_top, 1, 1);
+  F(flux_dn_dir_layer_base, 1, 1);
+  if (with_sunlit) {
+    F(ground_sunlit_frac, 0, 0);
+    F(roof_sunlit_frac, 1, 0);
+    F(wall_sunlit_frac, 1, 0);
+    F(veg_sunlit_frac, 1, 0);
+  }
+#undef F
+  return fl.n;
+}
+
+int ssb200_canopy_flux_scale_device(ssb200_canopy_flux *flux, const int32_t *nlay, const int32_t *istartlay,
+                                    const double *factor, void *stream) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  if (!flux || !nlay || !istartlay || !factor) return fail(SSB200_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(g_mutex);
+  Context &cx = g_ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int> lay2col((size_t)flux->ntotlay, 0);
+  for (int j = 0; j < flux->ncol; ++j)
+    for (int l = 0; l < nlay[j]; ++l) {
+      const long il = (long)istartlay[j] - 1 + l;
+      if (il < 0 || il >= flux->ntotlay) return fail(SSB200_ERR_SHAPE, "layer range outside 1..ntotlay");
+      lay2col[(size_t)il] = j;
+    }
+  SSB_CUDA(cx.d_lay2col.reserve(sizeof(int) * (lay2col.size() + 1)));
+  SSB_CUDA(cudaMemcpyAsync(cx.d_lay2col.p, lay2col.data(), sizeof(int) * lay2col.size(), cudaMemcpyHostToDevice, st));
+  SSB_CUDA(cudaStreamSynchronize(st));
+  FieldList fl;
+  collect_fields(flux, nullptr, nullptr, fl, false);
+  const long nmax = (long)(flux->ntotlay > flux->ncol ? flux->ntotlay : flux->ncol) * flux->nspec;
+  if (nmax > 0) {
+    k_scale<<<(unsigned)((nmax + 255) / 256), 256, 0, st>>>(fl, factor, (const int *)cx.d_lay2col.p, flux->nspec,
+                                                            flux->ncol, flux->ntotlay);
+    ++g_launches;
+    SSB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int ssb200_canopy_flux_sum_device(ssb200_canopy_flux *out, const ssb200_canopy_flux *a, const ssb200_canopy_flux *b,
+                                  void *stream) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  if (!out || !a || !b) return fail(SSB200_ERR_ARG, "NULL argument");
+  FieldList fl;
+  collect_fields(out, a, b, fl, true);
+  const long nmax = (long)(out->ntotlay > out->ncol ? out->ntotlay : out->ncol) * out->nspec;
+  if (nmax > 0) {
+    k_sum<<<(unsigned)((nmax + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fl, out->nspec, out->ncol, out->ntotlay);
+    ++g_launches;
+    SSB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int ssb200_canopy_flux_check_device(const ssb200_canopy_flux *flux, const ssb200_canopy_properties *cp,
+                                    double *residual, void *stream) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  if (!flux || !cp || !residual) return fail(SSB200_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(g_mutex);
+  Context &cx = g_ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ncol = (size_t)cp->ncol;
+  SSB_CUDA(cx.d_nlay.reserve(sizeof(int) * (ncol + 1)));
+  SSB_CUDA(cx.d_istart.reserve(sizeof(int) * (ncol + 1)));
+  SSB_CUDA(cx.d_irep.reserve(sizeof(int) * (ncol + 1)));
+  SSB_CUDA(cudaMemcpyAsync(cx.d_nlay.p, cp->nlay, sizeof(int) * ncol, cudaMemcpyHostToDevice, st));
+  SSB_CUDA(cudaMemcpyAsync(cx.d_istart.p, cp->istartlay, sizeof(int) * ncol, cudaMemcpyHostToDevice, st));
+  SSB_CUDA(cudaMemcpyAsync(cx.d_irep.p, cp->i_representation, sizeof(int) * ncol, cudaMemcpyHostToDevice, st));
+  SSB_CUDA(cudaStreamSynchronize(st));
+  cx.plan_uploaded = false;  // the index buffers were overwritten
+  cx.plan.valid = false;
+  if (ncol > 0) {
+    k_check<<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(*flux, (const int *)cx.d_nlay.p, (const int *)cx.d_istart.p,
+                                                            (const int *)cx.d_irep.p, (int)ncol, residual);
+    ++g_launches;
+    SSB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+double ssb200_measure_fp64_peak_tflops(int iters) {
+  if (ensure_device()) return -1.0;
+  if (iters <= 0) iters = 1 << 16;
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1.0;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  double *out = nullptr;
+  if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    k_fp64_peak<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  ++g_launches;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess) return -1.0;
+  return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+// ssb_driver.hpp - host-side launch plan of one radsurf call.
+//
+// Replaces the column loop + `select case` of radsurf
+// (radsurf/radsurf_interface.F90:105-313): columns are bucketed by solver
+// class (forest/urban x number of regions) so that every launch runs one
+// uniform kernel; Flat and single-layer urban tiles go to the surface kernel.
+// Within a class the columns are processed in chunks sized to the scratch
+// budget.  The orchestration is a template over a `Backend` (CUDA in
+// ssb_api.cu; a serial host loop in tests/hostcheck) so the same plan code is
+// exercised by CPU tests.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ssb_solver.cuh"
+
+namespace ssb {
+
+struct ColumnClass {
+  int urban, nreg;
+  std::vector<int> cols;
+};
+
+struct Plan {
+  // host copies used to detect a change of the column description between calls
+  std::vector<int> nlay, istartlay, irep;
+  int c1 = 0, c2 = -1;  // 0-based inclusive range
+  int nveg_forest = -1, nveg_urban = -1;
+  std::vector<ColumnClass> classes;
+  std::vector<int> surface_cols;
+  std::vector<int> all_cols;  // concatenation uploaded to the device
+  bool valid = false;
+  long generation = 0;  // bumped on every rebuild (device copies are refreshed when it changes)
+};
+
+inline int stream_capacity(int ns) {
+  if (ns <= 1) return 1;
+  if (ns <= 2) return 2;
+  if (ns <= 4) return 4;
+  if (ns <= 8) return 8;
+  return 0;
+}
+
+inline LgTable make_lg(const ssb200_legendre_gauss &s) {
+  LgTable t;
+  std::memset(&t, 0, sizeof(t));
+  t.ns = s.nstream;
+  for (int i = 0; i < SSB200_MAX_NSTREAM; ++i) {
+    t.mu[i] = s.mu[i];
+    t.tan_ang[i] = s.tan_ang[i];
+    t.weight[i] = s.weight[i];
+    t.hweight[i] = s.hweight[i];
+    t.vweight[i] = s.vweight[i];
+  }
+  t.vadjustment = s.vadjustment;
+  t.vadjustment2 = s.vadjustment2;
+  return t;
+}
+
+// Returns 0 or a negative SSB200_ERR_* code; `err` receives the message.
+inline int build_plan(const ssb200_config &cfg, const ssb200_canopy_properties &cp, int c1, int c2, Plan &plan,
+                      std::string &err) {
+  const int ncol = cp.ncol;
+  const bool same = plan.valid && plan.c1 == c1 && plan.c2 == c2 && (int)plan.nlay.size() == ncol &&
+                    plan.nveg_forest == cfg.n_vegetation_region_forest &&
+                    plan.nveg_urban == cfg.n_vegetation_region_urban &&
+                    std::memcmp(plan.nlay.data(), cp.nlay, sizeof(int) * ncol) == 0 &&
+                    std::memcmp(plan.istartlay.data(), cp.istartlay, sizeof(int) * ncol) == 0 &&
+                    std::memcmp(plan.irep.data(), cp.i_representation, sizeof(int) * ncol) == 0;
+  if (same) return 0;
+  const long generation = plan.generation + 1;
+  plan = Plan();
+  plan.generation = generation;
+  plan.nlay.assign(cp.nlay, cp.nlay + ncol);
+  plan.istartlay.assign(cp.istartlay, cp.istartlay + ncol);
+  plan.irep.assign(cp.i_representation, cp.i_representation + ncol);
+  plan.c1 = c1;
+  plan.c2 = c2;
+  plan.nveg_forest = cfg.n_vegetation_region_forest;
+  plan.nveg_urban = cfg.n_vegetation_region_urban;
+  auto class_of = [&](int urban, int nreg) -> ColumnClass & {
+    for (auto &k : plan.classes)
+      if (k.urban == urban && k.nreg == nreg) return k;
+    plan.classes.push_back(ColumnClass{urban, nreg, {}});
+    return plan.classes.back();
+  };
+  for (int j = c1; j <= c2; ++j) {
+    const int irep = cp.i_representation[j];
+    const int nl = cp.nlay[j];
+    if (irep != SSB200_TILE_FLAT) {
+      if (nl < 0 || cp.istartlay[j] < 1 || cp.istartlay[j] - 1 + nl > cp.ntotlay) {
+        err = "column " + std::to_string(j + 1) + ": layer range outside 1..ntotlay";
+        return SSB200_ERR_SHAPE;
+      }
+    }
+    switch (irep) {
+      case SSB200_TILE_FLAT:
+        plan.surface_cols.push_back(j);
+        break;
+      case SSB200_TILE_FOREST:
+        class_of(0, cfg.n_vegetation_region_forest + 1).cols.push_back(j);
+        break;
+      case SSB200_TILE_URBAN:
+        class_of(1, 1).cols.push_back(j);
+        break;
+      case SSB200_TILE_VEGETATED_URBAN:
+        class_of(1, cfg.n_vegetation_region_urban + 1).cols.push_back(j);
+        break;
+      case SSB200_TILE_SIMPLE_URBAN:
+      case SSB200_TILE_INFINITE_STREET:
+        if (nl > 1) {
+          err = "Attempt to use simple urban representation with more than one layer";
+          return SSB200_ERR_SIMPLE_URBAN_LAYERS;
+        }
+        plan.surface_cols.push_back(j);
+        break;
+      default:
+        break;  // unknown codes are skipped like the reference's select case
+    }
+  }
+  for (auto &k : plan.classes) {
+    if (k.nreg < 1 || k.nreg > SSB200_MAX_NREG) {
+      err = "number of regions outside 1..3";
+      return SSB200_ERR_UNSUPPORTED;
+    }
+    if (k.nreg > 1 && !cfg.do_vegetation) {
+      err = "Attempt to perform radiative transfer with more than one region when vegetation not enabled";
+      return SSB200_ERR_ARG;
+    }
+  }
+  for (auto &k : plan.classes) plan.all_cols.insert(plan.all_cols.end(), k.cols.begin(), k.cols.end());
+  plan.all_cols.insert(plan.all_cols.end(), plan.surface_cols.begin(), plan.surface_cols.end());
+  plan.valid = true;
+  return 0;
+}
+
+struct CallArgs {
+  const ssb200_config *config;
+  const ssb200_canopy_properties *cp;  // index arrays on host, doubles on device
+  const ssb200_sw_spectral_properties *sw;
+  const ssb200_lw_spectral_properties *lw;
+  ssb200_boundary_conds_out *bc;
+  ssb200_canopy_flux *sw_dir, *sw_diff, *lw_int, *lw_norm;
+};
+
+// Backend concept:
+//   const int *dev_cols(const Plan&, size_t offset)  device copy of plan.all_cols (+offset)
+//   const int *dev_nlay(), *dev_istartlay(), *dev_irep()
+//   double *scratch(size_t doubles)                  grow-only scratch
+//   size_t scratch_budget_doubles()
+//   int *dev_status()
+//   template<int NS> void layer_sw/layer_lw(const ClassArgs&, long nthreads)
+//   template<int NS> void sweeps_sw/sweeps_lw(const ClassArgs&, long nthreads)
+//   void surface(const SurfaceArgs&, int nsw_threads, int nlw_threads)
+template <class Backend>
+struct Dispatcher {
+  Backend &be;
+  explicit Dispatcher(Backend &b) : be(b) {}
+
+  template <int NS>
+  void run_class(ClassArgs a, bool lw, const Plan &plan, const ColumnClass &k, size_t col_offset) {
+    const SolveCfg &c = a.cfg;
+    const int n = c.nreg * c.ns, d = c.nreg, nrb = c.urban ? c.nreg + 1 : c.nreg, m = nrb * c.ns;
+    const size_t el = lw ? lw_layer_elems(n, c.nreg) : sw_layer_elems(n, d);
+    const size_t es = lw ? lw_sweep_elems(n, m, c.nreg, nrb) : sw_sweep_elems(n, d, m, nrb, c.nreg, nrb);
+    const size_t budget = be.scratch_budget_doubles();
+    size_t pos = 0;
+    const size_t ntot = k.cols.size();
+    while (pos < ntot) {
+      // grow the chunk while its scratch (sized by the tallest column) fits the budget
+      int lmax = 0;
+      size_t cnt = 0;
+      while (pos + cnt < ntot) {
+        const int nl = plan.nlay[k.cols[pos + cnt]];
+        const int lm = std::max(lmax, nl);
+        const size_t need = (el * (size_t)lm + es * (size_t)(lm + 1)) * (cnt + 1) * (size_t)c.nspec;
+        if (need > budget && cnt > 0) break;
+        lmax = lm;
+        ++cnt;
+      }
+      a.ncols = (int)cnt;
+      a.lmax = lmax;
+      a.cols = be.dev_cols(plan, col_offset + pos);
+      const size_t width = cnt * (size_t)c.nspec;
+      double *s = be.scratch((el * (size_t)lmax + es * (size_t)(lmax + 1)) * width);
+      a.layer = s;
+      a.sweep = s + el * (size_t)lmax * width;
+      if (lmax > 0) {
+        if (lw)
+          be.template layer_lw<NS>(a, (long)width * lmax);
+        else
+          be.template layer_sw<NS>(a, (long)width * lmax);
+      }
+      if (lw)
+        be.template sweeps_lw<NS>(a, (long)width);
+      else
+        be.template sweeps_sw<NS>(a, (long)width);
+      pos += cnt;
+    }
+  }
+
+  int run(const CallArgs &ca, const Plan &plan, std::string &err) {
+    const ssb200_config &cfg = *ca.config;
+    size_t col_offset = 0;
+    for (const ColumnClass &k : plan.classes) {
+      for (int pass = 0; pass < 2; ++pass) {
+        const bool lw = (pass == 1);
+        if (lw ? !cfg.do_lw : !cfg.do_sw) continue;
+        const ssb200_legendre_gauss &lgs =
+            lw ? (k.urban ? cfg.lg_lw_urban : cfg.lg_lw_forest) : (k.urban ? cfg.lg_sw_urban : cfg.lg_sw_forest);
+        const int cap = stream_capacity(lgs.nstream);
+        if (lgs.nstream < 1 || cap == 0) {
+          err = "number of streams outside 1..8";
+          return SSB200_ERR_UNSUPPORTED;
+        }
+        ClassArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.cfg.urban = k.urban;
+        a.cfg.lw = lw ? 1 : 0;
+        a.cfg.nreg = k.nreg;
+        a.cfg.ns = lgs.nstream;
+        a.cfg.nspec = lw ? cfg.nlw : cfg.nsw;
+        a.cfg.symmetric_scale =
+            k.urban ? cfg.use_symmetric_vegetation_scale_urban : cfg.use_symmetric_vegetation_scale_forest;
+        a.cfg.isolation = k.urban ? cfg.vegetation_isolation_factor_urban : cfg.vegetation_isolation_factor_forest;
+        a.cfg.min_veg = cfg.min_vegetation_fraction;
+        a.cfg.min_bld = cfg.min_building_fraction;
+        a.lg = make_lg(lgs);
+        a.nlay = be.dev_nlay();
+        a.istartlay = be.dev_istartlay();
+        a.cp = *ca.cp;
+        if (lw) {
+          a.lw = *ca.lw;
+          a.f1 = *ca.lw_int;
+          a.f2 = *ca.lw_norm;
+        } else {
+          a.sw = *ca.sw;
+          a.f1 = *ca.sw_dir;
+          a.f2 = *ca.sw_diff;
+        }
+        a.use_sw_direct_albedo = cfg.use_sw_direct_albedo;
+        a.bc = *ca.bc;
+        a.status = be.dev_status();
+        switch (cap) {
+          case 1: run_class<1>(a, lw, plan, k, col_offset); break;
+          case 2: run_class<2>(a, lw, plan, k, col_offset); break;
+          case 4: run_class<4>(a, lw, plan, k, col_offset); break;
+          default: run_class<8>(a, lw, plan, k, col_offset); break;
+        }
+      }
+      col_offset += k.cols.size();
+    }
+    if (!plan.surface_cols.empty()) {
+      SurfaceArgs s;
+      std::memset(&s, 0, sizeof(s));
+      s.ncols = (int)plan.surface_cols.size();
+      s.nsw = cfg.nsw;
+      s.nlw = cfg.nlw;
+      s.do_sw = cfg.do_sw;
+      s.do_lw = cfg.do_lw;
+      s.use_sw_direct_albedo = cfg.use_sw_direct_albedo;
+      s.min_veg = cfg.min_vegetation_fraction;
+      s.min_bld = cfg.min_building_fraction;
+      s.cols = be.dev_cols(plan, col_offset);
+      s.nlay = be.dev_nlay();
+      s.istartlay = be.dev_istartlay();
+      s.irep = be.dev_irep();
+      s.cp = *ca.cp;
+      if (cfg.do_sw) {
+        s.sw = *ca.sw;
+        s.sw_dir = *ca.sw_dir;
+        s.sw_diff = *ca.sw_diff;
+      }
+      if (cfg.do_lw) {
+        s.lw = *ca.lw;
+        s.lw_int = *ca.lw_int;
+        s.lw_norm = *ca.lw_norm;
+      }
+      s.bc = *ca.bc;
+      be.surface(s, cfg.do_sw ? s.ncols * cfg.nsw : 0, cfg.do_lw ? s.ncols * cfg.nlw : 0);
+    }
+    return 0;
+  }
+};
+
+// Argument checks shared by both entry points; returns 0 or SSB200_ERR_*.
+inline int validate_call(const CallArgs &ca, std::string &err) {
+  if (!ca.config || !ca.cp || !ca.bc) {
+    err = "config, canopy_props and bc_out must not be NULL";
+    return SSB200_ERR_ARG;
+  }
+  const ssb200_config &cfg = *ca.config;
+  const ssb200_canopy_properties &cp = *ca.cp;
+  if (cp.ncol < 0 || !cp.nlay || !cp.istartlay || !cp.i_representation) {
+    err = "canopy_props: nlay/istartlay/i_representation missing";
+    return SSB200_ERR_ARG;
+  }
+  if (cfg.do_sw) {
+    if (!ca.sw || !ca.sw_dir || !ca.sw_diff || !cp.cos_sza || !ca.bc->sw_albedo || !ca.bc->sw_albedo_dir) {
+      err = "do_sw requires sw_spectral_props, cos_sza, sw_norm_dir, sw_norm_diff and bc_out%sw_albedo*";
+      return SSB200_ERR_ARG;
+    }
+    if (ca.sw->nspec != cfg.nsw || ca.sw_dir->nspec != cfg.nsw || ca.sw_diff->nspec != cfg.nsw) {
+      err = "shortwave spectral resolution mismatch (config%nsw vs arrays)";
+      return SSB200_ERR_SHAPE;
+    }
+    if (cfg.use_sw_direct_albedo && !ca.sw->ground_albedo_dir) {
+      err = "use_sw_direct_albedo set but ground_albedo_dir not allocated";
+      return SSB200_ERR_ARG;
+    }
+  }
+  if (cfg.do_lw) {
+    if (!ca.lw || !ca.lw_int || !ca.lw_norm || !ca.bc->lw_emissivity || !ca.bc->lw_emission) {
+      err = "do_lw requires lw_spectral_props, lw_internal, lw_norm and bc_out%lw_*";
+      return SSB200_ERR_ARG;
+    }
+    if (ca.lw->nspec != cfg.nlw || ca.lw_int->nspec != cfg.nlw || ca.lw_norm->nspec != cfg.nlw) {
+      err = "longwave spectral resolution mismatch (config%nlw vs arrays)";
+      return SSB200_ERR_SHAPE;
+    }
+  }
+  return 0;
+}
+
+}  // namespace ssb

@@ -1,0 +1,86 @@
+// hostcheck.cpp - TEST INFRASTRUCTURE: compiles the product's solver bodies
+// (spartacus_surface_b200/csrc/*.cuh, the same code the CUDA kernels wrap) for
+// the host and runs them with a serial loop over "threads".  It lets the CPU
+// test-suite check the kernels' arithmetic, scratch indexing and launch plan
+// against the oracle without a GPU.  It is NOT a product path: nothing in the
+// package loads it, and the library itself has no CPU fallback.
+#include <vector>
+
+#include "../../spartacus_surface_b200/csrc/ssb_driver.hpp"
+
+namespace {
+
+struct HostBackend {
+  const ssb::Plan *plan = nullptr;
+  std::vector<double> buf;
+  int status = 0;
+  size_t budget = (size_t)1 << 22;  // small on purpose: exercises the chunk loop
+  const int *dev_cols(const ssb::Plan &p, size_t off) { return p.all_cols.data() + off; }
+  const int *dev_nlay() { return plan->nlay.data(); }
+  const int *dev_istartlay() { return plan->istartlay.data(); }
+  const int *dev_irep() { return plan->irep.data(); }
+  double *scratch(size_t n) {
+    if (buf.size() < n) buf.resize(n);
+    // poison so that reads of never-written scratch show up as NaN
+    for (size_t i = 0; i < n; ++i) buf[i] = __builtin_nan("");
+    return buf.data();
+  }
+  size_t scratch_budget_doubles() { return budget; }
+  int *dev_status() { return &status; }
+  template <int NS>
+  void layer_sw(const ssb::ClassArgs &a, long nt) {
+    const long width = (long)a.ncols * a.cfg.nspec;
+    for (long t = 0; t < nt; ++t) ssb::layer_problem_sw<NS>(a, (int)(t % width), (int)(t / width));
+  }
+  template <int NS>
+  void layer_lw(const ssb::ClassArgs &a, long nt) {
+    const long width = (long)a.ncols * a.cfg.nspec;
+    for (long t = 0; t < nt; ++t) ssb::layer_problem_lw<NS>(a, (int)(t % width), (int)(t / width));
+  }
+  template <int NS>
+  void sweeps_sw(const ssb::ClassArgs &a, long nt) {
+    for (long t = 0; t < nt; ++t) ssb::column_sweeps_sw<NS>(a, (int)t);
+  }
+  template <int NS>
+  void sweeps_lw(const ssb::ClassArgs &a, long nt) {
+    for (long t = 0; t < nt; ++t) ssb::column_sweeps_lw<NS>(a, (int)t);
+  }
+  void surface(const ssb::SurfaceArgs &s, int nsw_threads, int nlw_threads) {
+    for (int t = 0; t < nsw_threads; ++t) ssb::surface_column_sw(s, t / s.nsw, t % s.nsw);
+    for (int t = 0; t < nlw_threads; ++t) ssb::surface_column_lw(s, t / s.nlw, t % s.nlw);
+  }
+};
+
+}  // namespace
+
+extern "C" int hostcheck_radsurf(const ssb200_config *config, const ssb200_canopy_properties *cp,
+                                 const ssb200_sw_spectral_properties *sw, const ssb200_lw_spectral_properties *lw,
+                                 ssb200_boundary_conds_out *bc, int32_t istartcol, int32_t iendcol,
+                                 ssb200_canopy_flux *sw_dir, ssb200_canopy_flux *sw_diff,
+                                 ssb200_canopy_flux *lw_int, ssb200_canopy_flux *lw_norm, int64_t budget_doubles) {
+  ssb::CallArgs ca{config, cp, sw, lw, bc, sw_dir, sw_diff, lw_int, lw_norm};
+  std::string err;
+  int rc = ssb::validate_call(ca, err);
+  if (rc) {
+    std::fprintf(stderr, "hostcheck: %s\n", err.c_str());
+    return rc;
+  }
+  int c1 = istartcol > 0 ? istartcol : 1, c2 = iendcol > 0 ? iendcol : cp->ncol;
+  if (c2 > cp->ncol) c2 = cp->ncol;
+  ssb::Plan plan;
+  rc = ssb::build_plan(*config, *cp, c1 - 1, c2 - 1, plan, err);
+  if (rc) {
+    std::fprintf(stderr, "hostcheck: %s\n", err.c_str());
+    return rc;
+  }
+  HostBackend be;
+  be.plan = &plan;
+  if (budget_doubles > 0) be.budget = (size_t)budget_doubles;
+  ssb::Dispatcher<HostBackend> disp(be);
+  rc = disp.run(ca, plan, err);
+  if (rc) {
+    std::fprintf(stderr, "hostcheck: %s\n", err.c_str());
+    return rc;
+  }
+  return be.status;
+}

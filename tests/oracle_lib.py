@@ -12,19 +12,21 @@ from spartacus_surface_b200.radsurf_interface import marshal, call_radsurf
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
-_lib = None
+ORACLE_NOFMA_SO = os.path.join(ROOT, "oracle", "_build", "liboracle_nofma.so")
+_libs = {}
 
 
 def build():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
 
 
-def load():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(ORACLE_SO):
+def load(nofma=False):
+    """nofma=True: the build without FMA contraction (rounding-sensitivity probe)."""
+    path = ORACLE_NOFMA_SO if nofma else ORACLE_SO
+    if path not in _libs:
+        if not os.path.exists(path):
             build()
-        lib = C.CDLL(ORACLE_SO)
+        lib = C.CDLL(path)
         P = C.POINTER
         lib.oracle_legendre_gauss_init.argtypes = [C.c_int32, P(_abi.LegendreGauss)]
         lib.oracle_radsurf.argtypes = [P(_abi.Config), P(_abi.CanopyProperties), P(_abi.SwSpectralProperties),
@@ -36,20 +38,20 @@ def load():
         lib.oracle_calc_matrices_sw_eig.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_double] + [dp] * 12
         lib.oracle_calc_matrices_lw_eig.argtypes = [C.c_int32, C.c_double] + [dp] * 8
         lib.oracle_schur_invert_sw.argtypes = [C.c_int32, C.c_int32] + [dp] * 8
-        _lib = lib
-    return _lib
+        _libs[path] = lib
+    return _libs[path]
 
 
 def legendre_gauss_init(nstream, lg_ref):
     return load().oracle_legendre_gauss_init(nstream, lg_ref)
 
 
-def make_solver(nthreads=0, nblocksize=16):
+def make_solver(nthreads=0, nblocksize=16, nofma=False):
     """radsurf-compatible callable backed by the oracle."""
     def solver(config, canopy_props, sw, lw, bc_out, istartcol=None, iendcol=None,
                sw_norm_dir=None, sw_norm_diff=None, lw_internal=None, lw_norm=None):
         structs = marshal(config, canopy_props, sw, lw, bc_out, sw_norm_dir, sw_norm_diff, lw_internal, lw_norm)
-        rc = call_radsurf(load().oracle_radsurf, structs, istartcol, iendcol,
+        rc = call_radsurf(load(nofma).oracle_radsurf, structs, istartcol, iendcol,
                           extra=(C.c_int32(nthreads), C.c_int32(nblocksize)))
         if rc < 0:
             raise RuntimeError(f"oracle_radsurf failed rc={rc}")
