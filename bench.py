@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the SPARTACUS-Surface solver hot path on B200.
+
+Metric (BASELINE.json): column·g·layers / s, SW+LW, on the synthetic
+vegetated-urban canopy of SURVEY.md §8(d): 1,048,576 columns x 16 layers,
+nreg = 3, one SW and one LW interval (g = 2), FP64.  One "step" = one radsurf
+pass over all columns of the rank.  Columns are independent, so ranks are
+independent shards (no collective in the path); per-rank work is fixed and the
+run reports weak scaling.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--streams 2|4] [--columns C]
+  python bench.py --impl reference ...   # CPU oracle (restatement of the Fortran) on the host cores
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NLAY = 16
+FULL_COLUMNS = 1 << 20
+UNIT = "column*g*layers/s"
+METRIC = "column_g_layers_per_s_SW+LW"
+
+# Algorithmic FLOPs per (column, layer), nreg = 3 (SURVEY.md §8d / App. C closed form)
+FLOPS = {
+    2: {"sw_layer": 24.5e3, "sw_sweep": 4.0e3, "lw_layer": 13.5e3, "lw_sweep": 3.5e3},
+    4: {"sw_layer": 176.3e3, "sw_sweep": 25.2e3, "lw_layer": 105.4e3, "lw_sweep": 23.2e3},
+}
+# Compulsory HBM bytes per (column, layer): 25 input + 40 output doubles + per-column terms (§8d)
+ALGO_BYTES_PER_COL_LAYER = 540.0
+
+
+def make_config(streams):
+    from spartacus_surface_b200 import config_type
+    cfg = config_type(do_sw=True, do_lw=True, nsw=1, nlw=1, n_vegetation_region_urban=2,
+                      n_vegetation_region_forest=2, n_stream_sw_urban=streams, n_stream_lw_urban=streams,
+                      n_stream_sw_forest=streams, n_stream_lw_forest=streams)
+    return cfg
+
+
+def allocate_outputs(cfg, ncol, ntotlay, device=None, pinned=False):
+    from spartacus_surface_b200 import canopy_flux_type, boundary_conds_out_type
+    bc = boundary_conds_out_type().allocate(ncol, 1, 1, device=device)
+    fl = [canopy_flux_type().allocate(cfg, ncol, ntotlay, 1, use_direct=d, do_save_flux_profile=False, device=device)
+          for d in (True, True, False, False)]
+    return bc, fl
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (C++ restatement of the Fortran solver; the Fortran itself cannot be
+    built: no Fortran compiler in the image) on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from spartacus_surface_b200.synthetic import make_synthetic
+    cfg = make_config(args.streams).consolidate(oracle_lib.legendre_gauss_init)
+    ncol = args.cpu_columns
+    cp, sw, lw = make_synthetic(cfg, ncol, NLAY)
+    bc, fl = allocate_outputs(cfg, ncol, cp.ntotlay)
+    solver = oracle_lib.make_solver(nthreads=0, nblocksize=16)
+    threads = oracle_lib.load().oracle_num_threads()
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rc = solver(cfg, cp, sw, lw, bc, None, None, *fl)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        if it >= args.warmup:
+            times.append(dt)
+    units = ncol * NLAY * 2
+    total = sum(times)
+    value = units * len(times) / total
+    sample = f"{ncol} of {FULL_COLUMNS} synthetic columns per step (same generator and seed), OpenMP blocks of 16 columns"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.columns),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, ncol):
+    return {"workload": f"synthetic vegetated-urban canopy, {ncol} columns x {NLAY} layers x (1 SW + 1 LW) "
+                        f"intervals per GPU, nreg=3, {args.streams} streams per hemisphere",
+            "columns_per_gpu": ncol, "layers": NLAY, "streams": args.streams, "nreg": 3,
+            "parallelism": "independent column shards, no collective",
+            "l2": "inputs+outputs per step (>= 9 GB at full size) exceed the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 4, 8])
+    ap.add_argument("--columns", type=int, default=FULL_COLUMNS, help="columns per GPU")
+    ap.add_argument("--cpu-columns", type=int, default=131072, help="columns of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generic", action="store_true", help="force the generic kernels")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    from spartacus_surface_b200 import radsurf
+    from spartacus_surface_b200._lib import load
+    from spartacus_surface_b200.synthetic import make_synthetic, to_host
+
+    lib = load()
+    if not torch.cuda.is_available() or lib.ssb200_device_count() <= 0:
+        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    lib.ssb200_set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    if args.generic:
+        lib.ssb200_set_option(b"fast_kernels", 0)
+
+    cfg = make_config(args.streams).consolidate()
+    ncol = args.columns
+    cp, sw, lw = make_synthetic(cfg, ncol, NLAY, col_offset=rank * ncol, device=device)
+    bc, fl = allocate_outputs(cfg, ncol, cp.ntotlay, device=device)
+    stream = torch.cuda.current_stream().cuda_stream
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def step():
+        rc = radsurf(cfg, cp, sw, lw, bc, None, None, *fl, stream=stream)
+        assert rc == 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = lib.ssb200_kernel_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = lib.ssb200_kernel_launch_count() - launches0
+    barrier()
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    units_per_rank = ncol * NLAY * 2
+    value = world * units_per_rank * args.steps / (ms_max * 1e-3)
+
+    # ---- conservation residuals and parity on a subsample (reported, rank 0) --------------------
+    res = {}
+    names = ("sw_norm_dir", "sw_norm_diff", "lw_internal", "lw_norm")
+    for name, f in zip(names, fl):
+        r = torch.zeros(ncol, dtype=torch.float64, device=device)
+        s = f.as_struct()
+        cps = cp.as_struct()
+        rc = lib.ssb200_canopy_flux_check_device(C.byref(s), C.byref(cps), C.c_void_p(r.data_ptr()), None)
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        denom = f.top_dn[:, 0].abs().clamp_min(1e-30) if name != "lw_internal" else f.top_net[:, 0].abs().clamp_min(1e-30)
+        res[name] = float((r.abs() / denom).max().item())
+    nonfinite = int(sum((~torch.isfinite(getattr(f, k))).sum().item() for f in fl
+                        for k in ("ground_net", "top_net", "clear_air_abs", "veg_abs", "wall_net", "roof_net")))
+
+    out = None
+    if rank == 0:
+        # ---- per-kernel times (library CUDA events on the launch stream), separate pass ---------
+        lib.ssb200_set_profiling(1)
+        step()
+        torch.cuda.synchronize()
+        tms, cnt = (C.c_double * 5)(), (C.c_int64 * 5)()
+        lib.ssb200_last_kernel_times_ms(tms)
+        lib.ssb200_last_kernel_counts(cnt)
+        lib.ssb200_set_profiling(0)
+        fam = ["sw_layer", "sw_sweep", "lw_layer", "lw_sweep", "surface"]
+        kt = {fam[i]: {"ms": tms[i], "launches": int(cnt[i])} for i in range(5)}
+        fp64_peak = lib.ssb200_measure_fp64_peak_tflops(1 << 15)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        fl_tab = FLOPS.get(args.streams)
+        roofline = roofline_hbm = None
+        if fl_tab:
+            dom = max(("sw_layer", "lw_layer", "sw_sweep", "lw_sweep"), key=lambda k: kt[k]["ms"])
+            per_launch_ms = kt[dom]["ms"] / max(1, kt[dom]["launches"])
+            flops_per_launch = fl_tab[dom] * ncol * NLAY / max(1, kt[dom]["launches"])
+            achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
+            roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                        "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                        "peak_source": "measured in this run: register-resident independent DFMA chains on all SMs "
+                                       "(ssb200_measure_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
+                        "avg_launch_ms": per_launch_ms, "launches_per_step": kt[dom]["launches"],
+                        "algorithmic_flops_per_column_layer": fl_tab[dom]}
+            all_flops = sum(fl_tab.values()) * ncol * NLAY
+            step_ms = ms_max / args.steps
+            roofline["whole_step"] = {"achieved": all_flops / (step_ms * 1e-3) / 1e12,
+                                      "frac": all_flops / (step_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
+                                      "algorithmic_flops_per_column_layer": sum(fl_tab.values())}
+            gbs = ALGO_BYTES_PER_COL_LAYER * ncol * NLAY / (step_ms * 1e-3) / 1e9
+            roofline_hbm = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                            "note": "compulsory input+output bytes only; the path is FP64-bound, shown for context"}
+
+        # ---- end to end through the host-pointer C ABI entry (pinned host buffers) --------------
+        e2e = None
+        if args.e2e_steps > 0:
+            hcp, hsw, hlw = to_host(cp), to_host(sw), to_host(lw)
+            pin = []
+            for obj in (hcp, hsw, hlw):
+                for k, v in list(vars(obj).items()):
+                    if isinstance(v, np.ndarray) and v.dtype == np.float64:
+                        tt = torch.from_numpy(v).pin_memory()
+                        pin.append(tt)
+                        setattr(obj, k, tt.numpy())
+            hbc, hfl = allocate_outputs(cfg, ncol, hcp.ntotlay)
+            for obj in [hbc] + hfl:
+                for k, v in list(vars(obj).items()):
+                    if isinstance(v, np.ndarray) and v.dtype == np.float64:
+                        tt = torch.from_numpy(v).pin_memory()
+                        pin.append(tt)
+                        setattr(obj, k, tt.numpy())
+            h2d = sum(v.nbytes for obj in (hcp, hsw, hlw) for v in vars(obj).values()
+                      if isinstance(v, np.ndarray) and v.dtype == np.float64)
+            d2h = sum(v.nbytes for obj in [hbc] + hfl for v in vars(obj).values()
+                      if isinstance(v, np.ndarray) and v.dtype == np.float64)
+            radsurf(cfg, hcp, hsw, hlw, hbc, None, None, *hfl)  # warm-up (allocates the device mirrors)
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                rc = radsurf(cfg, hcp, hsw, hlw, hbc, None, None, *hfl)
+                assert rc == 0
+            dt = time.perf_counter() - t0
+            e2e = {"value": world * units_per_rank * args.e2e_steps / dt, "unit": UNIT,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": 1e3 * dt / args.e2e_steps,
+                   "note": "ssb200_radsurf with pinned host arrays: H2D of every input, kernels, D2H of every "
+                           "output, host wall clock; measured on rank 0 and scaled by the number of ranks"}
+            # parity of the device-resident result against the host-path result (same kernels)
+            dev_top = fl[0].top_net[:4096, 0].cpu().numpy()
+            assert np.array_equal(dev_top, hfl[0].top_net[:4096, 0]), "device and host entry disagree"
+
+        # ---- CPU baseline beside it (oracle on the host cores, bounded sample) -------------------
+        cpu = None
+        parity_err = None
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib
+            import parity
+            from spartacus_surface_b200.radsurf_canopy_flux import ALL_FIELDS
+            nc = min(args.cpu_columns, ncol)
+            ccp, csw, clw = make_synthetic(cfg, nc, NLAY, col_offset=rank * ncol)
+            cbc, cfl = allocate_outputs(cfg, nc, ccp.ntotlay)
+            solver = oracle_lib.make_solver()
+            solver(cfg, ccp, csw, clw, cbc, None, 256, *cfl)  # touch pages / warm caches
+            t0 = time.perf_counter()
+            rc = solver(cfg, ccp, csw, clw, cbc, None, None, *cfl)
+            dt = time.perf_counter() - t0
+            assert rc == 0
+            cpu = {"value": nc * NLAY * 2 / dt, "unit": UNIT, "cores": oracle_lib.load().oracle_num_threads(),
+                   "kind": "port",
+                   "sample": f"first {nc} of the {ncol} columns, one pass, OpenMP dynamic blocks of 16 columns "
+                             f"({dt:.1f} s); C++ restatement of the reference (no Fortran compiler in the image)"}
+            # parity of the GPU result on the same columns (max over fields of err relative to field max)
+            got = {n: {k: getattr(f, k)[:nc * (NLAY if getattr(f, k).shape[0] != ncol else 1)].cpu().numpy()
+                       for k in ALL_FIELDS if getattr(f, k) is not None} for n, f in zip(names, fl)}
+            exp = {n: {k: getattr(f, k) for k in ALL_FIELDS if getattr(f, k) is not None} for n, f in zip(names, cfl)}
+            errs = parity.field_errors(got, exp)
+            flux_fields = [k for k in errs if "sunlit" not in k[1]]
+            parity_err = {"max_rel_err_fluxes": max(errs[k] for k in flux_fields),
+                          "max_rel_err_sunlit_fractions": max([errs[k] for k in errs if "sunlit" in k[1]] or [0.0]),
+                          "columns": nc, "definition": "max|gpu-oracle| / max|oracle| per field"}
+
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, ncol),
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "kernel_times_one_step": kt,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "conservation_max_abs_residual_over_top_flux": res, "nonfinite_outputs": nonfinite,
+            "parity_vs_oracle": parity_err, "library": lib.ssb200_version().decode(),
+            "kernels": "generic" if args.generic else "fast where available",
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

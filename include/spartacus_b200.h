@@ -217,6 +217,8 @@ int64_t ssb200_kernel_launch_count(void);
  * events and synchronises at the end of the call). */
 int ssb200_set_profiling(int enable);
 int ssb200_last_kernel_times_ms(double out[5]);
+/* Launches per kernel family in that call (same order). */
+int ssb200_last_kernel_counts(int64_t out[5]);
 
 /* Tuning knobs: "scratch_budget_bytes" (device scratch per launch chunk;
  * 0 = automatic: half of the free memory, at most 24 GiB) and "fast_kernels"

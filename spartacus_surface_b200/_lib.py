@@ -37,6 +37,7 @@ def _declare(lib):
     lib.ssb200_kernel_launch_count.restype = C.c_int64
     lib.ssb200_set_profiling.argtypes = [C.c_int]
     lib.ssb200_last_kernel_times_ms.argtypes = [P(C.c_double)]
+    lib.ssb200_last_kernel_counts.argtypes = [P(C.c_int64)]
     lib.ssb200_release.restype = C.c_int
     lib.ssb200_set_option.argtypes = [C.c_char_p, C.c_int64]
     lib.ssb200_canopy_flux_scale_device.argtypes = [P(_abi.CanopyFlux), P(C.c_int32), P(C.c_int32),

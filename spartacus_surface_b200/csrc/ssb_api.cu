@@ -150,6 +150,7 @@ struct Context {
   size_t budget_doubles = 0;
   bool profiling = false;
   double times_ms[5] = {0, 0, 0, 0, 0};
+  long long counts[5] = {0, 0, 0, 0, 0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaError_t first_error = cudaSuccess;
   int fast_mode = 1;
@@ -180,6 +181,7 @@ struct CudaBackend {
       float ms = 0;
       cudaEventElapsedTime(&ms, cx.ev0, cx.ev1);
       cx.times_ms[family] += ms;
+      cx.counts[family] += 1;
     }
   }
   void check_launch() {
@@ -302,6 +304,7 @@ int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, i
       cudaEventCreate(&cx.ev1);
     }
     for (double &t : cx.times_ms) t = 0.0;
+    for (long long &n : cx.counts) n = 0;
   }
   CudaBackend be(cx);
   ssb::Dispatcher<CudaBackend> disp(be);
@@ -632,6 +635,12 @@ int ssb200_set_profiling(int enable) {
 int ssb200_last_kernel_times_ms(double out[5]) {
   std::lock_guard<std::mutex> lock(g_mutex);
   for (int i = 0; i < 5; ++i) out[i] = g_ctx.times_ms[i];
+  return 0;
+}
+
+int ssb200_last_kernel_counts(int64_t out[5]) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  for (int i = 0; i < 5; ++i) out[i] = g_ctx.counts[i];
   return 0;
 }
 

@@ -82,7 +82,9 @@ def make_synthetic(config, ncol, nlay=16, col_offset=0, device=None, seed=SEED):
     cp.cos_sza = contiguous(0.05 + 0.95 * u(1))
     cp.dz = flat(2.0 + 2.0 * ul(2))
     b0, p = 0.25 + 0.25 * u(3), 1.0 + u(4)
-    bf = b0[:, None] * (1.0 - lfrac[None, :]) ** p[:, None]
+    # b0 (1-x)(1-(p-1)x): monotone decreasing like b0 (1-x)^p but free of pow(), whose last bit
+    # differs between numpy and torch/CUDA
+    bf = b0[:, None] * ((1.0 - lfrac[None, :]) * (1.0 - (p[:, None] - 1.0) * lfrac[None, :]))
     cp.building_fraction = flat(bf)
     cp.building_scale = flat((20.0 + 20.0 * u(5))[:, None] + 0.0 * bf)
     lv = 4.0 + floor(9.0 * u(6))
@@ -108,6 +110,7 @@ def make_synthetic(config, ncol, nlay=16, col_offset=0, device=None, seed=SEED):
     sw.roof_albedo_dir = sw.roof_albedo.copy() if xp is np else sw.roof_albedo.clone()
 
     lw = lw_spectral_properties_type(nlw)
+    p4 = lambda t: (t * t) * (t * t)
     lw.air_ext = full((ntot, nlw), 1.0e-5)
     lw.air_ssa = full((ntot, nlw), 0.0)
     lw.veg_ssa = spec(flat((0.01 + 0.04 * u(15))[:, None] + 0.0 * bf), nlw)
@@ -118,10 +121,10 @@ def make_synthetic(config, ncol, nlay=16, col_offset=0, device=None, seed=SEED):
     lw.ground_emissivity = spec(0.85 + 0.14 * u(20), nlw)
     lw.roof_emissivity = spec(flat(0.85 + 0.14 * ul(21)), nlw)
     lw.wall_emissivity = spec(flat(0.85 + 0.14 * ul(22)), nlw)
-    lw.ground_emission = contiguous(StefanBoltzmann * lw.ground_emissivity * spec(t_ground, nlw) ** 4)
-    lw.roof_emission = contiguous(StefanBoltzmann * lw.roof_emissivity * spec(flat(t_roof), nlw) ** 4)
-    lw.wall_emission = contiguous(StefanBoltzmann * lw.wall_emissivity * spec(flat(t_wall), nlw) ** 4)
-    planck = contiguous(StefanBoltzmann * spec(flat(t_air), nlw) ** 4)
+    lw.ground_emission = contiguous(StefanBoltzmann * lw.ground_emissivity * p4(spec(t_ground, nlw)))
+    lw.roof_emission = contiguous(StefanBoltzmann * lw.roof_emissivity * p4(spec(flat(t_roof), nlw)))
+    lw.wall_emission = contiguous(StefanBoltzmann * lw.wall_emissivity * p4(spec(flat(t_wall), nlw)))
+    planck = contiguous(StefanBoltzmann * p4(spec(flat(t_air), nlw)))
     lw.clear_air_planck = planck
     lw.veg_planck = planck.copy() if xp is np else planck.clone()
     lw.veg_air_planck = planck.copy() if xp is np else planck.clone()
