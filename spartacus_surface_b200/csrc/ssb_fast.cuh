@@ -1,6 +1,7 @@
-// ssb_fast.cuh - sub-warp kernels for the hot configurations (filled in by
-// ssb_fast_impl.cuh); every hook returns false when it has no kernel for the
-// requested shape, in which case the generic one-thread-per-problem kernel runs.
+// ssb_fast.cuh - hooks of the register-resident ("fast") kernels.  A hook
+// returns false when it has no kernel for the requested shape, in which case
+// the generic one-thread-per-problem kernel runs.  Specialisations for the
+// stream counts that have fast kernels are defined in ssb_f_ns*_*.cu.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -15,4 +16,8 @@ template <int NS>
 inline bool fast_layer_lw(const ClassArgs &, long, cudaStream_t) {
   return false;
 }
+template <> bool fast_layer_sw<1>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_layer_sw<2>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_layer_lw<1>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_layer_lw<2>(const ClassArgs &, long, cudaStream_t);
 }  // namespace ssb

@@ -1,0 +1,321 @@
+// ssb_fast_layer.cuh - register-resident layer problems: one thread per
+// (column, interval, layer) with compile-time (NREG regions, NS streams).
+// Same inputs, outputs and scratch layout as layer_problem_sw/_lw of
+// ssb_solver.cuh (radsurf_urban_sw.F90:335-585, radsurf_urban_lw.F90:296-546
+// and the forest equivalents); the layer matrices come from ssb_fast_math.cuh.
+#pragma once
+#include "ssb_fast_math.cuh"
+#include "ssb_solver.cuh"
+
+namespace ssb {
+
+struct LayerOptics {
+  double ext[3], ssa[3], planck[3];
+  double wall_ext, wall_factor;
+  double zcos, cos_sza, tan0, sin0, dz;
+  double vssa, vplanck, vaplanck, ve;
+};
+
+// scatter a solved block (NR regions starting at region R0) into the full-size
+// scratch matrix, zeros elsewhere; every index is a compile-time constant
+template <int NREG, int NS, int NR, int R0, bool ROWS_STREAMS, bool COLS_STREAMS>
+SSB_HDI void put_block(double *S, int &e, const double *M, int lev, int nlev, int width, int q) {
+  constexpr int n = NREG * NS, d = NREG;
+  constexpr int R = ROWS_STREAMS ? n : d, C = COLS_STREAMS ? n : d;
+  constexpr int br = ROWS_STREAMS ? NR * NS : NR, bc = COLS_STREAMS ? NR * NS : NR;
+  constexpr int i0 = ROWS_STREAMS ? R0 * NS : R0, j0 = COLS_STREAMS ? R0 * NS : R0;
+  SSB_UNROLL
+  for (int j = 0; j < C; ++j) {
+    SSB_UNROLL
+    for (int i = 0; i < R; ++i) {
+      const int bi = i - i0, bj = j - j0;
+      const bool in = bi >= 0 && bi < br && bj >= 0 && bj < bc;
+      S[sidx(e + i + R * j, lev, nlev, width, q)] = in ? M[in ? bi + br * bj : 0] : 0.0;
+    }
+  }
+  e += R * C;
+}
+
+template <int NREG, int NS, int NR, int R0>
+SSB_HDI void fast_sw_branch(const ClassArgs &a, int q, int lev, const LayerGeom &gm, const LayerOptics &op) {
+  constexpr int N = NR * NS;
+  const SolveCfg &c = a.cfg;
+  constexpr int r0 = R0;
+  double g0[NR * NR], g1[N * N], g2[N * N], g3[N * NR], nsc[N], frac[NR];
+  SSB_UNROLL
+  for (int i = 0; i < NR * NR; ++i) g0[i] = 0.0;
+  SSB_UNROLL
+  for (int i = 0; i < N * N; ++i) {
+    g1[i] = 0.0;
+    g2[i] = 0.0;
+  }
+  SSB_UNROLL
+  for (int i = 0; i < N * NR; ++i) g3[i] = 0.0;
+  SSB_UNROLL
+  for (int rf = 0; rf < NR; ++rf) {
+    const int Rf = r0 + rf;
+    frac[rf] = (NR == 1) ? 1.0 : gm.frac[Rf];
+    SSB_UNROLL
+    for (int Rt = 0; Rt < NREG; ++Rt) {
+      if (Rt == Rf) continue;
+      const double fx = gm.f_exchange[Rt + 3 * Rf];
+      g0[rf + NR * rf] -= op.tan0 * fx;
+      SSB_UNROLL
+      for (int js = 0; js < NS; ++js) g1[(js + rf * NS) * (N + 1)] -= a.lg.tan_ang[js] * fx;
+      SSB_UNROLL
+      for (int rt = 0; rt < NR; ++rt) {
+        if (rt + r0 == Rt) {
+          g0[rt + NR * rf] = op.tan0 * fx;
+          SSB_UNROLL
+          for (int js = 0; js < NS; ++js) g1[(js + rt * NS) + N * (js + rf * NS)] = a.lg.tan_ang[js] * fx;
+        }
+      }
+    }
+  }
+  SSB_UNROLL
+  for (int r = 0; r < NR; ++r) {
+    const int Rr = r0 + r;
+    const double ext = op.ext[Rr], es = op.ext[Rr] * op.ssa[Rr];
+    const double fw = c.urban ? gm.f_wall[Rr] : 0.0;
+    g0[r + NR * r] = g0[r + NR * r] - ext / (c.urban ? op.zcos : op.cos_sza) - op.tan0 * fw * op.wall_ext;
+    SSB_UNROLL
+    for (int js = 0; js < NS; ++js) {
+      const int i = js + r * NS;
+      g1[i + N * i] = g1[i + N * i] - ext / a.lg.mu[js] - a.lg.tan_ang[js] * fw * op.wall_ext;
+      nsc[i] = 1.0 / (a.lg.weight[js] * a.lg.mu[js] * ((NR == 1) ? 1.0 : gm.frac[Rr]));
+      g3[i + N * r] = 0.5 * (a.lg.weight[js] * es + a.lg.vweight[js] * op.sin0 * fw * op.wall_factor);
+      SSB_UNROLL
+      for (int jt = 0; jt < NS; ++jt)
+        g2[(jt + r * NS) + N * i] =
+            0.5 * (a.lg.weight[jt] * es / a.lg.mu[js] + a.lg.vweight[jt] * a.lg.tan_ang[js] * fw * op.wall_factor);
+    }
+  }
+  SSB_UNROLL
+  for (int i = 0; i < N * N; ++i) g1[i] += g2[i];
+
+  double R[N * N], T[N * N], Idiff[N * N], Sup[N * NR], Sdn[N * NR], Idd[N * NR], E[NR * NR], Idir[NR * NR];
+  fast_layer_sw_math<NR, NS>(op.dz, g0, g1, g2, g3, nsc, frac, R, T, Sup, Sdn, E, Idir, Idiff, Idd);
+
+  const int nlev = a.lmax, width = a.ncols * c.nspec;
+  int e = 0;
+  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, R, lev, nlev, width, q);
+  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, T, lev, nlev, width, q);
+  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, Idiff, lev, nlev, width, q);
+  put_block<NREG, NS, NR, R0, true, false>(a.layer, e, Sup, lev, nlev, width, q);
+  put_block<NREG, NS, NR, R0, true, false>(a.layer, e, Sdn, lev, nlev, width, q);
+  put_block<NREG, NS, NR, R0, true, false>(a.layer, e, Idd, lev, nlev, width, q);
+  put_block<NREG, NS, NR, R0, false, false>(a.layer, e, E, lev, nlev, width, q);
+  put_block<NREG, NS, NR, R0, false, false>(a.layer, e, Idir, lev, nlev, width, q);
+  bool bad = false;
+  SSB_UNROLL
+  for (int i = 0; i < N * N; ++i) bad = bad || !(fabs(R[i]) < 1.0e300) || !(fabs(T[i]) < 1.0e300);
+  count_failure(a.status, bad ? 1 : 0);
+}
+
+SSB_HDI void load_geometry_inputs(const ClassArgs &a, int il, double &bf, double &bs, double &vf, double &vs,
+                                  double &ve, double &vcf, double &vfsd) {
+  const SolveCfg &c = a.cfg;
+  const bool veg = c.nreg > 1 || !c.urban;
+  bf = c.urban ? a.cp.building_fraction[il] : 0.0;
+  bs = c.urban ? a.cp.building_scale[il] : 0.0;
+  vf = (veg && a.cp.veg_fraction) ? a.cp.veg_fraction[il] : 0.0;
+  vs = (veg && a.cp.veg_scale) ? a.cp.veg_scale[il] : 1.0;
+  ve = (veg && a.cp.veg_ext) ? a.cp.veg_ext[il] : 0.0;
+  vcf = (c.urban && c.nreg > 1 && a.cp.veg_contact_fraction) ? a.cp.veg_contact_fraction[il] : 0.0;
+  vfsd = (c.nreg == 3) ? a.cp.veg_fsd[il] : 0.0;
+}
+
+template <int NREG, int NS>
+SSB_HD inline void fast_layer_problem_sw(const ClassArgs &a, int q, int lev) {
+  const SolveCfg &c = a.cfg;
+  const int nspec = c.nspec;
+  const int ic = q / nspec, g = q % nspec;
+  const int col = a.cols[ic];
+  if (lev >= a.nlay[col]) return;
+  LayerOptics op;
+  op.cos_sza = a.cp.cos_sza[col];
+  if (!(op.cos_sza > 0.0)) return;
+  const int il = a.istartlay[col] - 1 + lev;
+  op.zcos = c.urban ? dmax(op.cos_sza, 1.0e-6) : op.cos_sza;
+  op.sin0 = 0.0;
+  if (c.urban) {
+    op.sin0 = sqrt(1.0 - op.zcos * op.zcos);
+    op.tan0 = op.sin0 / op.zcos;
+  } else {
+    op.tan0 = sqrt(1.0 - op.cos_sza * op.cos_sza) / dmax(op.cos_sza, 1.0e-6);
+  }
+  op.dz = a.cp.dz[il];
+  double bf, bs, vf, vs, ve, vcf, vfsd;
+  load_geometry_inputs(a, il, bf, bs, vf, vs, ve, vcf, vfsd);
+  LayerGeom gm;
+  layer_geometry(c, bf, bs, vf, vs, vcf, vfsd, 1.0, gm);
+  op.ext[0] = SSB_LAY(a.sw.air_ext, g, il);
+  op.ssa[0] = SSB_LAY(a.sw.air_ssa, g, il);
+  SSB_UNROLL
+  for (int r = 1; r < NREG; ++r) {
+    const double vssa = SSB_LAY(a.sw.veg_ssa, g, il);
+    const double od = (NREG == 2) ? 1.0 : gm.od_scaling[r];
+    op.ext[r] = op.ext[0] + od * ve;
+    op.ssa[r] = (op.ext[0] * op.ssa[0] + od * ve * vssa) / dmax(op.ext[r], 1.0e-8);
+  }
+  op.wall_ext = 0.0;
+  op.wall_factor = 0.0;
+  if (c.urban) {
+    const double wa = SSB_LAY(a.sw.wall_albedo, g, il), wsf = SSB_LAY(a.sw.wall_specular_frac, g, il);
+    op.wall_ext = 1.0 - wa * wsf;
+    op.wall_factor = wa * (1.0 - wsf);
+  }
+  if (gm.nr == NREG) {
+    fast_sw_branch<NREG, NS, NREG, 0>(a, q, lev, gm, op);
+  } else if (gm.r0 == 0) {
+    fast_sw_branch<NREG, NS, 1, 0>(a, q, lev, gm, op);  // vegetation-free layer: clear region only
+  } else {
+    if (NREG > 1) fast_sw_branch<NREG, NS, (NREG > 1 ? NREG - 1 : 1), (NREG > 1 ? 1 : 0)>(a, q, lev, gm, op);
+  }
+}
+
+template <int NREG, int NS, int NR, int R0>
+SSB_HDI void fast_lw_branch(const ClassArgs &a, int q, int lev, const LayerGeom &gm, const LayerOptics &op,
+                            double wall_emission, int g, int il) {
+  constexpr int N = NR * NS;
+  const SolveCfg &c = a.cfg;
+  constexpr int r0 = R0;
+  double g1[N * N], g2[N * N], nsc[N], brate[N];
+  SSB_UNROLL
+  for (int i = 0; i < N * N; ++i) {
+    g1[i] = 0.0;
+    g2[i] = 0.0;
+  }
+  SSB_UNROLL
+  for (int rf = 0; rf < NR; ++rf) {
+    const int Rf = r0 + rf;
+    SSB_UNROLL
+    for (int Rt = 0; Rt < NREG; ++Rt) {
+      if (Rt == Rf) continue;
+      const double fx = gm.f_exchange[Rt + 3 * Rf];
+      SSB_UNROLL
+      for (int js = 0; js < NS; ++js) g1[(js + rf * NS) * (N + 1)] -= a.lg.tan_ang[js] * fx;
+      SSB_UNROLL
+      for (int rt = 0; rt < NR; ++rt) {
+        if (rt + r0 == Rt) {
+          SSB_UNROLL
+          for (int js = 0; js < NS; ++js) g1[(js + rt * NS) + N * (js + rf * NS)] = a.lg.tan_ang[js] * fx;
+        }
+      }
+    }
+  }
+  SSB_UNROLL
+  for (int r = 0; r < NR; ++r) {
+    const int Rr = r0 + r;
+    const double ext = op.ext[Rr], es = op.ext[Rr] * op.ssa[Rr];
+    const double fw = c.urban ? gm.f_wall[Rr] : 0.0;
+    const double volume_emiss = gm.frac[Rr] * (ext * (1.0 - op.ssa[Rr]) * op.planck[Rr]);
+    const double wall_emiss = c.urban ? gm.norm_perim_wall[Rr] * a.lg.vadjustment * wall_emission : 0.0;
+    SSB_UNROLL
+    for (int js = 0; js < NS; ++js) {
+      const int i = js + r * NS;
+      g1[i + N * i] = g1[i + N * i] - ext / a.lg.mu[js] - a.lg.tan_ang[js] * fw * op.wall_ext;
+      nsc[i] = 1.0 / (a.lg.weight[js] * a.lg.mu[js] * ((NR == 1) ? 1.0 : gm.frac[Rr]));
+      brate[i] = (a.lg.hweight[js] / a.lg.mu[js]) * volume_emiss + (0.5 * a.lg.vweight[js]) * wall_emiss;
+      SSB_UNROLL
+      for (int jt = 0; jt < NS; ++jt)
+        g2[(jt + r * NS) + N * i] =
+            0.5 * (a.lg.weight[jt] * es / a.lg.mu[js] + a.lg.vweight[jt] * a.lg.tan_ang[js] * fw * op.wall_factor);
+    }
+  }
+  SSB_UNROLL
+  for (int i = 0; i < N * N; ++i) g1[i] += g2[i];
+
+  double R[N * N], T[N * N], IF[N * N], src[N], isrc[N];
+  fast_layer_lw_math<NR, NS>(op.dz, g1, g2, brate, nsc, R, T, src, IF, isrc);
+
+  constexpr int n = NREG * NS;
+  const int nlev = a.lmax, width = a.ncols * c.nspec;
+  int e = 0;
+  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, R, lev, nlev, width, q);
+  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, T, lev, nlev, width, q);
+  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, IF, lev, nlev, width, q);
+  constexpr int i0 = R0 * NS;
+  SSB_UNROLL
+  for (int i = 0; i < n; ++i) {
+    const int bi = i - i0;
+    const bool in = bi >= 0 && bi < N;
+    a.layer[sidx(e + i, lev, nlev, width, q)] = in ? src[in ? bi : 0] : 0.0;
+    a.layer[sidx(e + n + i, lev, nlev, width, q)] = in ? isrc[in ? bi : 0] : 0.0;
+  }
+  bool bad = false;
+  SSB_UNROLL
+  for (int i = 0; i < N * N; ++i) bad = bad || !(fabs(R[i]) < 1.0e300) || !(fabs(T[i]) < 1.0e300);
+  count_failure(a.status, bad ? 1 : 0);
+}
+
+template <int NREG, int NS>
+SSB_HD inline void fast_layer_problem_lw(const ClassArgs &a, int q, int lev) {
+  const SolveCfg &c = a.cfg;
+  const int nspec = c.nspec;
+  const int ic = q / nspec, g = q % nspec;
+  const int col = a.cols[ic];
+  if (lev >= a.nlay[col]) return;
+  const int il = a.istartlay[col] - 1 + lev;
+  LayerOptics op;
+  op.dz = a.cp.dz[il];
+  double bf, bs, vf, vs, ve, vcf, vfsd;
+  load_geometry_inputs(a, il, bf, bs, vf, vs, ve, vcf, vfsd);
+  LayerGeom gm;
+  layer_geometry(c, bf, bs, vf, vs, vcf, vfsd, a.lg.vadjustment2, gm);
+  op.ext[0] = SSB_LAY(a.lw.air_ext, g, il);
+  op.ssa[0] = SSB_LAY(a.lw.air_ssa, g, il);
+  op.planck[0] = SSB_LAY(a.lw.clear_air_planck, g, il);
+  double vssa = 0.0, vplanck = 0.0, vaplanck = 0.0;
+  if (NREG > 1) {
+    vssa = SSB_LAY(a.lw.veg_ssa, g, il);
+    vplanck = SSB_LAY(a.lw.veg_planck, g, il);
+    vaplanck = SSB_LAY(a.lw.veg_air_planck, g, il);
+  }
+  SSB_UNROLL
+  for (int r = 1; r < NREG; ++r) {
+    const double od = (NREG == 2) ? 1.0 : gm.od_scaling[r];
+    op.ext[r] = op.ext[0] + od * ve;
+    op.ssa[r] = (op.ext[0] * op.ssa[0] + od * ve * vssa) / dmax(op.ext[r], 1.0e-8);
+    op.planck[r] = (op.ext[0] * (1.0 - op.ssa[0]) * vaplanck + od * ve * (1.0 - vssa) * vplanck) /
+                   dmax(op.ext[r] * (1.0 - op.ssa[r]), 1.0e-8);
+  }
+  op.wall_ext = 1.0;
+  op.wall_factor = c.urban ? 1.0 - SSB_LAY(a.lw.wall_emissivity, 0, il) : 0.0;
+  const double wall_emission = c.urban ? SSB_LAY(a.lw.wall_emission, g, il) : 0.0;
+
+  // bookkeeping terms of urban_lw:447-476 for all regions (same as the generic path)
+  constexpr int n = NREG * NS, d = NREG;
+  double emiss_factor = 0.0;
+  SSB_UNROLL
+  for (int js = 0; js < NS; ++js) emiss_factor += a.lg.hweight[js] / a.lg.mu[js];
+  emiss_factor = 2.0 * emiss_factor;
+  const int nlev = a.lmax, width = a.ncols * nspec;
+  const int e_book = 3 * n * n + 2 * n;
+  double wsum = 0.0;
+  SSB_UNROLL
+  for (int Rr = 0; Rr < NREG; ++Rr) {
+    const double volume_emiss = gm.frac[Rr] * (op.ext[Rr] * (1.0 - op.ssa[Rr]) * op.planck[Rr]);
+    a.layer[sidx(e_book + Rr, lev, nlev, width, q)] = emiss_factor * volume_emiss;
+    double e_air = 0.0, e_veg = 0.0;
+    if (Rr > 0) {
+      e_air = emiss_factor * gm.frac[Rr] * op.ext[0] * (1.0 - op.ssa[0]) * vaplanck;
+      e_veg = emiss_factor * gm.frac[Rr] * ve * (1.0 - vssa) * vplanck * gm.od_scaling[Rr];
+    }
+    a.layer[sidx(e_book + d + Rr, lev, nlev, width, q)] = e_air;
+    a.layer[sidx(e_book + 2 * d + Rr, lev, nlev, width, q)] = e_veg;
+    wsum += gm.norm_perim_wall[Rr];
+  }
+  a.layer[sidx(e_book + 3 * d, lev, nlev, width, q)] = c.urban ? (wsum * a.lg.vadjustment) * wall_emission : 0.0;
+
+  if (gm.nr == NREG) {
+    fast_lw_branch<NREG, NS, NREG, 0>(a, q, lev, gm, op, wall_emission, g, il);
+  } else if (gm.r0 == 0) {
+    fast_lw_branch<NREG, NS, 1, 0>(a, q, lev, gm, op, wall_emission, g, il);
+  } else {
+    if (NREG > 1)
+      fast_lw_branch<NREG, NS, (NREG > 1 ? NREG - 1 : 1), (NREG > 1 ? 1 : 0)>(a, q, lev, gm, op, wall_emission, g, il);
+  }
+}
+
+}  // namespace ssb

@@ -1,0 +1,195 @@
+// ssb_small.cuh - compile-time-sized dense algebra for the register-resident
+// ("fast") kernels: every loop has constant bounds and is fully unrolled, every
+// index is static, so a matrix lives in registers of the one thread that owns
+// the problem.  No dynamic control flow except a fixed number of Jacobi sweeps.
+//
+// These routines back ssb_fast_math.cuh, which evaluates the same layer
+// quantities as radtool_calc_matrices_{sw,lw}_eig.F90 through an algebraically
+// equivalent but cheaper and better conditioned route.
+#pragma once
+#include "ssb_math.cuh"
+
+#if defined(__CUDACC__)
+#define SSB_UNROLL _Pragma("unroll")
+#else
+#define SSB_UNROLL
+#endif
+
+namespace ssb {
+
+// C (R x C) = A (R x K) * B (K x C)
+template <int R, int K, int C>
+SSB_HDI void sm_mul(const double *A, const double *B, double *Cm) {
+  SSB_UNROLL
+  for (int j = 0; j < C; ++j) {
+    SSB_UNROLL
+    for (int i = 0; i < R; ++i) {
+      double s = 0.0;
+      SSB_UNROLL
+      for (int k = 0; k < K; ++k) s = fma(A[i + R * k], B[k + K * j], s);
+      Cm[i + R * j] = s;
+    }
+  }
+}
+
+// y (R) = A (R x C) x (C)
+template <int R, int C>
+SSB_HDI void sm_mulvec(const double *A, const double *x, double *y) {
+  SSB_UNROLL
+  for (int i = 0; i < R; ++i) {
+    double s = 0.0;
+    SSB_UNROLL
+    for (int j = 0; j < C; ++j) s = fma(A[i + R * j], x[j], s);
+    y[i] = s;
+  }
+}
+
+// In-place LU without pivoting, Doolittle (unit lower factor); the reciprocals
+// of the pivots are stored on the diagonal so that solves need no division.
+template <int N>
+SSB_HDI void sm_lu(double *A) {
+  SSB_UNROLL
+  for (int k = 0; k < N; ++k) {
+    const double inv = 1.0 / A[k + N * k];
+    A[k + N * k] = inv;
+    SSB_UNROLL
+    for (int i = k + 1; i < N; ++i) A[i + N * k] *= inv;
+    SSB_UNROLL
+    for (int j = k + 1; j < N; ++j) {
+      const double akj = A[k + N * j];
+      SSB_UNROLL
+      for (int i = k + 1; i < N; ++i) A[i + N * j] = fma(-A[i + N * k], akj, A[i + N * j]);
+    }
+  }
+}
+
+// Solve A X = B in place (B: N x C) with the factors of sm_lu.
+template <int N, int C>
+SSB_HDI void sm_lu_solve_left(const double *LU, double *B) {
+  SSB_UNROLL
+  for (int j = 0; j < C; ++j) {
+    double *x = B + N * j;
+    SSB_UNROLL
+    for (int i = 1; i < N; ++i) {
+      double s = x[i];
+      SSB_UNROLL
+      for (int k = 0; k < i; ++k) s = fma(-LU[i + N * k], x[k], s);
+      x[i] = s;
+    }
+    SSB_UNROLL
+    for (int i = N - 1; i >= 0; --i) {
+      double s = x[i];
+      SSB_UNROLL
+      for (int k = i + 1; k < N; ++k) s = fma(-LU[i + N * k], x[k], s);
+      x[i] = s * LU[i + N * i];
+    }
+  }
+}
+
+// Solve X A = B in place (B: R x N): X = B U^-1 L^-1.
+template <int R, int N>
+SSB_HDI void sm_lu_solve_right(const double *LU, double *B) {
+  // X U = B : forward over columns
+  SSB_UNROLL
+  for (int j = 0; j < N; ++j) {
+    SSB_UNROLL
+    for (int k = 0; k < j; ++k) {
+      const double u = LU[k + N * j];
+      SSB_UNROLL
+      for (int i = 0; i < R; ++i) B[i + R * j] = fma(-B[i + R * k], u, B[i + R * j]);
+    }
+    const double inv = LU[j + N * j];
+    SSB_UNROLL
+    for (int i = 0; i < R; ++i) B[i + R * j] *= inv;
+  }
+  // Y L = X : backward over columns (unit diagonal)
+  SSB_UNROLL
+  for (int j = N - 2; j >= 0; --j) {
+    SSB_UNROLL
+    for (int k = j + 1; k < N; ++k) {
+      const double l = LU[k + N * j];
+      SSB_UNROLL
+      for (int i = 0; i < R; ++i) B[i + R * j] = fma(-B[i + R * k], l, B[i + R * j]);
+    }
+  }
+}
+
+// Cholesky factor of a symmetric positive definite matrix (lower triangle of A
+// read, L written in the lower triangle, reciprocal diagonal in `dinv`).
+template <int N>
+SSB_HDI void sm_cholesky(double *A, double *dinv) {
+  SSB_UNROLL
+  for (int j = 0; j < N; ++j) {
+    double d = A[j + N * j];
+    SSB_UNROLL
+    for (int k = 0; k < j; ++k) d = fma(-A[j + N * k], A[j + N * k], d);
+    const double l = sqrt(d);
+    const double inv = 1.0 / l;
+    A[j + N * j] = l;
+    dinv[j] = inv;
+    SSB_UNROLL
+    for (int i = j + 1; i < N; ++i) {
+      double s = A[i + N * j];
+      SSB_UNROLL
+      for (int k = 0; k < j; ++k) s = fma(-A[i + N * k], A[j + N * k], s);
+      A[i + N * j] = s * inv;
+    }
+  }
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric matrix (full storage):
+// on return A holds the eigenvalues on its diagonal and U the orthonormal
+// eigenvectors (columns).  A fixed number of sweeps keeps warps convergent;
+// rotations whose pivot is already negligible are skipped by predication.
+template <int N>
+SSB_HDI void sm_jacobi(double *A, double *U, double *eval, int nsweep) {
+  SSB_UNROLL
+  for (int j = 0; j < N; ++j) {
+    SSB_UNROLL
+    for (int i = 0; i < N; ++i) U[i + N * j] = (i == j) ? 1.0 : 0.0;
+  }
+  for (int sweep = 0; sweep < nsweep; ++sweep) {
+    SSB_UNROLL
+    for (int p = 0; p < N - 1; ++p) {
+      SSB_UNROLL
+      for (int q = p + 1; q < N; ++q) {
+        const double apq = A[p + N * q];
+        const double app = A[p + N * p], aqq = A[q + N * q];
+        // skip when the rotation would not change the diagonal to working precision
+        const bool tiny = fabs(apq) <= 1.0e-300 || fabs(apq) < 1.0e-19 * (fabs(app) + fabs(aqq));
+        const double theta = 0.5 * (aqq - app) / (tiny ? 1.0 : apq);
+        const double t0 = 1.0 / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+        const double t = tiny ? 0.0 : (theta < 0.0 ? -t0 : t0);
+        const double c = 1.0 / sqrt(fma(t, t, 1.0));
+        const double s = t * c;
+        const double tau = s / (1.0 + c);
+        A[p + N * p] = fma(-t, apq, app);
+        A[q + N * q] = fma(t, apq, aqq);
+        A[p + N * q] = 0.0;
+        A[q + N * p] = 0.0;
+        SSB_UNROLL
+        for (int k = 0; k < N; ++k) {
+          if (k != p && k != q) {
+            const double akp = A[k + N * p], akq = A[k + N * q];
+            const double nkp = fma(-s, fma(tau, akp, akq), akp);
+            const double nkq = fma(s, fma(-tau, akq, akp), akq);
+            A[k + N * p] = nkp;
+            A[p + N * k] = nkp;
+            A[k + N * q] = nkq;
+            A[q + N * k] = nkq;
+          }
+        }
+        SSB_UNROLL
+        for (int k = 0; k < N; ++k) {
+          const double ukp = U[k + N * p], ukq = U[k + N * q];
+          U[k + N * p] = fma(-s, fma(tau, ukp, ukq), ukp);
+          U[k + N * q] = fma(s, fma(-tau, ukq, ukp), ukq);
+        }
+      }
+    }
+  }
+  SSB_UNROLL
+  for (int i = 0; i < N; ++i) eval[i] = A[i + N * i];
+}
+
+}  // namespace ssb

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../spartacus_surface_b200/csrc/ssb_driver.hpp"
+#include "../../spartacus_surface_b200/csrc/ssb_fast_layer.cuh"
 
 namespace {
 
@@ -14,6 +15,7 @@ struct HostBackend {
   const ssb::Plan *plan = nullptr;
   std::vector<double> buf;
   int status = 0;
+  bool fast = false;  // use the register-resident layer bodies where they exist (ns <= 2)
   size_t budget = (size_t)1 << 22;  // small on purpose: exercises the chunk loop
   const int *dev_cols(const ssb::Plan &p, size_t off) { return p.all_cols.data() + off; }
   const int *dev_nlay() { return plan->nlay.data(); }
@@ -30,12 +32,34 @@ struct HostBackend {
   template <int NS>
   void layer_sw(const ssb::ClassArgs &a, long nt) {
     const long width = (long)a.ncols * a.cfg.nspec;
-    for (long t = 0; t < nt; ++t) ssb::layer_problem_sw<NS>(a, (int)(t % width), (int)(t / width));
+    const bool f = fast && a.cfg.ns == NS && NS <= 2;
+    for (long t = 0; t < nt; ++t) {
+      const int q = (int)(t % width), lev = (int)(t / width);
+      if (f && a.cfg.nreg == 1)
+        ssb::fast_layer_problem_sw<1, (NS <= 2 ? NS : 1)>(a, q, lev);
+      else if (f && a.cfg.nreg == 2)
+        ssb::fast_layer_problem_sw<2, (NS <= 2 ? NS : 1)>(a, q, lev);
+      else if (f && a.cfg.nreg == 3)
+        ssb::fast_layer_problem_sw<3, (NS <= 2 ? NS : 1)>(a, q, lev);
+      else
+        ssb::layer_problem_sw<NS>(a, q, lev);
+    }
   }
   template <int NS>
   void layer_lw(const ssb::ClassArgs &a, long nt) {
     const long width = (long)a.ncols * a.cfg.nspec;
-    for (long t = 0; t < nt; ++t) ssb::layer_problem_lw<NS>(a, (int)(t % width), (int)(t / width));
+    const bool f = fast && a.cfg.ns == NS && NS <= 2;
+    for (long t = 0; t < nt; ++t) {
+      const int q = (int)(t % width), lev = (int)(t / width);
+      if (f && a.cfg.nreg == 1)
+        ssb::fast_layer_problem_lw<1, (NS <= 2 ? NS : 1)>(a, q, lev);
+      else if (f && a.cfg.nreg == 2)
+        ssb::fast_layer_problem_lw<2, (NS <= 2 ? NS : 1)>(a, q, lev);
+      else if (f && a.cfg.nreg == 3)
+        ssb::fast_layer_problem_lw<3, (NS <= 2 ? NS : 1)>(a, q, lev);
+      else
+        ssb::layer_problem_lw<NS>(a, q, lev);
+    }
   }
   template <int NS>
   void sweeps_sw(const ssb::ClassArgs &a, long nt) {
@@ -57,7 +81,8 @@ extern "C" int hostcheck_radsurf(const ssb200_config *config, const ssb200_canop
                                  const ssb200_sw_spectral_properties *sw, const ssb200_lw_spectral_properties *lw,
                                  ssb200_boundary_conds_out *bc, int32_t istartcol, int32_t iendcol,
                                  ssb200_canopy_flux *sw_dir, ssb200_canopy_flux *sw_diff,
-                                 ssb200_canopy_flux *lw_int, ssb200_canopy_flux *lw_norm, int64_t budget_doubles) {
+                                 ssb200_canopy_flux *lw_int, ssb200_canopy_flux *lw_norm, int64_t budget_doubles,
+                                 int32_t fast) {
   ssb::CallArgs ca{config, cp, sw, lw, bc, sw_dir, sw_diff, lw_int, lw_norm};
   std::string err;
   int rc = ssb::validate_call(ca, err);
@@ -76,6 +101,7 @@ extern "C" int hostcheck_radsurf(const ssb200_config *config, const ssb200_canop
   HostBackend be;
   be.plan = &plan;
   if (budget_doubles > 0) be.budget = (size_t)budget_doubles;
+  be.fast = fast != 0;
   ssb::Dispatcher<HostBackend> disp(be);
   rc = disp.run(ca, plan, err);
   if (rc) {

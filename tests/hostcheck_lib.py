@@ -34,17 +34,17 @@ def load():
         lib.hostcheck_radsurf.argtypes = [P(_abi.Config), P(_abi.CanopyProperties), P(_abi.SwSpectralProperties),
                                           P(_abi.LwSpectralProperties), P(_abi.BoundaryCondsOut), C.c_int32,
                                           C.c_int32, P(_abi.CanopyFlux), P(_abi.CanopyFlux), P(_abi.CanopyFlux),
-                                          P(_abi.CanopyFlux), C.c_int64]
+                                          P(_abi.CanopyFlux), C.c_int64, C.c_int32]
         _lib = lib
     return _lib
 
 
-def make_solver(budget_doubles=0):
+def make_solver(budget_doubles=0, fast=False):
     def solver(config, canopy_props, sw, lw, bc_out, istartcol=None, iendcol=None,
                sw_norm_dir=None, sw_norm_diff=None, lw_internal=None, lw_norm=None):
         structs = marshal(config, canopy_props, sw, lw, bc_out, sw_norm_dir, sw_norm_diff, lw_internal, lw_norm)
         rc = call_radsurf(load().hostcheck_radsurf, structs, istartcol, iendcol,
-                          extra=(C.c_int64(budget_doubles),))
+                          extra=(C.c_int64(budget_doubles), C.c_int32(1 if fast else 0)))
         if rc < 0:
             raise RuntimeError(f"hostcheck_radsurf failed rc={rc}")
         return rc

@@ -68,3 +68,15 @@ def test_column_range_leaves_other_columns_untouched():
             assert np.array_equal(v[lo:hi], full[name][k][lo:hi]), (name, k)
             outside = np.concatenate([v[:lo].ravel(), v[hi:].ravel()])
             assert np.all(outside == 7.0), (name, k)
+
+
+@pytest.mark.parametrize("case", golden_io.list_cases())
+def test_fast_layer_math_within_sensitivity(case):
+    """The register-resident layer formulation (symmetrised Jacobi eigenproblem, sum/difference
+    two-point solve; csrc/ssb_fast_math.cuh) against the oracle, tolerance of tests/parity.py."""
+    import parity
+    _, got = _run(case, hostcheck_lib.make_solver(fast=True))
+    _, ora = _run(case, oracle_lib.make_solver())
+    _, orb = _run(case, oracle_lib.make_solver(nofma=True))
+    ok, worst, lines = parity.check(got, ora, orb)
+    assert ok, "\n".join(lines)
