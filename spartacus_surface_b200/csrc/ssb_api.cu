@@ -221,10 +221,24 @@ struct CudaBackend {
   }
   template <int NS>
   void sweeps_sw(const ssb::ClassArgs &a, long nt) {
+    if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
+      tick(1, true);
+      const bool done = ssb::fast_sweeps_sw<NS>(a, nt, cx.stream);
+      if (done) check_launch();
+      tick(1, false);
+      if (done) return;
+    }
     launch(ssb::launch_sweeps_sw<NS>, a, nt, 1);
   }
   template <int NS>
   void sweeps_lw(const ssb::ClassArgs &a, long nt) {
+    if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
+      tick(3, true);
+      const bool done = ssb::fast_sweeps_lw<NS>(a, nt, cx.stream);
+      if (done) check_launch();
+      tick(3, false);
+      if (done) return;
+    }
     launch(ssb::launch_sweeps_lw<NS>, a, nt, 3);
   }
   void surface(const ssb::SurfaceArgs &s, int nsw_threads, int nlw_threads) {

@@ -8,6 +8,7 @@
 
 #include "../../spartacus_surface_b200/csrc/ssb_driver.hpp"
 #include "../../spartacus_surface_b200/csrc/ssb_fast_layer.cuh"
+#include "../../spartacus_surface_b200/csrc/ssb_fast_sweeps.cuh"
 
 namespace {
 
@@ -61,12 +62,36 @@ struct HostBackend {
         ssb::layer_problem_lw<NS>(a, q, lev);
     }
   }
+  template <int NS, bool LW, int NREG, bool URBAN>
+  void fast_sweeps(const ssb::ClassArgs &a, long nt) {
+    for (long t = 0; t < nt; ++t) {
+      if (LW)
+        ssb::fast_column_sweeps_lw<NREG, (NS <= 2 ? NS : 1), URBAN>(a, (int)t);
+      else
+        ssb::fast_column_sweeps_sw<NREG, (NS <= 2 ? NS : 1), URBAN>(a, (int)t);
+    }
+  }
+  template <int NS, bool LW>
+  bool try_fast_sweeps(const ssb::ClassArgs &a, long nt) {
+    if (!(fast && a.cfg.ns == NS && NS <= 2)) return false;
+    switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
+      case 2: fast_sweeps<NS, LW, 1, false>(a, nt); return true;
+      case 3: fast_sweeps<NS, LW, 1, true>(a, nt); return true;
+      case 4: fast_sweeps<NS, LW, 2, false>(a, nt); return true;
+      case 5: fast_sweeps<NS, LW, 2, true>(a, nt); return true;
+      case 6: fast_sweeps<NS, LW, 3, false>(a, nt); return true;
+      case 7: fast_sweeps<NS, LW, 3, true>(a, nt); return true;
+      default: return false;
+    }
+  }
   template <int NS>
   void sweeps_sw(const ssb::ClassArgs &a, long nt) {
+    if (try_fast_sweeps<NS, false>(a, nt)) return;
     for (long t = 0; t < nt; ++t) ssb::column_sweeps_sw<NS>(a, (int)t);
   }
   template <int NS>
   void sweeps_lw(const ssb::ClassArgs &a, long nt) {
+    if (try_fast_sweeps<NS, true>(a, nt)) return;
     for (long t = 0; t < nt; ++t) ssb::column_sweeps_lw<NS>(a, (int)t);
   }
   void surface(const ssb::SurfaceArgs &s, int nsw_threads, int nlw_threads) {
