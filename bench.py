@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--generic", action="store_true", help="force the generic kernels")
+    ap.add_argument("--minblocks", type=int, default=0, help="launch-bounds variant of the fast layer kernels")
+    ap.add_argument("--minblocks-sweeps", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -183,6 +185,10 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     if args.generic:
         lib.ssb200_set_option(b"fast_kernels", 0)
+    if args.minblocks:
+        lib.ssb200_set_option(b"fast_minblocks", args.minblocks)
+    if args.minblocks_sweeps:
+        lib.ssb200_set_option(b"fast_minblocks_sweeps", args.minblocks_sweeps)
 
     cfg = make_config(args.streams).consolidate()
     ncol = args.columns

@@ -154,6 +154,7 @@ struct Context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaError_t first_error = cudaSuccess;
   int fast_mode = 1;
+  int fast_minblocks = 2, fast_minblocks_sweeps = 2;  // __launch_bounds__ min blocks of the fast kernels
 };
 Context g_ctx;
 
@@ -201,7 +202,7 @@ struct CudaBackend {
   void layer_sw(const ssb::ClassArgs &a, long nt) {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(0, true);
-      const bool done = ssb::fast_layer_sw<NS>(a, nt, cx.stream);
+      const bool done = ssb::fast_layer_sw<NS>(a, nt, cx.stream, cx.fast_minblocks);
       if (done) check_launch();
       tick(0, false);
       if (done) return;
@@ -212,7 +213,7 @@ struct CudaBackend {
   void layer_lw(const ssb::ClassArgs &a, long nt) {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(2, true);
-      const bool done = ssb::fast_layer_lw<NS>(a, nt, cx.stream);
+      const bool done = ssb::fast_layer_lw<NS>(a, nt, cx.stream, cx.fast_minblocks);
       if (done) check_launch();
       tick(2, false);
       if (done) return;
@@ -223,7 +224,7 @@ struct CudaBackend {
   void sweeps_sw(const ssb::ClassArgs &a, long nt) {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(1, true);
-      const bool done = ssb::fast_sweeps_sw<NS>(a, nt, cx.stream);
+      const bool done = ssb::fast_sweeps_sw<NS>(a, nt, cx.stream, cx.fast_minblocks_sweeps);
       if (done) check_launch();
       tick(1, false);
       if (done) return;
@@ -234,7 +235,7 @@ struct CudaBackend {
   void sweeps_lw(const ssb::ClassArgs &a, long nt) {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(3, true);
-      const bool done = ssb::fast_sweeps_lw<NS>(a, nt, cx.stream);
+      const bool done = ssb::fast_sweeps_lw<NS>(a, nt, cx.stream, cx.fast_minblocks_sweeps);
       if (done) check_launch();
       tick(3, false);
       if (done) return;
@@ -667,6 +668,14 @@ int ssb200_set_option(const char *name, int64_t value) {
   }
   if (n == "fast_kernels") {
     g_ctx.fast_mode = value != 0;
+    return 0;
+  }
+  if (n == "fast_minblocks") {
+    g_ctx.fast_minblocks = (int)value;
+    return 0;
+  }
+  if (n == "fast_minblocks_sweeps") {
+    g_ctx.fast_minblocks_sweeps = (int)value;
     return 0;
   }
   return fail(SSB200_ERR_ARG, "unknown option " + n);

@@ -11,84 +11,118 @@ namespace ssb {
 constexpr int kFastBlock = 128;
 
 #ifdef SSB_KIND_SW
-template <int NREG, int NS>
-__global__ void __launch_bounds__(kFastBlock) k_fast_layer_sw(ClassArgs a, long nt) {
+template <int NREG, int NS, int MINB>
+__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_sw(ClassArgs a, long nt) {
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
   const long width = (long)a.ncols * a.cfg.nspec;
   fast_layer_problem_sw<NREG, NS>(a, (int)(t % width), (int)(t / width));
 }
-template <>
-bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
-  if (a.cfg.ns != SSB_NS) return false;
+template <int NREG, int NS>
+static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
+  if (minb >= 4)
+    k_fast_layer_sw<NREG, NS, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
+  else if (minb == 3)
+    k_fast_layer_sw<NREG, NS, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
+  else
+    k_fast_layer_sw<NREG, NS, 2><<<grid, kFastBlock, 0, st>>>(a, nt);
+}
+template <>
+bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
+  if (a.cfg.ns != SSB_NS) return false;
   switch (a.cfg.nreg) {
-    case 1: k_fast_layer_sw<1, SSB_NS><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 2: k_fast_layer_sw<2, SSB_NS><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 3: k_fast_layer_sw<3, SSB_NS><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
+    case 1: launch_fast_layer_sw<1, SSB_NS>(a, nt, st, minb); return true;
+    case 2: launch_fast_layer_sw<2, SSB_NS>(a, nt, st, minb); return true;
+    case 3: launch_fast_layer_sw<3, SSB_NS>(a, nt, st, minb); return true;
     default: return false;
   }
 }
-template <int NREG, int NS, bool URBAN>
-__global__ void __launch_bounds__(kFastBlock) k_fast_sweeps_sw(ClassArgs a, long nt) {
+template <int NREG, int NS, bool URBAN, int MINB>
+__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_sweeps_sw(ClassArgs a, long nt) {
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
   fast_column_sweeps_sw<NREG, NS, URBAN>(a, (int)t);
 }
-template <>
-bool fast_sweeps_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
-  if (a.cfg.ns != SSB_NS) return false;
+template <int NREG, int NS, bool URBAN>
+static void launch_fast_sweeps_sw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
-  const int key = a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0);
-  switch (key) {
-    case 2: k_fast_sweeps_sw<1, SSB_NS, false><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 3: k_fast_sweeps_sw<1, SSB_NS, true><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 4: k_fast_sweeps_sw<2, SSB_NS, false><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 5: k_fast_sweeps_sw<2, SSB_NS, true><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 6: k_fast_sweeps_sw<3, SSB_NS, false><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 7: k_fast_sweeps_sw<3, SSB_NS, true><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
+  if (minb >= 4)
+    k_fast_sweeps_sw<NREG, NS, URBAN, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
+  else if (minb == 3)
+    k_fast_sweeps_sw<NREG, NS, URBAN, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
+  else
+    k_fast_sweeps_sw<NREG, NS, URBAN, 2><<<grid, kFastBlock, 0, st>>>(a, nt);
+}
+template <>
+bool fast_sweeps_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
+  if (a.cfg.ns != SSB_NS) return false;
+  switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
+    case 2: launch_fast_sweeps_sw<1, SSB_NS, false>(a, nt, st, minb); return true;
+    case 3: launch_fast_sweeps_sw<1, SSB_NS, true>(a, nt, st, minb); return true;
+    case 4: launch_fast_sweeps_sw<2, SSB_NS, false>(a, nt, st, minb); return true;
+    case 5: launch_fast_sweeps_sw<2, SSB_NS, true>(a, nt, st, minb); return true;
+    case 6: launch_fast_sweeps_sw<3, SSB_NS, false>(a, nt, st, minb); return true;
+    case 7: launch_fast_sweeps_sw<3, SSB_NS, true>(a, nt, st, minb); return true;
     default: return false;
   }
 }
 #endif
 
 #ifdef SSB_KIND_LW
-template <int NREG, int NS>
-__global__ void __launch_bounds__(kFastBlock) k_fast_layer_lw(ClassArgs a, long nt) {
+template <int NREG, int NS, int MINB>
+__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_lw(ClassArgs a, long nt) {
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
   const long width = (long)a.ncols * a.cfg.nspec;
   fast_layer_problem_lw<NREG, NS>(a, (int)(t % width), (int)(t / width));
 }
-template <>
-bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
-  if (a.cfg.ns != SSB_NS) return false;
+template <int NREG, int NS>
+static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
+  if (minb >= 4)
+    k_fast_layer_lw<NREG, NS, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
+  else if (minb == 3)
+    k_fast_layer_lw<NREG, NS, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
+  else
+    k_fast_layer_lw<NREG, NS, 2><<<grid, kFastBlock, 0, st>>>(a, nt);
+}
+template <>
+bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
+  if (a.cfg.ns != SSB_NS) return false;
   switch (a.cfg.nreg) {
-    case 1: k_fast_layer_lw<1, SSB_NS><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 2: k_fast_layer_lw<2, SSB_NS><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 3: k_fast_layer_lw<3, SSB_NS><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
+    case 1: launch_fast_layer_lw<1, SSB_NS>(a, nt, st, minb); return true;
+    case 2: launch_fast_layer_lw<2, SSB_NS>(a, nt, st, minb); return true;
+    case 3: launch_fast_layer_lw<3, SSB_NS>(a, nt, st, minb); return true;
     default: return false;
   }
 }
-template <int NREG, int NS, bool URBAN>
-__global__ void __launch_bounds__(kFastBlock) k_fast_sweeps_lw(ClassArgs a, long nt) {
+template <int NREG, int NS, bool URBAN, int MINB>
+__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_sweeps_lw(ClassArgs a, long nt) {
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
   fast_column_sweeps_lw<NREG, NS, URBAN>(a, (int)t);
 }
-template <>
-bool fast_sweeps_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
-  if (a.cfg.ns != SSB_NS) return false;
+template <int NREG, int NS, bool URBAN>
+static void launch_fast_sweeps_lw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
-  const int key = a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0);
-  switch (key) {
-    case 2: k_fast_sweeps_lw<1, SSB_NS, false><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 3: k_fast_sweeps_lw<1, SSB_NS, true><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 4: k_fast_sweeps_lw<2, SSB_NS, false><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 5: k_fast_sweeps_lw<2, SSB_NS, true><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 6: k_fast_sweeps_lw<3, SSB_NS, false><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
-    case 7: k_fast_sweeps_lw<3, SSB_NS, true><<<grid, kFastBlock, 0, st>>>(a, nt); return true;
+  if (minb >= 4)
+    k_fast_sweeps_lw<NREG, NS, URBAN, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
+  else if (minb == 3)
+    k_fast_sweeps_lw<NREG, NS, URBAN, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
+  else
+    k_fast_sweeps_lw<NREG, NS, URBAN, 2><<<grid, kFastBlock, 0, st>>>(a, nt);
+}
+template <>
+bool fast_sweeps_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
+  if (a.cfg.ns != SSB_NS) return false;
+  switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
+    case 2: launch_fast_sweeps_lw<1, SSB_NS, false>(a, nt, st, minb); return true;
+    case 3: launch_fast_sweeps_lw<1, SSB_NS, true>(a, nt, st, minb); return true;
+    case 4: launch_fast_sweeps_lw<2, SSB_NS, false>(a, nt, st, minb); return true;
+    case 5: launch_fast_sweeps_lw<2, SSB_NS, true>(a, nt, st, minb); return true;
+    case 6: launch_fast_sweeps_lw<3, SSB_NS, false>(a, nt, st, minb); return true;
+    case 7: launch_fast_sweeps_lw<3, SSB_NS, true>(a, nt, st, minb); return true;
     default: return false;
   }
 }

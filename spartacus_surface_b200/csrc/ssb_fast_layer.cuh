@@ -41,13 +41,14 @@ SSB_HDI void fast_sw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
   constexpr int N = NR * NS;
   const SolveCfg &c = a.cfg;
   constexpr int r0 = R0;
-  double g0[NR * NR], g1[N * N], g2[N * N], g3[N * NR], nsc[N], frac[NR];
+  // D = G1-G2 (exchange and loss, no scattering), S = G1+G2 = D + 2 G2
+  double g0[NR * NR], Dm[N * N], Sm[N * N], g3[N * NR], nsc[N], ninv[N], frac[NR];
   SSB_UNROLL
   for (int i = 0; i < NR * NR; ++i) g0[i] = 0.0;
   SSB_UNROLL
   for (int i = 0; i < N * N; ++i) {
-    g1[i] = 0.0;
-    g2[i] = 0.0;
+    Dm[i] = 0.0;
+    Sm[i] = 0.0;
   }
   SSB_UNROLL
   for (int i = 0; i < N * NR; ++i) g3[i] = 0.0;
@@ -61,13 +62,13 @@ SSB_HDI void fast_sw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
       const double fx = gm.f_exchange[Rt + 3 * Rf];
       g0[rf + NR * rf] -= op.tan0 * fx;
       SSB_UNROLL
-      for (int js = 0; js < NS; ++js) g1[(js + rf * NS) * (N + 1)] -= a.lg.tan_ang[js] * fx;
+      for (int js = 0; js < NS; ++js) Dm[(js + rf * NS) * (N + 1)] -= a.lg.tan_ang[js] * fx;
       SSB_UNROLL
       for (int rt = 0; rt < NR; ++rt) {
         if (rt + r0 == Rt) {
           g0[rt + NR * rf] = op.tan0 * fx;
           SSB_UNROLL
-          for (int js = 0; js < NS; ++js) g1[(js + rt * NS) + N * (js + rf * NS)] = a.lg.tan_ang[js] * fx;
+          for (int js = 0; js < NS; ++js) Dm[(js + rt * NS) + N * (js + rf * NS)] = a.lg.tan_ang[js] * fx;
         }
       }
     }
@@ -81,20 +82,22 @@ SSB_HDI void fast_sw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
     SSB_UNROLL
     for (int js = 0; js < NS; ++js) {
       const int i = js + r * NS;
-      g1[i + N * i] = g1[i + N * i] - ext / a.lg.mu[js] - a.lg.tan_ang[js] * fw * op.wall_ext;
-      nsc[i] = 1.0 / (a.lg.weight[js] * a.lg.mu[js] * ((NR == 1) ? 1.0 : gm.frac[Rr]));
+      const double rmu = 1.0 / a.lg.mu[js];
+      Dm[i + N * i] = Dm[i + N * i] - ext * rmu - a.lg.tan_ang[js] * fw * op.wall_ext;
+      ninv[i] = a.lg.weight[js] * a.lg.mu[js] * ((NR == 1) ? 1.0 : gm.frac[Rr]);
+      nsc[i] = 1.0 / ninv[i];
       g3[i + N * r] = 0.5 * (a.lg.weight[js] * es + a.lg.vweight[js] * op.sin0 * fw * op.wall_factor);
       SSB_UNROLL
       for (int jt = 0; jt < NS; ++jt)
-        g2[(jt + r * NS) + N * i] =
-            0.5 * (a.lg.weight[jt] * es / a.lg.mu[js] + a.lg.vweight[jt] * a.lg.tan_ang[js] * fw * op.wall_factor);
+        Sm[(jt + r * NS) + N * i] =
+            a.lg.weight[jt] * es * rmu + a.lg.vweight[jt] * a.lg.tan_ang[js] * fw * op.wall_factor;  // 2 G2
     }
   }
   SSB_UNROLL
-  for (int i = 0; i < N * N; ++i) g1[i] += g2[i];
+  for (int i = 0; i < N * N; ++i) Sm[i] += Dm[i];
 
   double R[N * N], T[N * N], Idiff[N * N], Sup[N * NR], Sdn[N * NR], Idd[N * NR], E[NR * NR], Idir[NR * NR];
-  fast_layer_sw_math<NR, NS>(op.dz, g0, g1, g2, g3, nsc, frac, R, T, Sup, Sdn, E, Idir, Idiff, Idd);
+  fast_layer_sw_math<NR, NS>(op.dz, g0, Dm, Sm, g3, nsc, ninv, frac, R, T, Sup, Sdn, E, Idir, Idiff, Idd);
 
   const int nlev = a.lmax, width = a.ncols * c.nspec;
   int e = 0;
@@ -180,11 +183,11 @@ SSB_HDI void fast_lw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
   constexpr int N = NR * NS;
   const SolveCfg &c = a.cfg;
   constexpr int r0 = R0;
-  double g1[N * N], g2[N * N], nsc[N], brate[N];
+  double Dm[N * N], Sm[N * N], nsc[N], ninv[N], brate[N];
   SSB_UNROLL
   for (int i = 0; i < N * N; ++i) {
-    g1[i] = 0.0;
-    g2[i] = 0.0;
+    Dm[i] = 0.0;
+    Sm[i] = 0.0;
   }
   SSB_UNROLL
   for (int rf = 0; rf < NR; ++rf) {
@@ -194,12 +197,12 @@ SSB_HDI void fast_lw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
       if (Rt == Rf) continue;
       const double fx = gm.f_exchange[Rt + 3 * Rf];
       SSB_UNROLL
-      for (int js = 0; js < NS; ++js) g1[(js + rf * NS) * (N + 1)] -= a.lg.tan_ang[js] * fx;
+      for (int js = 0; js < NS; ++js) Dm[(js + rf * NS) * (N + 1)] -= a.lg.tan_ang[js] * fx;
       SSB_UNROLL
       for (int rt = 0; rt < NR; ++rt) {
         if (rt + r0 == Rt) {
           SSB_UNROLL
-          for (int js = 0; js < NS; ++js) g1[(js + rt * NS) + N * (js + rf * NS)] = a.lg.tan_ang[js] * fx;
+          for (int js = 0; js < NS; ++js) Dm[(js + rt * NS) + N * (js + rf * NS)] = a.lg.tan_ang[js] * fx;
         }
       }
     }
@@ -214,20 +217,22 @@ SSB_HDI void fast_lw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
     SSB_UNROLL
     for (int js = 0; js < NS; ++js) {
       const int i = js + r * NS;
-      g1[i + N * i] = g1[i + N * i] - ext / a.lg.mu[js] - a.lg.tan_ang[js] * fw * op.wall_ext;
-      nsc[i] = 1.0 / (a.lg.weight[js] * a.lg.mu[js] * ((NR == 1) ? 1.0 : gm.frac[Rr]));
-      brate[i] = (a.lg.hweight[js] / a.lg.mu[js]) * volume_emiss + (0.5 * a.lg.vweight[js]) * wall_emiss;
+      const double rmu = 1.0 / a.lg.mu[js];
+      Dm[i + N * i] = Dm[i + N * i] - ext * rmu - a.lg.tan_ang[js] * fw * op.wall_ext;
+      ninv[i] = a.lg.weight[js] * a.lg.mu[js] * ((NR == 1) ? 1.0 : gm.frac[Rr]);
+      nsc[i] = 1.0 / ninv[i];
+      brate[i] = (a.lg.hweight[js] * rmu) * volume_emiss + (0.5 * a.lg.vweight[js]) * wall_emiss;
       SSB_UNROLL
       for (int jt = 0; jt < NS; ++jt)
-        g2[(jt + r * NS) + N * i] =
-            0.5 * (a.lg.weight[jt] * es / a.lg.mu[js] + a.lg.vweight[jt] * a.lg.tan_ang[js] * fw * op.wall_factor);
+        Sm[(jt + r * NS) + N * i] =
+            a.lg.weight[jt] * es * rmu + a.lg.vweight[jt] * a.lg.tan_ang[js] * fw * op.wall_factor;  // 2 G2
     }
   }
   SSB_UNROLL
-  for (int i = 0; i < N * N; ++i) g1[i] += g2[i];
+  for (int i = 0; i < N * N; ++i) Sm[i] += Dm[i];
 
   double R[N * N], T[N * N], IF[N * N], src[N], isrc[N];
-  fast_layer_lw_math<NR, NS>(op.dz, g1, g2, brate, nsc, R, T, src, IF, isrc);
+  fast_layer_lw_math<NR, NS>(op.dz, Dm, Sm, brate, nsc, ninv, R, T, src, IF, isrc);
 
   constexpr int n = NREG * NS;
   const int nlev = a.lmax, width = a.ncols * c.nspec;

@@ -137,42 +137,73 @@ SSB_HDI void sm_cholesky(double *A, double *dinv) {
   }
 }
 
+// warp-uniform "everybody converged" vote (plain value on the host)
+SSB_HDI bool all_lanes(bool pred) {
+#if defined(__CUDA_ARCH__)
+  return __all_sync(__activemask(), pred);
+#else
+  return pred;
+#endif
+}
+
+SSB_HDI double rsqrt_pos(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // Cyclic Jacobi eigen-decomposition of a symmetric matrix (full storage):
 // on return A holds the eigenvalues on its diagonal and U the orthonormal
-// eigenvectors (columns).  A fixed number of sweeps keeps warps convergent;
-// rotations whose pivot is already negligible are skipped by predication.
+// eigenvectors (columns).  The rotation parameters come from two reciprocal
+// square roots (no division):  with alpha = (aqq-app)/2, beta = apq,
+// h = sqrt(alpha^2+beta^2):  cos^2 = (1 + |alpha|/h)/2,
+// sin = sign(alpha) beta / (2 h cos).  Sweeps stop when every lane of the warp
+// has converged (off-diagonal mass below eps^2 of the diagonal mass) or after
+// `max_sweeps`; the pair loops are unrolled so all indices stay static.
 template <int N>
-SSB_HDI void sm_jacobi(double *A, double *U, double *eval, int nsweep) {
+SSB_HDI void sm_jacobi(double *A, double *U, double *eval, int max_sweeps) {
   SSB_UNROLL
   for (int j = 0; j < N; ++j) {
     SSB_UNROLL
     for (int i = 0; i < N; ++i) U[i + N * j] = (i == j) ? 1.0 : 0.0;
   }
-  for (int sweep = 0; sweep < nsweep; ++sweep) {
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    SSB_UNROLL
+    for (int p = 0; p < N; ++p) {
+      diag = fma(A[p + N * p], A[p + N * p], diag);
+      SSB_UNROLL
+      for (int q = p + 1; q < N; ++q) off = fma(A[p + N * q], A[p + N * q], off);
+    }
+    if (all_lanes(off <= 1.0e-33 * diag)) break;
     SSB_UNROLL
     for (int p = 0; p < N - 1; ++p) {
       SSB_UNROLL
       for (int q = p + 1; q < N; ++q) {
-        const double apq = A[p + N * q];
+        const double beta = A[p + N * q];
         const double app = A[p + N * p], aqq = A[q + N * q];
-        // skip when the rotation would not change the diagonal to working precision
-        const bool tiny = fabs(apq) <= 1.0e-300 || fabs(apq) < 1.0e-19 * (fabs(app) + fabs(aqq));
-        const double theta = 0.5 * (aqq - app) / (tiny ? 1.0 : apq);
-        const double t0 = 1.0 / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-        const double t = tiny ? 0.0 : (theta < 0.0 ? -t0 : t0);
-        const double c = 1.0 / sqrt(fma(t, t, 1.0));
-        const double s = t * c;
-        const double tau = s / (1.0 + c);
-        A[p + N * p] = fma(-t, apq, app);
-        A[q + N * q] = fma(t, apq, aqq);
+        const double alpha = 0.5 * (aqq - app);
+        const double h2 = fma(alpha, alpha, beta * beta);
+        // negligible pivot (or an exactly zero 2x2 block): identity rotation
+        const bool skip = !(beta * beta > 1.0e-40 * h2);
+        const double rh = rsqrt_pos(skip ? 1.0 : h2);
+        const double x = fma(0.5 * fabs(alpha), rh, 0.5);
+        const double rc = rsqrt_pos(x);
+        const double c = skip ? 1.0 : x * rc;
+        const double s = skip ? 0.0 : (alpha < 0.0 ? -0.5 : 0.5) * beta * rh * rc;
+        const double t = s * rc;  // tan = sin / cos
+        A[p + N * p] = fma(-t, beta, app);
+        A[q + N * q] = fma(t, beta, aqq);
         A[p + N * q] = 0.0;
         A[q + N * p] = 0.0;
         SSB_UNROLL
         for (int k = 0; k < N; ++k) {
           if (k != p && k != q) {
             const double akp = A[k + N * p], akq = A[k + N * q];
-            const double nkp = fma(-s, fma(tau, akp, akq), akp);
-            const double nkq = fma(s, fma(-tau, akq, akp), akq);
+            const double nkp = fma(c, akp, -(s * akq));
+            const double nkq = fma(s, akp, c * akq);
             A[k + N * p] = nkp;
             A[p + N * k] = nkp;
             A[k + N * q] = nkq;
@@ -182,8 +213,8 @@ SSB_HDI void sm_jacobi(double *A, double *U, double *eval, int nsweep) {
         SSB_UNROLL
         for (int k = 0; k < N; ++k) {
           const double ukp = U[k + N * p], ukq = U[k + N * q];
-          U[k + N * p] = fma(-s, fma(tau, ukp, ukq), ukp);
-          U[k + N * q] = fma(s, fma(-tau, ukq, ukp), ukq);
+          U[k + N * p] = fma(c, ukp, -(s * ukq));
+          U[k + N * q] = fma(s, ukp, c * ukq);
         }
       }
     }
