@@ -154,7 +154,7 @@ struct Context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaError_t first_error = cudaSuccess;
   int fast_mode = 1;
-  int fast_minblocks = 2, fast_minblocks_sweeps = 2;  // __launch_bounds__ min blocks of the fast kernels
+  int fast_minblocks = 3, fast_minblocks_sweeps = 2;  // __launch_bounds__ min blocks of the fast kernels
 };
 Context g_ctx;
 

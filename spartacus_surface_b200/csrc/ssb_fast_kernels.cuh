@@ -40,19 +40,26 @@ bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int min
 }
 template <int NREG, int NS, bool URBAN, int MINB>
 __global__ void __launch_bounds__(kFastBlock, MINB) k_fast_sweeps_sw(ClassArgs a, long nt) {
+  extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
-  fast_column_sweeps_sw<NREG, NS, URBAN>(a, (int)t);
+  const StateMem st{ssb_state + threadIdx.x, (int)blockDim.x};
+  fast_column_sweeps_sw<NREG, NS, URBAN>(a, (int)t, st);
 }
 template <int NREG, int NS, bool URBAN>
 static void launch_fast_sweeps_sw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
-  if (minb >= 4)
-    k_fast_sweeps_sw<NREG, NS, URBAN, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
-  else if (minb == 3)
-    k_fast_sweeps_sw<NREG, NS, URBAN, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
-  else
-    k_fast_sweeps_sw<NREG, NS, URBAN, 2><<<grid, kFastBlock, 0, st>>>(a, nt);
+  const size_t smem = sizeof(double) * SwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
+  if (minb >= 4) {
+    cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fast_sweeps_sw<NREG, NS, URBAN, 4><<<grid, kFastBlock, smem, st>>>(a, nt);
+  } else if (minb == 3) {
+    cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fast_sweeps_sw<NREG, NS, URBAN, 3><<<grid, kFastBlock, smem, st>>>(a, nt);
+  } else {
+    cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fast_sweeps_sw<NREG, NS, URBAN, 2><<<grid, kFastBlock, smem, st>>>(a, nt);
+  }
 }
 template <>
 bool fast_sweeps_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
@@ -99,19 +106,26 @@ bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int min
 }
 template <int NREG, int NS, bool URBAN, int MINB>
 __global__ void __launch_bounds__(kFastBlock, MINB) k_fast_sweeps_lw(ClassArgs a, long nt) {
+  extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
-  fast_column_sweeps_lw<NREG, NS, URBAN>(a, (int)t);
+  const StateMem st{ssb_state + threadIdx.x, (int)blockDim.x};
+  fast_column_sweeps_lw<NREG, NS, URBAN>(a, (int)t, st);
 }
 template <int NREG, int NS, bool URBAN>
 static void launch_fast_sweeps_lw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
-  if (minb >= 4)
-    k_fast_sweeps_lw<NREG, NS, URBAN, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
-  else if (minb == 3)
-    k_fast_sweeps_lw<NREG, NS, URBAN, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
-  else
-    k_fast_sweeps_lw<NREG, NS, URBAN, 2><<<grid, kFastBlock, 0, st>>>(a, nt);
+  const size_t smem = sizeof(double) * LwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
+  if (minb >= 4) {
+    cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fast_sweeps_lw<NREG, NS, URBAN, 4><<<grid, kFastBlock, smem, st>>>(a, nt);
+  } else if (minb == 3) {
+    cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fast_sweeps_lw<NREG, NS, URBAN, 3><<<grid, kFastBlock, smem, st>>>(a, nt);
+  } else {
+    cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fast_sweeps_lw<NREG, NS, URBAN, 2><<<grid, kFastBlock, smem, st>>>(a, nt);
+  }
 }
 template <>
 bool fast_sweeps_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {

@@ -3,39 +3,42 @@
 //
 // Same recurrences and outputs as column_sweeps_sw/_lw of ssb_solver.cuh
 // (radsurf_urban_sw.F90:591-984, radsurf_urban_lw.F90:552-858 and the forest
-// equivalents) with two changes that cut the inter-sweep state:
+// equivalents), organised around HBM traffic, which bounds these kernels:
 //  * only a_above, d_above (or source_above) and the LU factors of the
 //    denominator I - a_above R are kept per interface; the "below" albedo
 //    matrices (which carry the extra roof region) are never formed in the
-//    downward passes - their action on a flux vector is evaluated as
+//    downward pass - their action on a flux vector is evaluated as
 //      a_below x = R x + T D^-1 (a_above (T x))   (+ the roof block),
-//    and likewise for d_below and source_below;
+//    and likewise for d_below and source_below (SURVEY F6);
 //  * the overlap matrices U, V are recomputed from the region fractions of the
-//    two adjacent layers instead of being stored.
+//    two adjacent layers instead of being stored;
+//  * the two downward passes of the reference (direct and diffuse source in
+//    the shortwave, internal emission and incoming in the longwave) run
+//    together, so every layer matrix is streamed from HBM once per layer and
+//    each loaded element feeds both passes;
+//  * the state carried up the column (a_above, d_above) lives in a per-thread
+//    slice of shared memory (`StateMem`), which keeps the upward sweep inside
+//    the register file.
 #pragma once
 #include "ssb_fast_layer.cuh"
 
 namespace ssb {
 
-template <int N, int C>
-SSB_HDI void sload(const double *S, int e0, int lev, int nlev, int width, int q, double *dst) {
-  SSB_UNROLL
-  for (int i = 0; i < N * C; ++i) dst[i] = S[sidx(e0 + i, lev, nlev, width, q)];
-}
-template <int N, int C>
-SSB_HDI void sstore(double *S, int e0, int lev, int nlev, int width, int q, const double *src) {
-  SSB_UNROLL
-  for (int i = 0; i < N * C; ++i) S[sidx(e0 + i, lev, nlev, width, q)] = src[i];
-}
-// y += A x with A (R x C) read straight from scratch
-template <int R, int C>
-SSB_HDI void smv_acc(const double *S, int e0, int lev, int nlev, int width, int q, const double *x, double *y) {
-  SSB_UNROLL
-  for (int j = 0; j < C; ++j) {
-    SSB_UNROLL
-    for (int i = 0; i < R; ++i) y[i] = fma(S[sidx(e0 + i + R * j, lev, nlev, width, q)], x[j], y[i]);
-  }
-}
+// per-thread state slice: element e at p[e * stride] (shared memory, stride =
+// blockDim.x, on the device; a plain local array on the host)
+struct StateMem {
+  double *p;
+  int stride;
+  SSB_HDI double &operator()(int e) const { return p[(size_t)e * stride]; }
+};
+
+struct Scr {  // one scratch area (layer or interface) of the calling problem
+  const double *base;
+  double *wbase;
+  int nlev, width, q;
+  SSB_HDI double ld(int e, int lev) const { return base[sidx(e, lev, nlev, width, q)]; }
+  SSB_HDI void st(int e, int lev, double v) const { wbase[sidx(e, lev, nlev, width, q)] = v; }
+};
 
 // (V (x) I_NS) x : below-interface vector (NRB*NS) from the above-interface one (NREG*NS)
 template <int NREG, int NRB, int NS>
@@ -52,8 +55,130 @@ SSB_HDI void expand_down(const double *V, const double *x, double *y) {
   }
 }
 
+// y1 += A x1, y2 += A x2 with A (R x C) streamed once from scratch
+template <int R, int C>
+SSB_HDI void smv2(const Scr &S, int e0, int lev, const double *x1, const double *x2, double *y1, double *y2) {
+  SSB_UNROLL
+  for (int j = 0; j < C; ++j) {
+    SSB_UNROLL
+    for (int i = 0; i < R; ++i) {
+      const double a = S.ld(e0 + i + R * j, lev);
+      y1[i] = fma(a, x1[j], y1[i]);
+      y2[i] = fma(a, x2[j], y2[i]);
+    }
+  }
+}
+template <int R, int C>
+SSB_HDI void smv1(const Scr &S, int e0, int lev, const double *x, double *y) {
+  SSB_UNROLL
+  for (int j = 0; j < C; ++j) {
+    SSB_UNROLL
+    for (int i = 0; i < R; ++i) y[i] = fma(S.ld(e0 + i + R * j, lev), x[j], y[i]);
+  }
+}
+
+// One step of the upward adding sweep shared by SW and LW: given a_above (in
+// `st`, n x n at offset 0) and the layer's R, T in scratch, produce
+//   LU  = factors of I - a_above R           (returned in registers, stored to scratch at oLU)
+//   X   = D^-1 (a_above T)                   (n x n)
+//   Wx  = D^-1 (a_above Wa + Wb)             (n x NW extra right-hand sides supplied by the caller
+//                                             through `rhs_extra`, already holding Wb on entry;
+//                                             Wa is streamed from the layer scratch at oWa)
+template <int n, int NW>
+SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl, int oR, int oT, int oWa, int oLU,
+                         double *LU, double *X, double *rhs_extra) {
+  double Aa[n * n];
+  SSB_UNROLL
+  for (int i = 0; i < n * n; ++i) Aa[i] = st(i);
+  SSB_UNROLL
+  for (int j = 0; j < n; ++j) {
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) LU[i + n * j] = (i == j) ? 1.0 : 0.0;
+    SSB_UNROLL
+    for (int k = 0; k < n; ++k) {
+      const double r = L.ld(oR + k + n * j, jl);
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) LU[i + n * j] = fma(-Aa[i + n * k], r, LU[i + n * j]);
+    }
+  }
+  sm_lu<n>(LU);
+  SSB_UNROLL
+  for (int i = 0; i < n * n; ++i) W.st(oLU + i, jl, LU[i]);
+  SSB_UNROLL
+  for (int j = 0; j < n; ++j) {
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) X[i + n * j] = 0.0;
+    SSB_UNROLL
+    for (int k = 0; k < n; ++k) {
+      const double t = L.ld(oT + k + n * j, jl);
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) X[i + n * j] = fma(Aa[i + n * k], t, X[i + n * j]);
+    }
+  }
+  SSB_UNROLL
+  for (int j = 0; j < NW; ++j) {
+    SSB_UNROLL
+    for (int k = 0; k < n; ++k) {
+      const double w = L.ld(oWa + k + n * j, jl);
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) rhs_extra[i + n * j] = fma(Aa[i + n * k], w, rhs_extra[i + n * j]);
+    }
+  }
+  sm_lu_solve_left<n, n>(LU, X);
+  sm_lu_solve_left<n, NW>(LU, rhs_extra);
+}
+
+// a_above(next)[(u,jt),(up,js)] = sum_{lo,lo'} U[u,lo] V[lo',up] Ab[(lo,jt),(lo',js)] + roof term,
+// evaluated per stream pair as a 3x3 "region sandwich" and written to the state slice
+template <int NREG, int NRB, int NS>
+SSB_HDI void overlap_matrix(const double *Ab, const double *rb, const double *U, const double *V,
+                            const StateMem &st, int o) {
+  constexpr int n = NREG * NS;
+  SSB_UNROLL
+  for (int jt = 0; jt < NS; ++jt) {
+    SSB_UNROLL
+    for (int js = 0; js < NS; ++js) {
+      double BV[NREG * NREG];  // [lo + NREG*up]
+      SSB_UNROLL
+      for (int up = 0; up < NREG; ++up) {
+        SSB_UNROLL
+        for (int lo = 0; lo < NREG; ++lo) {
+          double s = 0.0;
+          SSB_UNROLL
+          for (int l2 = 0; l2 < NREG; ++l2) s = fma(Ab[(lo * NS + jt) + n * (l2 * NS + js)], V[l2 + NRB * up], s);
+          BV[lo + NREG * up] = s;
+        }
+      }
+      SSB_UNROLL
+      for (int up = 0; up < NREG; ++up) {
+        SSB_UNROLL
+        for (int u = 0; u < NREG; ++u) {
+          double s = 0.0;
+          SSB_UNROLL
+          for (int lo = 0; lo < NREG; ++lo) s = fma(U[u + NREG * lo], BV[lo + NREG * up], s);
+          if (NRB > NREG) s = fma(U[u + NREG * NREG] * rb[jt], V[NREG + NRB * up], s);
+          st(o + (u * NS + jt) + n * (up * NS + js)) = s;
+        }
+      }
+    }
+  }
+}
+
+// ===========================================================================
+// Shortwave
+// ===========================================================================
 template <int NREG, int NS, bool URBAN>
-SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q) {
+struct SwSweepLayout {
+  static constexpr int n = NREG * NS, d = NREG;
+  static constexpr int oR = 0, oT = n * n, oIdiff = 2 * n * n, oSup = 3 * n * n, oSdn = oSup + n * d,
+                       oIdd = oSdn + n * d, oE = oIdd + n * d, oIdir = oE + d * d;
+  static constexpr int oAa = 0, oDa = n * n, oLU = oDa + n * d;  // interface scratch of the fast path
+  static constexpr int state_doubles = n * n + n * d;
+};
+
+template <int NREG, int NS, bool URBAN>
+SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateMem &st) {
+  typedef SwSweepLayout<NREG, NS, URBAN> Lay;
   constexpr int n = NREG * NS, d = NREG, NRB = URBAN ? NREG + 1 : NREG, m = NRB * NS;
   const SolveCfg &c = a.cfg;
   const int nspec = c.nspec;
@@ -91,66 +216,60 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q) {
     mu_inv[js] = 1.0 / a.lg.mu[js];
     tang[js] = a.lg.tan_ang[js];
   }
-  const double *LS = a.layer;
-  double *WS = a.sweep;
-  const int nlev = a.lmax, wlev = a.lmax + 1;
-  constexpr int oR = 0, oT = n * n, oIdiff = 2 * n * n, oSup = 3 * n * n, oSdn = oSup + n * d, oIdd = oSdn + n * d,
-                oE = oIdd + n * d, oIdir = oE + d * d;
-  constexpr int oAa = 0, oDa = n * n, oLU = oDa + n * d;  // fast-path sweep scratch
+  const Scr L{a.layer, a.layer, a.lmax, width, q};
+  const Scr W{a.sweep, a.sweep, a.lmax + 1, width, q};
 
-  double Aa[n * n], Da[n * d];
-  // ---- upward sweep ---------------------------------------------------------
+  // ---- upward sweep: state = [a_above (n x n) | d_above (n x d)] ------------
   SSB_UNROLL
-  for (int i = 0; i < n * n; ++i) Aa[i] = 0.0;
-  SSB_UNROLL
-  for (int i = 0; i < n * d; ++i) Da[i] = 0.0;
+  for (int i = 0; i < Lay::state_doubles; ++i) st(i) = 0.0;
   SSB_UNROLL
   for (int r = 0; r < NREG; ++r) {
     SSB_UNROLL
     for (int jt = 0; jt < NS; ++jt) {
-      Da[(jt + r * NS) + n * r] = zcos * galb_dir * hw[jt];
+      st(Lay::oDa + (jt + r * NS) + n * r) = zcos * galb_dir * hw[jt];
       SSB_UNROLL
-      for (int jf = 0; jf < NS; ++jf) Aa[(jt + r * NS) + n * (jf + r * NS)] = galb * hw[jt];
+      for (int jf = 0; jf < NS; ++jf) st((jt + r * NS) + n * (jf + r * NS)) = galb * hw[jt];
     }
   }
-  sstore<n, n>(WS, oAa, 0, wlev, width, q, Aa);
-  sstore<n, d>(WS, oDa, 0, wlev, width, q, Da);
+  SSB_UNROLL
+  for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, 0, st(i));
   for (int jl = 0; jl < nlay; ++jl) {
     const int il = il1 + jl;
-    double R[n * n], T[n * n], LU[n * n], X[n * n];
-    sload<n, n>(LS, oR, jl, nlev, width, q, R);
-    sload<n, n>(LS, oT, jl, nlev, width, q, T);
-    sm_mul<n, n, n>(Aa, R, LU);
-    SSB_UNROLL
-    for (int j = 0; j < n; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) LU[i + n * j] = (i == j ? 1.0 : 0.0) - LU[i + n * j];
-    }
-    sm_lu<n>(LU);
-    sstore<n, n>(WS, oLU, jl, wlev, width, q, LU);
-    sm_mul<n, n, n>(Aa, T, X);
-    sm_lu_solve_left<n, n>(LU, X);
-    double Ab[n * n];
-    sm_mul<n, n, n>(T, X, Ab);
-    SSB_UNROLL
-    for (int i = 0; i < n * n; ++i) Ab[i] += R[i];
-    // d_below (street part)
-    double Db[n * d];
+    double X[n * n], Wd[n * d];
     {
-      double Su[n * d], Sd[n * d], E[d * d], W1[n * d], W2[n * d];
-      sload<n, d>(LS, oSup, jl, nlev, width, q, Su);
-      sload<n, d>(LS, oSdn, jl, nlev, width, q, Sd);
-      sload<d, d>(LS, oE, jl, nlev, width, q, E);
-      sm_mul<n, d, d>(Da, E, W1);
-      sm_mul<n, n, d>(Aa, Sd, W2);
+      double LU[n * n];
+      // Wd <- d_above E, then adding_core adds a_above Sdn and applies D^-1
       SSB_UNROLL
-      for (int i = 0; i < n * d; ++i) W1[i] += W2[i];
-      sm_lu_solve_left<n, d>(LU, W1);
-      sm_mul<n, n, d>(T, W1, Db);
-      SSB_UNROLL
-      for (int i = 0; i < n * d; ++i) Db[i] += Su[i];
+      for (int j = 0; j < d; ++j) {
+        SSB_UNROLL
+        for (int i = 0; i < n; ++i) Wd[i + n * j] = 0.0;
+        SSB_UNROLL
+        for (int k = 0; k < d; ++k) {
+          const double e = L.ld(Lay::oE + k + d * j, jl);
+          SSB_UNROLL
+          for (int i = 0; i < n; ++i) Wd[i + n * j] = fma(st(Lay::oDa + i + n * k), e, Wd[i + n * j]);
+        }
+      }
+      adding_core<n, d>(st, L, W, jl, Lay::oR, Lay::oT, Lay::oSdn, Lay::oLU, LU, X, Wd);
     }
-    double rb[NS], rd[NS];  // roof rows of a_below / d_below
+    // [a_below | d_below] (street part) = [R | Sup] + T [X | Wd]
+    double Ab[n * n], Db[n * d];
+    SSB_UNROLL
+    for (int i = 0; i < n * n; ++i) Ab[i] = L.ld(Lay::oR + i, jl);
+    SSB_UNROLL
+    for (int i = 0; i < n * d; ++i) Db[i] = L.ld(Lay::oSup + i, jl);
+    SSB_UNROLL
+    for (int k = 0; k < n; ++k) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) {
+        const double t = L.ld(Lay::oT + i + n * k, jl);
+        SSB_UNROLL
+        for (int j = 0; j < n; ++j) Ab[i + n * j] = fma(t, X[k + n * j], Ab[i + n * j]);
+        SSB_UNROLL
+        for (int j = 0; j < d; ++j) Db[i + n * j] = fma(t, Wd[k + n * j], Db[i + n * j]);
+      }
+    }
+    double rb[NS], rd[NS];
     SSB_UNROLL
     for (int js = 0; js < NS; ++js) rb[js] = rd[js] = 0.0;
     if (URBAN) {
@@ -164,67 +283,35 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q) {
     }
     double U[12], V[12];
     overlap_at(a, il1, nlay, jl + 1, U, V);
-    // a_above(next) = (U (x) I) a_below (V (x) I), d_above(next) = (U (x) I) d_below V
-    {
-      double AV[n * n];  // street rows of a_below (V (x) I)
+    overlap_matrix<NREG, NRB, NS>(Ab, rb, U, V, st, Lay::oAa);
+    // d_above(next)[(u,jt), up] = sum U[u,lo] (Db V)[(lo,jt), up] + roof
+    SSB_UNROLL
+    for (int jt = 0; jt < NS; ++jt) {
+      double DV[NREG * NREG];
       SSB_UNROLL
       for (int up = 0; up < NREG; ++up) {
         SSB_UNROLL
-        for (int js = 0; js < NS; ++js) {
-          SSB_UNROLL
-          for (int i = 0; i < n; ++i) {
-            double s = 0.0;
-            SSB_UNROLL
-            for (int lo = 0; lo < NREG; ++lo) s = fma(Ab[i + n * (lo * NS + js)], V[lo + NRB * up], s);
-            AV[i + n * (up * NS + js)] = s;
-          }
-        }
-      }
-      SSB_UNROLL
-      for (int up = 0; up < NREG; ++up) {
-        SSB_UNROLL
-        for (int js = 0; js < NS; ++js) {
-          SSB_UNROLL
-          for (int u = 0; u < NREG; ++u) {
-            SSB_UNROLL
-            for (int jt = 0; jt < NS; ++jt) {
-              double s = 0.0;
-              SSB_UNROLL
-              for (int lo = 0; lo < NREG; ++lo) s = fma(U[u + NREG * lo], AV[(lo * NS + jt) + n * (up * NS + js)], s);
-              if (URBAN) s = fma(U[u + NREG * NREG] * rb[jt], V[NREG + NRB * up], s);
-              Aa[(u * NS + jt) + n * (up * NS + js)] = s;
-            }
-          }
-        }
-      }
-      double DV[n * d];
-      SSB_UNROLL
-      for (int up = 0; up < NREG; ++up) {
-        SSB_UNROLL
-        for (int i = 0; i < n; ++i) {
+        for (int lo = 0; lo < NREG; ++lo) {
           double s = 0.0;
           SSB_UNROLL
-          for (int lo = 0; lo < NREG; ++lo) s = fma(Db[i + n * lo], V[lo + NRB * up], s);
-          DV[i + n * up] = s;
+          for (int l2 = 0; l2 < NREG; ++l2) s = fma(Db[(lo * NS + jt) + n * l2], V[l2 + NRB * up], s);
+          DV[lo + NREG * up] = s;
         }
       }
       SSB_UNROLL
       for (int up = 0; up < NREG; ++up) {
         SSB_UNROLL
         for (int u = 0; u < NREG; ++u) {
+          double s = 0.0;
           SSB_UNROLL
-          for (int jt = 0; jt < NS; ++jt) {
-            double s = 0.0;
-            SSB_UNROLL
-            for (int lo = 0; lo < NREG; ++lo) s = fma(U[u + NREG * lo], DV[(lo * NS + jt) + n * up], s);
-            if (URBAN) s = fma(U[u + NREG * NREG] * rd[jt], V[NREG + NRB * up], s);
-            Da[(u * NS + jt) + n * up] = s;
-          }
+          for (int lo = 0; lo < NREG; ++lo) s = fma(U[u + NREG * lo], DV[lo + NREG * up], s);
+          if (URBAN) s = fma(U[u + NREG * NREG] * rd[jt], V[NREG + NRB * up], s);
+          st(Lay::oDa + (u * NS + jt) + n * up) = s;
         }
       }
     }
-    sstore<n, n>(WS, oAa, jl + 1, wlev, width, q, Aa);
-    sstore<n, d>(WS, oDa, jl + 1, wlev, width, q, Da);
+    SSB_UNROLL
+    for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, jl + 1, st(i));
   }
   double talb_diff = 0.0, talb_dir = 0.0;
   {
@@ -232,237 +319,263 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q) {
     for (int i = 0; i < NS; ++i) {
       double s = 0.0;
       SSB_UNROLL
-      for (int j = 0; j < NS; ++j) s = fma(Aa[i + n * j], hw[j], s);
+      for (int j = 0; j < NS; ++j) s = fma(st(i + n * j), hw[j], s);
       talb_diff += s;
     }
     double s = 0.0;
     SSB_UNROLL
-    for (int js = 0; js < NS; ++js) s += Da[js];
+    for (int js = 0; js < NS; ++js) s += st(Lay::oDa + js);
     talb_dir = s / zcos;
     a.bc.sw_albedo[(size_t)g + (size_t)nspec * col] = talb_diff;
     a.bc.sw_albedo_dir[(size_t)g + (size_t)nspec * col] = talb_dir;
   }
 
-  // ---- two downward passes ----------------------------------------------------
-  for (int pass = 0; pass < 2; ++pass) {
-    const bool direct = (pass == 0);
-    const ssb200_canopy_flux &f = direct ? fdir : fdif;
-    double dir_above[d], diff_above[n], up_above[n];
-    SSB_UNROLL
-    for (int i = 0; i < d; ++i) dir_above[i] = 0.0;
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      diff_above[i] = 0.0;
-      up_above[i] = 0.0;
-    }
-    double flux_dn_dir_clear = 1.0 / zcos;
-    if (direct) {
-      dir_above[0] = 1.0 / zcos;
-      SSB_FC(f, top_dn_dir) = 1.0;
-      SSB_FC(f, top_dn) = 1.0;
-      SSB_FC(f, top_net) = 1.0 * (1.0 - talb_dir);
-      if (URBAN && own && f.roof_sunlit_frac && nlay > 0) f.roof_sunlit_frac[il1 + nlay - 1] = 1.0;
-    } else {
-      SSB_UNROLL
-      for (int js = 0; js < NS; ++js) diff_above[js] = hw[js];
-      SSB_FC(f, top_dn_dir) = 0.0;
-      SSB_FC(f, top_dn) = 1.0;
-      SSB_FC(f, top_net) = 1.0 - talb_diff;
-    }
-    for (int jl = nlay - 1; jl >= 0; --jl) {
-      const int il = il1 + jl;
-      LayerGeom gm;
-      double bf, vf, ve;
-      geometry_of_layer(a, il, 1.0, gm, bf, vf, ve);
+  // ---- downward sweep, direct (suffix d) and diffuse (suffix f) sources together ----
+  double dir_above[d], xa_d[n], xa_f[n], ua_d[n], ua_f[n];
+  SSB_UNROLL
+  for (int i = 0; i < d; ++i) dir_above[i] = 0.0;
+  SSB_UNROLL
+  for (int i = 0; i < n; ++i) xa_d[i] = xa_f[i] = ua_d[i] = ua_f[i] = 0.0;
+  dir_above[0] = 1.0 / zcos;
+  SSB_UNROLL
+  for (int js = 0; js < NS; ++js) xa_f[js] = hw[js];
+  SSB_FC(fdir, top_dn_dir) = 1.0;
+  SSB_FC(fdir, top_dn) = 1.0;
+  SSB_FC(fdir, top_net) = 1.0 * (1.0 - talb_dir);
+  SSB_FC(fdif, top_dn_dir) = 0.0;
+  SSB_FC(fdif, top_dn) = 1.0;
+  SSB_FC(fdif, top_net) = 1.0 - talb_diff;
+  if (URBAN && own && fdir.roof_sunlit_frac && nlay > 0) fdir.roof_sunlit_frac[il1 + nlay - 1] = 1.0;
+  double flux_dn_dir_clear = 1.0 / zcos;
+  for (int jl = nlay - 1; jl >= 0; --jl) {
+    const int il = il1 + jl;
+    LayerGeom gm;
+    double bf, vf, ve;
+    geometry_of_layer(a, il, 1.0, gm, bf, vf, ve);
+    double xb_d[m], xb_f[m], dir_below[NRB];
+    {
       double U[12], V[12];
       overlap_at(a, il1, nlay, jl + 1, U, V);
-      double diff_below[m], dir_below[NRB], up_below[m];
-      expand_down<NREG, NRB, NS>(V, diff_above, diff_below);
+      expand_down<NREG, NRB, NS>(V, xa_d, xb_d);
+      expand_down<NREG, NRB, NS>(V, xa_f, xb_f);
       SSB_UNROLL
       for (int lo = 0; lo < NRB; ++lo) {
         double s = 0.0;
         SSB_UNROLL
         for (int up = 0; up < NREG; ++up) s = fma(V[lo + NRB * up], dir_above[up], s);
-        dir_below[lo] = direct ? s : 0.0;
-      }
-      double LU[n * n];
-      sload<n, n>(WS, oLU, jl, wlev, width, q, LU);
-      // y = T x + Sdn dirb ; refl = d_above (E dirb)
-      double y[n], refl[n], ddir[d];
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        y[i] = 0.0;
-        refl[i] = 0.0;
-      }
-      smv_acc<n, n>(LS, oT, jl, nlev, width, q, diff_below, y);
-      if (direct) {
-        smv_acc<n, d>(LS, oSdn, jl, nlev, width, q, dir_below, y);
-        double da_new[d];
-        SSB_UNROLL
-        for (int i = 0; i < d; ++i) da_new[i] = 0.0;
-        smv_acc<d, d>(LS, oE, jl, nlev, width, q, dir_below, da_new);
-        SSB_UNROLL
-        for (int i = 0; i < d; ++i) {
-          ddir[i] = dir_below[i] - da_new[i];
-          dir_above[i] = da_new[i];
-        }
-        smv_acc<n, d>(WS, oDa, jl, wlev, width, q, dir_above, refl);
-      } else {
-        SSB_UNROLL
-        for (int i = 0; i < d; ++i) ddir[i] = 0.0;
-      }
-      // z1 = D^-1 (A y + refl) for up_below ; diff_above = D^-1 (y + R refl)
-      double z1[n], z2[n];
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        z1[i] = refl[i];
-        z2[i] = y[i];
-      }
-      smv_acc<n, n>(WS, oAa, jl, wlev, width, q, y, z1);
-      if (direct) smv_acc<n, n>(LS, oR, jl, nlev, width, q, refl, z2);
-      sm_lu_solve_left<n, 1>(LU, z1);
-      sm_lu_solve_left<n, 1>(LU, z2);
-      // up_below (street part) = R x + Sup dirb + T z1
-      SSB_UNROLL
-      for (int i = 0; i < m; ++i) up_below[i] = 0.0;
-      smv_acc<n, n>(LS, oR, jl, nlev, width, q, diff_below, up_below);
-      smv_acc<n, n>(LS, oT, jl, nlev, width, q, z1, up_below);
-      if (direct) smv_acc<n, d>(LS, oSup, jl, nlev, width, q, dir_below, up_below);
-      if (URBAN) {
-        const double ralb = SSB_LAY(a.sw.roof_albedo, g, il);
-        const double ralb_dir = a.sw.roof_albedo_dir ? SSB_LAY(a.sw.roof_albedo_dir, g, il) : ralb;
-        double sroof = 0.0;
-        SSB_UNROLL
-        for (int js = 0; js < NS; ++js) sroof += diff_below[n + js];
-        double roof_up = 0.0;
-        SSB_UNROLL
-        for (int js = 0; js < NS; ++js) {
-          up_below[n + js] = ralb * hw[js] * sroof + (direct ? zcos * ralb_dir * hw[js] * dir_below[NREG] : 0.0);
-          roof_up += up_below[n + js];
-        }
-        if (direct) {
-          SSB_FL(f, roof_in_dir, il) = zcos * dir_below[NREG];
-          SSB_FL(f, roof_in, il) = SSB_FL(f, roof_in_dir, il) + sroof;
-        } else {
-          SSB_FL(f, roof_in, il) = sroof;
-        }
-        SSB_FL(f, roof_net, il) = SSB_FL(f, roof_in, il) - roof_up;
-      }
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        diff_above[i] = z2[i];
-        up_above[i] = refl[i];
-      }
-      smv_acc<n, n>(WS, oAa, jl, wlev, width, q, diff_above, up_above);
-
-      if (f.flux_dn_layer_top) {
-        double s_db = 0.0, s_da = 0.0, s_ub = 0.0, s_ua = 0.0, s_dirb = 0.0, s_dira = 0.0;
-        SSB_UNROLL
-        for (int i = 0; i < n; ++i) {
-          s_db += diff_below[i];
-          s_da += diff_above[i];
-          s_ub += up_below[i];
-          s_ua += up_above[i];
-        }
-        SSB_UNROLL
-        for (int i = 0; i < d; ++i) {
-          s_dirb += dir_below[i];
-          s_dira += dir_above[i];
-        }
-        if (direct) {
-          SSB_FL(f, flux_dn_dir_layer_top, il) = zcos * s_dirb;
-          SSB_FL(f, flux_dn_layer_top, il) = zcos * s_dirb + s_db;
-          SSB_FL(f, flux_dn_dir_layer_base, il) = zcos * s_dira;
-          SSB_FL(f, flux_dn_layer_base, il) = zcos * s_dira + s_da;
-        } else {
-          SSB_FL(f, flux_dn_layer_top, il) = s_db;
-          SSB_FL(f, flux_dn_layer_base, il) = s_da;
-        }
-        SSB_FL(f, flux_up_layer_top, il) = s_ub;
-        SSB_FL(f, flux_up_layer_base, il) = s_ua;
-      }
-      // integrated fluxes
-      double conv[n], iflux_diff[n], iflux_dir[d];
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        conv[i] = diff_below[i] - diff_above[i] - up_below[i] + up_above[i];
-        iflux_diff[i] = 0.0;
-      }
-      SSB_UNROLL
-      for (int i = 0; i < d; ++i) iflux_dir[i] = 0.0;
-      smv_acc<n, n>(LS, oIdiff, jl, nlev, width, q, conv, iflux_diff);
-      if (direct) {
-        smv_acc<d, d>(LS, oIdir, jl, nlev, width, q, ddir, iflux_dir);
-        smv_acc<n, d>(LS, oIdd, jl, nlev, width, q, ddir, iflux_diff);
-      }
-      double smu[NREG], stan[NREG];
-      SSB_UNROLL
-      for (int r = 0; r < NREG; ++r) {
-        smu[r] = 0.0;
-        stan[r] = 0.0;
-        SSB_UNROLL
-        for (int js = 0; js < NS; ++js) {
-          smu[r] = fma(iflux_diff[r * NS + js], mu_inv[js], smu[r]);
-          stan[r] = fma(iflux_diff[r * NS + js], tang[js], stan[r]);
-        }
-      }
-      const double air_ext = SSB_LAY(a.sw.air_ext, g, il);
-      const double air_abs = air_ext * (1.0 - SSB_LAY(a.sw.air_ssa, g, il));
-      SSB_FL(f, clear_air_abs, il) = air_abs * (iflux_dir[0] + smu[0]);
-      if (NREG > 1) {
-        const double vabs = ve * (1.0 - SSB_LAY(a.sw.veg_ssa, g, il));
-        double s_air = 0.0, s_veg = 0.0, s_vdir = 0.0;
-        SSB_UNROLL
-        for (int r = 1; r < NREG; ++r) {
-          s_air += air_abs * (iflux_dir[r] + smu[r]);
-          s_vdir += vabs * iflux_dir[r] * gm.od_scaling[r];
-          s_veg += vabs * (iflux_dir[r] + smu[r]) * gm.od_scaling[r];
-        }
-        SSB_FL(f, veg_air_abs, il) = s_air;
-        SSB_FL(f, veg_abs, il) = s_veg;
-        if (direct) SSB_FL(f, veg_abs_dir, il) = s_vdir;
-      }
-      if (URBAN) {
-        const double walb = SSB_LAY(a.sw.wall_albedo, g, il);
-        double win_dir = 0.0, win = 0.0;
-        SSB_UNROLL
-        for (int r = 0; r < NREG; ++r) {
-          win_dir += gm.f_wall[r] * sin0 * iflux_dir[r];
-          win += gm.f_wall[r] * stan[r];
-        }
-        if (direct) SSB_FL(f, wall_in_dir, il) = win_dir;
-        SSB_FL(f, wall_in, il) = (direct ? win_dir : 0.0) + win;
-        SSB_FL(f, wall_net, il) = SSB_FL(f, wall_in, il) * (1.0 - walb);
-      }
-      if (direct) {
-        const double nonb_here = URBAN ? 1.0 - bf : 1.0;
-        double nonb_above = 1.0;
-        if (URBAN && jl + 1 < nlay) nonb_above = 1.0 - a.cp.building_fraction[il + 1];
-        if (URBAN) {
-          const double roof_fraction = (jl == nlay - 1) ? bf : dmax(0.0, bf - a.cp.building_fraction[il + 1]);
-          if (own && f.roof_sunlit_frac)
-            f.roof_sunlit_frac[il] = SSB_FL(f, roof_in_dir, il) * nonb_above /
-                                     (zcos * flux_dn_dir_clear * dmax(c.min_bld, roof_fraction));
-          flux_dn_dir_clear = flux_dn_dir_clear * nonb_here / nonb_above;
-        }
-        const double air_ext_t = a.sw.air_ext[(size_t)itransp + (size_t)nspec * il];
-        const double trans_dir_clear = exp(-air_ext_t * a.cp.dz[il] / zcos);
-        const double int_flux_dir_clear = (air_ext_t > 0.0)
-                                              ? flux_dn_dir_clear * (1.0 - trans_dir_clear) * zcos / air_ext_t
-                                              : flux_dn_dir_clear * a.cp.dz[il];
-        if (own) {
-          if ((URBAN ? NREG > 1 : true) && f.veg_sunlit_frac && a.cp.veg_ext && a.cp.veg_fraction && a.sw.veg_ssa) {
-            const double veg_abs_dir_clear = int_flux_dir_clear * ve * (1.0 - SSB_LAY(a.sw.veg_ssa, g, il)) * vf;
-            f.veg_sunlit_frac[il] = SSB_FL(f, veg_abs_dir, il) / dmax(SSB_EPS, veg_abs_dir_clear);
-          }
-          if (URBAN && f.wall_sunlit_frac)
-            f.wall_sunlit_frac[il] =
-                0.5 * SSB_FL(f, wall_in_dir, il) / dmax(SSB_EPS, (gm.f_wall_dir_clear * sin0 * int_flux_dir_clear));
-        }
-        flux_dn_dir_clear = flux_dn_dir_clear * trans_dir_clear;
+        dir_below[lo] = s;
       }
     }
-    double s_dir = 0.0, s_dn = 0.0, s_up = 0.0, s_vert = 0.0;
+    // y = T x (+ Sdn dirb) ; dir_above = E dirb ; refl = d_above dir_above
+    double y_d[n], y_f[n], refl[n], ddir[d];
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) y_d[i] = y_f[i] = refl[i] = 0.0;
+    smv2<n, n>(L, Lay::oT, jl, xb_d, xb_f, y_d, y_f);
+    smv1<n, d>(L, Lay::oSdn, jl, dir_below, y_d);
+    {
+      double da_new[d];
+      SSB_UNROLL
+      for (int i = 0; i < d; ++i) da_new[i] = 0.0;
+      smv1<d, d>(L, Lay::oE, jl, dir_below, da_new);
+      SSB_UNROLL
+      for (int i = 0; i < d; ++i) {
+        ddir[i] = dir_below[i] - da_new[i];
+        dir_above[i] = da_new[i];
+      }
+    }
+    smv1<n, d>(W, Lay::oDa, jl, dir_above, refl);
+    // z1 = D^-1 (a_above y + refl) ; z2 = D^-1 (y + R refl) ; ub = R x (street part of up_below)
+    double z1_d[n], z1_f[n], z2_d[n], z2_f[n], ub_d[m], ub_f[m];
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      z1_d[i] = refl[i];
+      z1_f[i] = 0.0;
+      z2_d[i] = y_d[i];
+      z2_f[i] = y_f[i];
+    }
+    SSB_UNROLL
+    for (int i = 0; i < m; ++i) ub_d[i] = ub_f[i] = 0.0;
+    smv2<n, n>(W, Lay::oAa, jl, y_d, y_f, z1_d, z1_f);
+    SSB_UNROLL
+    for (int j = 0; j < n; ++j) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) {
+        const double r = L.ld(Lay::oR + i + n * j, jl);
+        z2_d[i] = fma(r, refl[j], z2_d[i]);
+        ub_d[i] = fma(r, xb_d[j], ub_d[i]);
+        ub_f[i] = fma(r, xb_f[j], ub_f[i]);
+      }
+    }
+    {
+      double LU[n * n];
+      SSB_UNROLL
+      for (int i = 0; i < n * n; ++i) LU[i] = W.ld(Lay::oLU + i, jl);
+      sm_lu_solve_left<n, 1>(LU, z1_d);
+      sm_lu_solve_left<n, 1>(LU, z1_f);
+      sm_lu_solve_left<n, 1>(LU, z2_d);
+      sm_lu_solve_left<n, 1>(LU, z2_f);
+    }
+    smv2<n, n>(L, Lay::oT, jl, z1_d, z1_f, ub_d, ub_f);
+    smv1<n, d>(L, Lay::oSup, jl, dir_below, ub_d);
+    if (URBAN) {
+      const double ralb = SSB_LAY(a.sw.roof_albedo, g, il);
+      const double ralb_dir = a.sw.roof_albedo_dir ? SSB_LAY(a.sw.roof_albedo_dir, g, il) : ralb;
+      double sroof_d = 0.0, sroof_f = 0.0, rup_d = 0.0, rup_f = 0.0;
+      SSB_UNROLL
+      for (int js = 0; js < NS; ++js) {
+        sroof_d += xb_d[n + js];
+        sroof_f += xb_f[n + js];
+      }
+      SSB_UNROLL
+      for (int js = 0; js < NS; ++js) {
+        ub_d[n + js] = ralb * hw[js] * sroof_d + zcos * ralb_dir * hw[js] * dir_below[NREG];
+        ub_f[n + js] = ralb * hw[js] * sroof_f;
+        rup_d += ub_d[n + js];
+        rup_f += ub_f[n + js];
+      }
+      SSB_FL(fdir, roof_in_dir, il) = zcos * dir_below[NREG];
+      SSB_FL(fdir, roof_in, il) = SSB_FL(fdir, roof_in_dir, il) + sroof_d;
+      SSB_FL(fdir, roof_net, il) = SSB_FL(fdir, roof_in, il) - rup_d;
+      SSB_FL(fdif, roof_in, il) = sroof_f;
+      SSB_FL(fdif, roof_net, il) = sroof_f - rup_f;
+    }
+    // fluxes just above the base: x_above = z2 ; up_above = a_above z2 + refl
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      xa_d[i] = z2_d[i];
+      xa_f[i] = z2_f[i];
+      ua_d[i] = refl[i];
+      ua_f[i] = 0.0;
+    }
+    smv2<n, n>(W, Lay::oAa, jl, xa_d, xa_f, ua_d, ua_f);
+    if (fdir.flux_dn_layer_top || fdif.flux_dn_layer_top) {
+      double s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sdb = 0.0, sda = 0.0;
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) {
+        s[0] += xb_d[i];
+        s[1] += xa_d[i];
+        s[2] += ub_d[i];
+        s[3] += ua_d[i];
+        s[4] += xb_f[i];
+        s[5] += xa_f[i];
+        s[6] += ub_f[i];
+        s[7] += ua_f[i];
+      }
+      SSB_UNROLL
+      for (int i = 0; i < d; ++i) {
+        sdb += dir_below[i];
+        sda += dir_above[i];
+      }
+      if (fdir.flux_dn_layer_top) {
+        SSB_FL(fdir, flux_dn_dir_layer_top, il) = zcos * sdb;
+        SSB_FL(fdir, flux_dn_layer_top, il) = zcos * sdb + s[0];
+        SSB_FL(fdir, flux_dn_dir_layer_base, il) = zcos * sda;
+        SSB_FL(fdir, flux_dn_layer_base, il) = zcos * sda + s[1];
+        SSB_FL(fdir, flux_up_layer_top, il) = s[2];
+        SSB_FL(fdir, flux_up_layer_base, il) = s[3];
+      }
+      if (fdif.flux_dn_layer_top) {
+        SSB_FL(fdif, flux_dn_layer_top, il) = s[4];
+        SSB_FL(fdif, flux_dn_layer_base, il) = s[5];
+        SSB_FL(fdif, flux_up_layer_top, il) = s[6];
+        SSB_FL(fdif, flux_up_layer_base, il) = s[7];
+      }
+    }
+    // integrated fluxes across the layer
+    double if_d[n], if_f[n], idir[d];
+    {
+      double cv_d[n], cv_f[n];
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) {
+        cv_d[i] = xb_d[i] - xa_d[i] - ub_d[i] + ua_d[i];
+        cv_f[i] = xb_f[i] - xa_f[i] - ub_f[i] + ua_f[i];
+        if_d[i] = if_f[i] = 0.0;
+      }
+      SSB_UNROLL
+      for (int i = 0; i < d; ++i) idir[i] = 0.0;
+      smv2<n, n>(L, Lay::oIdiff, jl, cv_d, cv_f, if_d, if_f);
+      smv1<d, d>(L, Lay::oIdir, jl, ddir, idir);
+      smv1<n, d>(L, Lay::oIdd, jl, ddir, if_d);
+    }
+    double smu_d[NREG], smu_f[NREG], stan_d[NREG], stan_f[NREG];
+    SSB_UNROLL
+    for (int r = 0; r < NREG; ++r) {
+      smu_d[r] = smu_f[r] = stan_d[r] = stan_f[r] = 0.0;
+      SSB_UNROLL
+      for (int js = 0; js < NS; ++js) {
+        smu_d[r] = fma(if_d[r * NS + js], mu_inv[js], smu_d[r]);
+        smu_f[r] = fma(if_f[r * NS + js], mu_inv[js], smu_f[r]);
+        stan_d[r] = fma(if_d[r * NS + js], tang[js], stan_d[r]);
+        stan_f[r] = fma(if_f[r * NS + js], tang[js], stan_f[r]);
+      }
+    }
+    const double air_ext = SSB_LAY(a.sw.air_ext, g, il);
+    const double air_abs = air_ext * (1.0 - SSB_LAY(a.sw.air_ssa, g, il));
+    SSB_FL(fdir, clear_air_abs, il) = air_abs * (idir[0] + smu_d[0]);
+    SSB_FL(fdif, clear_air_abs, il) = air_abs * smu_f[0];
+    if (NREG > 1) {
+      const double vabs = ve * (1.0 - SSB_LAY(a.sw.veg_ssa, g, il));
+      double air_d = 0.0, veg_d = 0.0, vdir = 0.0, air_f = 0.0, veg_f = 0.0;
+      SSB_UNROLL
+      for (int r = 1; r < NREG; ++r) {
+        air_d += air_abs * (idir[r] + smu_d[r]);
+        vdir += vabs * idir[r] * gm.od_scaling[r];
+        veg_d += vabs * (idir[r] + smu_d[r]) * gm.od_scaling[r];
+        air_f += air_abs * smu_f[r];
+        veg_f += vabs * smu_f[r] * gm.od_scaling[r];
+      }
+      SSB_FL(fdir, veg_air_abs, il) = air_d;
+      SSB_FL(fdir, veg_abs, il) = veg_d;
+      SSB_FL(fdir, veg_abs_dir, il) = vdir;
+      SSB_FL(fdif, veg_air_abs, il) = air_f;
+      SSB_FL(fdif, veg_abs, il) = veg_f;
+    }
+    if (URBAN) {
+      const double walb = SSB_LAY(a.sw.wall_albedo, g, il);
+      double win_dir = 0.0, win_d = 0.0, win_f = 0.0;
+      SSB_UNROLL
+      for (int r = 0; r < NREG; ++r) {
+        win_dir += gm.f_wall[r] * sin0 * idir[r];
+        win_d += gm.f_wall[r] * stan_d[r];
+        win_f += gm.f_wall[r] * stan_f[r];
+      }
+      SSB_FL(fdir, wall_in_dir, il) = win_dir;
+      SSB_FL(fdir, wall_in, il) = win_dir + win_d;
+      SSB_FL(fdir, wall_net, il) = (win_dir + win_d) * (1.0 - walb);
+      SSB_FL(fdif, wall_in, il) = win_f;
+      SSB_FL(fdif, wall_net, il) = win_f * (1.0 - walb);
+    }
+    {
+      // spectrally independent sunlit fractions from the most transparent interval (urban_sw:805-848)
+      const double nonb_here = URBAN ? 1.0 - bf : 1.0;
+      double nonb_above = 1.0;
+      if (URBAN && jl + 1 < nlay) nonb_above = 1.0 - a.cp.building_fraction[il + 1];
+      if (URBAN) {
+        const double roof_fraction = (jl == nlay - 1) ? bf : dmax(0.0, bf - a.cp.building_fraction[il + 1]);
+        if (own && fdir.roof_sunlit_frac)
+          fdir.roof_sunlit_frac[il] = SSB_FL(fdir, roof_in_dir, il) * nonb_above /
+                                      (zcos * flux_dn_dir_clear * dmax(c.min_bld, roof_fraction));
+        flux_dn_dir_clear = flux_dn_dir_clear * nonb_here / nonb_above;
+      }
+      const double air_ext_t = a.sw.air_ext[(size_t)itransp + (size_t)nspec * il];
+      const double trans_dir_clear = exp(-air_ext_t * a.cp.dz[il] / zcos);
+      const double int_flux_dir_clear = (air_ext_t > 0.0)
+                                            ? flux_dn_dir_clear * (1.0 - trans_dir_clear) * zcos / air_ext_t
+                                            : flux_dn_dir_clear * a.cp.dz[il];
+      if (own) {
+        if ((URBAN ? NREG > 1 : true) && fdir.veg_sunlit_frac && a.cp.veg_ext && a.cp.veg_fraction && a.sw.veg_ssa) {
+          const double veg_abs_dir_clear = int_flux_dir_clear * ve * (1.0 - SSB_LAY(a.sw.veg_ssa, g, il)) * vf;
+          fdir.veg_sunlit_frac[il] = SSB_FL(fdir, veg_abs_dir, il) / dmax(SSB_EPS, veg_abs_dir_clear);
+        }
+        if (URBAN && fdir.wall_sunlit_frac)
+          fdir.wall_sunlit_frac[il] =
+              0.5 * SSB_FL(fdir, wall_in_dir, il) / dmax(SSB_EPS, (gm.f_wall_dir_clear * sin0 * int_flux_dir_clear));
+      }
+      flux_dn_dir_clear = flux_dn_dir_clear * trans_dir_clear;
+    }
+  }
+  {
+    double s_dir = 0.0, dn_d = 0.0, up_d = 0.0, vt_d = 0.0, dn_f = 0.0, up_f = 0.0, vt_f = 0.0;
     SSB_UNROLL
     for (int i = 0; i < d; ++i) s_dir += dir_above[i];
     SSB_UNROLL
@@ -470,22 +583,41 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q) {
       SSB_UNROLL
       for (int js = 0; js < NS; ++js) {
         const int i = js + r * NS;
-        s_dn += diff_above[i];
-        s_up += up_above[i];
-        s_vert += (diff_above[i] + up_above[i]) * tang[js] / SSB_PI;
+        dn_d += xa_d[i];
+        up_d += ua_d[i];
+        vt_d += (xa_d[i] + ua_d[i]) * tang[js] / SSB_PI;
+        dn_f += xa_f[i];
+        up_f += ua_f[i];
+        vt_f += (xa_f[i] + ua_f[i]) * tang[js] / SSB_PI;
       }
     }
-    SSB_FC(f, ground_dn_dir) = direct ? zcos * s_dir : 0.0;
-    SSB_FC(f, ground_dn) = SSB_FC(f, ground_dn_dir) + s_dn;
-    SSB_FC(f, ground_net) = SSB_FC(f, ground_dn) - s_up;
-    SSB_FC(f, ground_vertical_diff) = s_vert;
-    if (direct && own && f.ground_sunlit_frac)
-      f.ground_sunlit_frac[col] = SSB_FC(f, ground_dn_dir) / (zcos * flux_dn_dir_clear);
+    SSB_FC(fdir, ground_dn_dir) = zcos * s_dir;
+    SSB_FC(fdir, ground_dn) = zcos * s_dir + dn_d;
+    SSB_FC(fdir, ground_net) = SSB_FC(fdir, ground_dn) - up_d;
+    SSB_FC(fdir, ground_vertical_diff) = vt_d;
+    if (own && fdir.ground_sunlit_frac)
+      fdir.ground_sunlit_frac[col] = SSB_FC(fdir, ground_dn_dir) / (zcos * flux_dn_dir_clear);
+    SSB_FC(fdif, ground_dn_dir) = 0.0;
+    SSB_FC(fdif, ground_dn) = dn_f;
+    SSB_FC(fdif, ground_net) = dn_f - up_f;
+    SSB_FC(fdif, ground_vertical_diff) = vt_f;
   }
 }
 
+// ===========================================================================
+// Longwave
+// ===========================================================================
 template <int NREG, int NS, bool URBAN>
-SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q) {
+struct LwSweepLayout {
+  static constexpr int n = NREG * NS, d = NREG;
+  static constexpr int oR = 0, oT = n * n, oIF = 2 * n * n, oSrc = 3 * n * n, oIsrc = oSrc + n, oBook = oIsrc + n;
+  static constexpr int oAa = 0, oSa = n * n, oLU = oSa + n;
+  static constexpr int state_doubles = n * n + n;
+};
+
+template <int NREG, int NS, bool URBAN>
+SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateMem &st) {
+  typedef LwSweepLayout<NREG, NS, URBAN> Lay;
   constexpr int n = NREG * NS, d = NREG, NRB = URBAN ? NREG + 1 : NREG, m = NRB * NS;
   const SolveCfg &c = a.cfg;
   const int nspec = c.nspec;
@@ -503,15 +635,12 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q) {
     mu_inv[js] = 1.0 / a.lg.mu[js];
     tang[js] = a.lg.tan_ang[js];
   }
-  const double *LS = a.layer;
-  double *WS = a.sweep;
-  const int nlev = a.lmax, wlev = a.lmax + 1;
-  constexpr int oR = 0, oT = n * n, oIF = 2 * n * n, oSrc = 3 * n * n, oIsrc = oSrc + n, oBook = oIsrc + n;
-  constexpr int oAa = 0, oSa = n * n, oLU = oSa + n;
-
+  const Scr L{a.layer, a.layer, a.lmax, width, q};
+  const Scr W{a.sweep, a.sweep, a.lmax + 1, width, q};
   const double gemis = a.lw.ground_emissivity[(size_t)g + (size_t)nspec * col];
   const double gemission = a.lw.ground_emission[(size_t)g + (size_t)nspec * col];
-  double Aa[n * n], Sa[n];
+
+  // ---- upward sweep: state = [a_above (n x n) | source_above (n)] ------------
   {
     double frac0[3] = {1.0, 0.0, 0.0};
     if (nlay > 0) {
@@ -520,48 +649,44 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q) {
                        (veg && a.cp.veg_fraction) ? a.cp.veg_fraction[il1] : 0.0, frac0);
     }
     SSB_UNROLL
-    for (int i = 0; i < n * n; ++i) Aa[i] = 0.0;
+    for (int i = 0; i < Lay::state_doubles; ++i) st(i) = 0.0;
     SSB_UNROLL
     for (int r = 0; r < NREG; ++r) {
       SSB_UNROLL
       for (int jt = 0; jt < NS; ++jt) {
         SSB_UNROLL
-        for (int jf = 0; jf < NS; ++jf) Aa[(jt + r * NS) + n * (jf + r * NS)] = (1.0 - gemis) * hw[jt];
-        Sa[jt + r * NS] = (hw[jt] * frac0[r]) * gemission;
+        for (int jf = 0; jf < NS; ++jf) st((jt + r * NS) + n * (jf + r * NS)) = (1.0 - gemis) * hw[jt];
+        st(Lay::oSa + jt + r * NS) = (hw[jt] * frac0[r]) * gemission;
       }
     }
   }
-  sstore<n, n>(WS, oAa, 0, wlev, width, q, Aa);
-  sstore<n, 1>(WS, oSa, 0, wlev, width, q, Sa);
+  SSB_UNROLL
+  for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, 0, st(i));
   for (int jl = 0; jl < nlay; ++jl) {
     const int il = il1 + jl;
-    double R[n * n], T[n * n], LU[n * n], X[n * n], src[n];
-    sload<n, n>(LS, oR, jl, nlev, width, q, R);
-    sload<n, n>(LS, oT, jl, nlev, width, q, T);
-    sload<n, 1>(LS, oSrc, jl, nlev, width, q, src);
-    sm_mul<n, n, n>(Aa, R, LU);
-    SSB_UNROLL
-    for (int j = 0; j < n; ++j) {
+    double X[n * n], v1[n];
+    {
+      double LU[n * n];
+      // v1 <- source_above, then adding_core adds a_above src and applies D^-1
       SSB_UNROLL
-      for (int i = 0; i < n; ++i) LU[i + n * j] = (i == j ? 1.0 : 0.0) - LU[i + n * j];
+      for (int i = 0; i < n; ++i) v1[i] = st(Lay::oSa + i);
+      adding_core<n, 1>(st, L, W, jl, Lay::oR, Lay::oT, Lay::oSrc, Lay::oLU, LU, X, v1);
     }
-    sm_lu<n>(LU);
-    sstore<n, n>(WS, oLU, jl, wlev, width, q, LU);
-    sm_mul<n, n, n>(Aa, T, X);
-    sm_lu_solve_left<n, n>(LU, X);
-    double Ab[n * n];
-    sm_mul<n, n, n>(T, X, Ab);
+    double Ab[n * n], Sb[n];
     SSB_UNROLL
-    for (int i = 0; i < n * n; ++i) Ab[i] += R[i];
-    // source_below (street part) = src + T D^-1 (Sa + Aa src)
-    double Sb[n], v1[n];
-    sm_mulvec<n, n>(Aa, src, v1);
+    for (int i = 0; i < n * n; ++i) Ab[i] = L.ld(Lay::oR + i, jl);
     SSB_UNROLL
-    for (int i = 0; i < n; ++i) v1[i] += Sa[i];
-    sm_lu_solve_left<n, 1>(LU, v1);
-    sm_mulvec<n, n>(T, v1, Sb);
+    for (int i = 0; i < n; ++i) Sb[i] = L.ld(Lay::oSrc + i, jl);
     SSB_UNROLL
-    for (int i = 0; i < n; ++i) Sb[i] += src[i];
+    for (int k = 0; k < n; ++k) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) {
+        const double t = L.ld(Lay::oT + i + n * k, jl);
+        SSB_UNROLL
+        for (int j = 0; j < n; ++j) Ab[i + n * j] = fma(t, X[k + n * j], Ab[i + n * j]);
+        Sb[i] = fma(t, v1[k], Sb[i]);
+      }
+    }
     double rb[NS], rs[NS];
     SSB_UNROLL
     for (int js = 0; js < NS; ++js) rb[js] = rs[js] = 0.0;
@@ -577,52 +702,20 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q) {
     }
     double U[12], V[12];
     overlap_at(a, il1, nlay, jl + 1, U, V);
-    {
-      double AV[n * n];
+    overlap_matrix<NREG, NRB, NS>(Ab, rb, U, V, st, Lay::oAa);
+    SSB_UNROLL
+    for (int u = 0; u < NREG; ++u) {
       SSB_UNROLL
-      for (int up = 0; up < NREG; ++up) {
+      for (int jt = 0; jt < NS; ++jt) {
+        double s = 0.0;
         SSB_UNROLL
-        for (int js = 0; js < NS; ++js) {
-          SSB_UNROLL
-          for (int i = 0; i < n; ++i) {
-            double s = 0.0;
-            SSB_UNROLL
-            for (int lo = 0; lo < NREG; ++lo) s = fma(Ab[i + n * (lo * NS + js)], V[lo + NRB * up], s);
-            AV[i + n * (up * NS + js)] = s;
-          }
-        }
-      }
-      SSB_UNROLL
-      for (int up = 0; up < NREG; ++up) {
-        SSB_UNROLL
-        for (int js = 0; js < NS; ++js) {
-          SSB_UNROLL
-          for (int u = 0; u < NREG; ++u) {
-            SSB_UNROLL
-            for (int jt = 0; jt < NS; ++jt) {
-              double s = 0.0;
-              SSB_UNROLL
-              for (int lo = 0; lo < NREG; ++lo) s = fma(U[u + NREG * lo], AV[(lo * NS + jt) + n * (up * NS + js)], s);
-              if (URBAN) s = fma(U[u + NREG * NREG] * rb[jt], V[NREG + NRB * up], s);
-              Aa[(u * NS + jt) + n * (up * NS + js)] = s;
-            }
-          }
-        }
-      }
-      SSB_UNROLL
-      for (int u = 0; u < NREG; ++u) {
-        SSB_UNROLL
-        for (int jt = 0; jt < NS; ++jt) {
-          double s = 0.0;
-          SSB_UNROLL
-          for (int lo = 0; lo < NREG; ++lo) s = fma(U[u + NREG * lo], Sb[lo * NS + jt], s);
-          if (URBAN) s = fma(U[u + NREG * NREG], rs[jt], s);
-          Sa[u * NS + jt] = s;
-        }
+        for (int lo = 0; lo < NREG; ++lo) s = fma(U[u + NREG * lo], Sb[lo * NS + jt], s);
+        if (URBAN) s = fma(U[u + NREG * NREG], rs[jt], s);
+        st(Lay::oSa + u * NS + jt) = s;
       }
     }
-    sstore<n, n>(WS, oAa, jl + 1, wlev, width, q, Aa);
-    sstore<n, 1>(WS, oSa, jl + 1, wlev, width, q, Sa);
+    SSB_UNROLL
+    for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, jl + 1, st(i));
   }
   double top_emissivity, top_emission = 0.0;
   {
@@ -631,184 +724,224 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q) {
     for (int i = 0; i < NS; ++i) {
       double s = 0.0;
       SSB_UNROLL
-      for (int j = 0; j < NS; ++j) s = fma(Aa[i + n * j], hw[j], s);
+      for (int j = 0; j < NS; ++j) s = fma(st(i + n * j), hw[j], s);
       sAll += s;
-      top_emission += Sa[i];
+      top_emission += st(Lay::oSa + i);
     }
     top_emissivity = 1.0 - sAll;
     a.bc.lw_emissivity[(size_t)g + (size_t)nspec * col] = top_emissivity;
     a.bc.lw_emission[(size_t)g + (size_t)nspec * col] = top_emission;
   }
 
-  double gvd_internal = 0.0;
-  for (int pass = 0; pass < 2; ++pass) {
-    const bool internal = (pass == 0);
-    const ssb200_canopy_flux &f = internal ? fint : fnorm;
-    double dn_above[n], up_above[n];
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      dn_above[i] = 0.0;
-      up_above[i] = 0.0;
-    }
-    if (internal) {
-      SSB_FC(f, top_dn) = 0.0;
-      SSB_FC(f, top_net) = -top_emission;
-    } else {
-      SSB_UNROLL
-      for (int js = 0; js < NS; ++js) dn_above[js] = hw[js];
-      SSB_FC(f, top_dn) = 1.0;
-      SSB_FC(f, top_net) = top_emissivity;
-    }
-    for (int jl = nlay - 1; jl >= 0; --jl) {
-      const int il = il1 + jl;
-      LayerGeom gm;
-      double bf, vf, ve;
-      geometry_of_layer(a, il, a.lg.vadjustment2, gm, bf, vf, ve);
+  // ---- downward sweep: internal emission (suffix i) and incoming flux (suffix f) together ----
+  double xa_i[n], xa_f[n], ua_i[n], ua_f[n];
+  SSB_UNROLL
+  for (int i = 0; i < n; ++i) xa_i[i] = xa_f[i] = ua_i[i] = ua_f[i] = 0.0;
+  SSB_UNROLL
+  for (int js = 0; js < NS; ++js) xa_f[js] = hw[js];
+  SSB_FC(fint, top_dn) = 0.0;
+  SSB_FC(fint, top_net) = -top_emission;
+  SSB_FC(fnorm, top_dn) = 1.0;
+  SSB_FC(fnorm, top_net) = top_emissivity;
+  for (int jl = nlay - 1; jl >= 0; --jl) {
+    const int il = il1 + jl;
+    LayerGeom gm;
+    double bf, vf, ve;
+    geometry_of_layer(a, il, a.lg.vadjustment2, gm, bf, vf, ve);
+    double xb_i[m], xb_f[m];
+    {
       double U[12], V[12];
       overlap_at(a, il1, nlay, jl + 1, U, V);
-      double dn_below[m], up_below[m];
-      expand_down<NREG, NRB, NS>(V, dn_above, dn_below);
-      double LU[n * n], src[n], sa[n];
-      sload<n, n>(WS, oLU, jl, wlev, width, q, LU);
+      expand_down<NREG, NRB, NS>(V, xa_i, xb_i);
+      expand_down<NREG, NRB, NS>(V, xa_f, xb_f);
+    }
+    double src[n], sa[n];
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      src[i] = L.ld(Lay::oSrc + i, jl);
+      sa[i] = W.ld(Lay::oSa + i, jl);
+    }
+    // y = T x (+ src) ; z1 = D^-1 (a_above y + sa) ; z2 = D^-1 (y + R sa) ; ub = R x + src
+    double y_i[n], y_f[n];
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      y_i[i] = src[i];
+      y_f[i] = 0.0;
+    }
+    smv2<n, n>(L, Lay::oT, jl, xb_i, xb_f, y_i, y_f);
+    double z1_i[n], z1_f[n], z2_i[n], z2_f[n], ub_i[m], ub_f[m];
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      z1_i[i] = sa[i];
+      z1_f[i] = 0.0;
+      z2_i[i] = y_i[i];
+      z2_f[i] = y_f[i];
+    }
+    SSB_UNROLL
+    for (int i = 0; i < m; ++i) ub_i[i] = ub_f[i] = 0.0;
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) ub_i[i] = src[i];
+    smv2<n, n>(W, Lay::oAa, jl, y_i, y_f, z1_i, z1_f);
+    SSB_UNROLL
+    for (int j = 0; j < n; ++j) {
       SSB_UNROLL
       for (int i = 0; i < n; ++i) {
-        src[i] = 0.0;
-        sa[i] = 0.0;
-      }
-      if (internal) {
-        sload<n, 1>(LS, oSrc, jl, nlev, width, q, src);
-        sload<n, 1>(WS, oSa, jl, wlev, width, q, sa);
-      }
-      // y = T x + src
-      double y[n];
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) y[i] = 0.0;
-      smv_acc<n, n>(LS, oT, jl, nlev, width, q, dn_below, y);
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) y[i] += src[i];
-      // z1 = D^-1 (Aa y + Sa) ; z2 = D^-1 (y + R Sa)
-      double z1[n], z2[n];
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        z1[i] = sa[i];
-        z2[i] = y[i];
-      }
-      smv_acc<n, n>(WS, oAa, jl, wlev, width, q, y, z1);
-      if (internal) smv_acc<n, n>(LS, oR, jl, nlev, width, q, sa, z2);
-      sm_lu_solve_left<n, 1>(LU, z1);
-      sm_lu_solve_left<n, 1>(LU, z2);
-      SSB_UNROLL
-      for (int i = 0; i < m; ++i) up_below[i] = 0.0;
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) up_below[i] = src[i];
-      smv_acc<n, n>(LS, oR, jl, nlev, width, q, dn_below, up_below);
-      smv_acc<n, n>(LS, oT, jl, nlev, width, q, z1, up_below);
-      if (URBAN) {
-        const double bfj = a.cp.building_fraction[il];
-        const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + 1]) : bfj;
-        const double remis = SSB_LAY(a.lw.roof_emissivity, g, il), remission = SSB_LAY(a.lw.roof_emission, g, il);
-        double sroof = 0.0, roof_up = 0.0;
-        SSB_UNROLL
-        for (int js = 0; js < NS; ++js) sroof += dn_below[n + js];
-        SSB_UNROLL
-        for (int js = 0; js < NS; ++js) {
-          up_below[n + js] = (1.0 - remis) * hw[js] * sroof + (internal ? hw[js] * remission * exposed : 0.0);
-          roof_up += up_below[n + js];
-        }
-        SSB_FL(f, roof_in, il) = sroof;
-        SSB_FL(f, roof_net, il) = sroof - roof_up;
-      }
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        dn_above[i] = z2[i];
-        up_above[i] = sa[i];
-      }
-      smv_acc<n, n>(WS, oAa, jl, wlev, width, q, dn_above, up_above);
-      if (f.flux_dn_layer_top) {
-        double s_db = 0.0, s_da = 0.0, s_ub = 0.0, s_ua = 0.0;
-        SSB_UNROLL
-        for (int i = 0; i < n; ++i) {
-          s_db += dn_below[i];
-          s_da += dn_above[i];
-          s_ub += up_below[i];
-          s_ua += up_above[i];
-        }
-        SSB_FL(f, flux_dn_layer_top, il) = s_db;
-        SSB_FL(f, flux_up_layer_top, il) = s_ub;
-        SSB_FL(f, flux_dn_layer_base, il) = s_da;
-        SSB_FL(f, flux_up_layer_base, il) = s_ua;
-      }
-      double tv[n], iflux[n], book[3 * d + 1];
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        tv[i] = dn_below[i] + up_above[i];
-        iflux[i] = 0.0;
-      }
-      SSB_UNROLL
-      for (int i = 0; i < 3 * d + 1; ++i) book[i] = 0.0;
-      smv_acc<n, n>(LS, oIF, jl, nlev, width, q, tv, iflux);
-      if (internal) {
-        double isrc[n];
-        sload<n, 1>(LS, oIsrc, jl, nlev, width, q, isrc);
-        SSB_UNROLL
-        for (int i = 0; i < n; ++i) iflux[i] += isrc[i];
-        sload<3 * d + 1, 1>(LS, oBook, jl, nlev, width, q, book);
-      }
-      double smu[NREG], stan[NREG];
-      SSB_UNROLL
-      for (int r = 0; r < NREG; ++r) {
-        smu[r] = 0.0;
-        stan[r] = 0.0;
-        SSB_UNROLL
-        for (int js = 0; js < NS; ++js) {
-          smu[r] = fma(iflux[r * NS + js], mu_inv[js], smu[r]);
-          stan[r] = fma(iflux[r * NS + js], tang[js], stan[r]);
-        }
-      }
-      const double dz = a.cp.dz[il];
-      const double air_abs = SSB_LAY(a.lw.air_ext, g, il) * (1.0 - SSB_LAY(a.lw.air_ssa, g, il));
-      SSB_FL(f, clear_air_abs, il) = air_abs * smu[0] - book[0] * dz;
-      if (NREG > 1) {
-        const double vabs = ve * (1.0 - SSB_LAY(a.lw.veg_ssa, g, il));
-        double s_air = 0.0, s_veg = 0.0;
-        SSB_UNROLL
-        for (int r = 1; r < NREG; ++r) {
-          s_air += air_abs * smu[r] - book[d + r] * dz;
-          s_veg += vabs * smu[r] * gm.od_scaling[r] - book[2 * d + r] * dz;
-        }
-        SSB_FL(f, veg_air_abs, il) = s_air;
-        SSB_FL(f, veg_abs, il) = s_veg;
-      }
-      if (URBAN) {
-        double win = 0.0;
-        SSB_UNROLL
-        for (int r = 0; r < NREG; ++r) win += gm.f_wall[r] * stan[r];
-        const double wemis = SSB_LAY(a.lw.wall_emissivity, g, il);
-        SSB_FL(f, wall_in, il) = win;
-        SSB_FL(f, wall_net, il) = win * wemis - book[3 * d] * dz;
+        const double r = L.ld(Lay::oR + i + n * j, jl);
+        z2_i[i] = fma(r, sa[j], z2_i[i]);
+        ub_i[i] = fma(r, xb_i[j], ub_i[i]);
+        ub_f[i] = fma(r, xb_f[j], ub_f[i]);
       }
     }
-    double s_dn = 0.0, s_up = 0.0, s_vert = 0.0;
+    {
+      double LU[n * n];
+      SSB_UNROLL
+      for (int i = 0; i < n * n; ++i) LU[i] = W.ld(Lay::oLU + i, jl);
+      sm_lu_solve_left<n, 1>(LU, z1_i);
+      sm_lu_solve_left<n, 1>(LU, z1_f);
+      sm_lu_solve_left<n, 1>(LU, z2_i);
+      sm_lu_solve_left<n, 1>(LU, z2_f);
+    }
+    smv2<n, n>(L, Lay::oT, jl, z1_i, z1_f, ub_i, ub_f);
+    if (URBAN) {
+      const double bfj = a.cp.building_fraction[il];
+      const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + 1]) : bfj;
+      const double remis = SSB_LAY(a.lw.roof_emissivity, g, il), remission = SSB_LAY(a.lw.roof_emission, g, il);
+      double sroof_i = 0.0, sroof_f = 0.0, rup_i = 0.0, rup_f = 0.0;
+      SSB_UNROLL
+      for (int js = 0; js < NS; ++js) {
+        sroof_i += xb_i[n + js];
+        sroof_f += xb_f[n + js];
+      }
+      SSB_UNROLL
+      for (int js = 0; js < NS; ++js) {
+        ub_i[n + js] = (1.0 - remis) * hw[js] * sroof_i + hw[js] * remission * exposed;
+        ub_f[n + js] = (1.0 - remis) * hw[js] * sroof_f;
+        rup_i += ub_i[n + js];
+        rup_f += ub_f[n + js];
+      }
+      SSB_FL(fint, roof_in, il) = sroof_i;
+      SSB_FL(fint, roof_net, il) = sroof_i - rup_i;
+      SSB_FL(fnorm, roof_in, il) = sroof_f;
+      SSB_FL(fnorm, roof_net, il) = sroof_f - rup_f;
+    }
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      xa_i[i] = z2_i[i];
+      xa_f[i] = z2_f[i];
+      ua_i[i] = sa[i];
+      ua_f[i] = 0.0;
+    }
+    smv2<n, n>(W, Lay::oAa, jl, xa_i, xa_f, ua_i, ua_f);
+    if (fint.flux_dn_layer_top || fnorm.flux_dn_layer_top) {
+      double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) {
+        s[0] += xb_i[i];
+        s[1] += xa_i[i];
+        s[2] += ub_i[i];
+        s[3] += ua_i[i];
+        s[4] += xb_f[i];
+        s[5] += xa_f[i];
+        s[6] += ub_f[i];
+        s[7] += ua_f[i];
+      }
+      if (fint.flux_dn_layer_top) {
+        SSB_FL(fint, flux_dn_layer_top, il) = s[0];
+        SSB_FL(fint, flux_dn_layer_base, il) = s[1];
+        SSB_FL(fint, flux_up_layer_top, il) = s[2];
+        SSB_FL(fint, flux_up_layer_base, il) = s[3];
+      }
+      if (fnorm.flux_dn_layer_top) {
+        SSB_FL(fnorm, flux_dn_layer_top, il) = s[4];
+        SSB_FL(fnorm, flux_dn_layer_base, il) = s[5];
+        SSB_FL(fnorm, flux_up_layer_top, il) = s[6];
+        SSB_FL(fnorm, flux_up_layer_base, il) = s[7];
+      }
+    }
+    double if_i[n], if_f[n], book[3 * d + 1];
+    {
+      double tv_i[n], tv_f[n];
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) {
+        tv_i[i] = xb_i[i] + ua_i[i];
+        tv_f[i] = xb_f[i] + ua_f[i];
+        if_i[i] = L.ld(Lay::oIsrc + i, jl);
+        if_f[i] = 0.0;
+      }
+      smv2<n, n>(L, Lay::oIF, jl, tv_i, tv_f, if_i, if_f);
+      SSB_UNROLL
+      for (int i = 0; i < 3 * d + 1; ++i) book[i] = L.ld(Lay::oBook + i, jl);
+    }
+    double smu_i[NREG], smu_f[NREG], stan_i[NREG], stan_f[NREG];
+    SSB_UNROLL
+    for (int r = 0; r < NREG; ++r) {
+      smu_i[r] = smu_f[r] = stan_i[r] = stan_f[r] = 0.0;
+      SSB_UNROLL
+      for (int js = 0; js < NS; ++js) {
+        smu_i[r] = fma(if_i[r * NS + js], mu_inv[js], smu_i[r]);
+        smu_f[r] = fma(if_f[r * NS + js], mu_inv[js], smu_f[r]);
+        stan_i[r] = fma(if_i[r * NS + js], tang[js], stan_i[r]);
+        stan_f[r] = fma(if_f[r * NS + js], tang[js], stan_f[r]);
+      }
+    }
+    const double dz = a.cp.dz[il];
+    const double air_abs = SSB_LAY(a.lw.air_ext, g, il) * (1.0 - SSB_LAY(a.lw.air_ssa, g, il));
+    SSB_FL(fint, clear_air_abs, il) = air_abs * smu_i[0] - book[0] * dz;
+    SSB_FL(fnorm, clear_air_abs, il) = air_abs * smu_f[0];
+    if (NREG > 1) {
+      const double vabs = ve * (1.0 - SSB_LAY(a.lw.veg_ssa, g, il));
+      double air_i = 0.0, veg_i = 0.0, air_f = 0.0, veg_f = 0.0;
+      SSB_UNROLL
+      for (int r = 1; r < NREG; ++r) {
+        air_i += air_abs * smu_i[r] - book[d + r] * dz;
+        veg_i += vabs * smu_i[r] * gm.od_scaling[r] - book[2 * d + r] * dz;
+        air_f += air_abs * smu_f[r];
+        veg_f += vabs * smu_f[r] * gm.od_scaling[r];
+      }
+      SSB_FL(fint, veg_air_abs, il) = air_i;
+      SSB_FL(fint, veg_abs, il) = veg_i;
+      SSB_FL(fnorm, veg_air_abs, il) = air_f;
+      SSB_FL(fnorm, veg_abs, il) = veg_f;
+    }
+    if (URBAN) {
+      double win_i = 0.0, win_f = 0.0;
+      SSB_UNROLL
+      for (int r = 0; r < NREG; ++r) {
+        win_i += gm.f_wall[r] * stan_i[r];
+        win_f += gm.f_wall[r] * stan_f[r];
+      }
+      const double wemis = SSB_LAY(a.lw.wall_emissivity, g, il);
+      SSB_FL(fint, wall_in, il) = win_i;
+      SSB_FL(fint, wall_net, il) = win_i * wemis - book[3 * d] * dz;
+      SSB_FL(fnorm, wall_in, il) = win_f;
+      SSB_FL(fnorm, wall_net, il) = win_f * wemis;
+    }
+  }
+  {
+    double dn_i = 0.0, up_i = 0.0, vt_i = 0.0, dn_f = 0.0, up_f = 0.0, vt_f = 0.0;
     SSB_UNROLL
     for (int r = 0; r < NREG; ++r) {
       SSB_UNROLL
       for (int js = 0; js < NS; ++js) {
         const int i = js + r * NS;
-        s_dn += dn_above[i];
-        s_up += up_above[i];
-        s_vert += (dn_above[i] + up_above[i]) * tang[js] / SSB_PI;
+        dn_i += xa_i[i];
+        up_i += ua_i[i];
+        vt_i += (xa_i[i] + ua_i[i]) * tang[js] / SSB_PI;
+        dn_f += xa_f[i];
+        up_f += ua_f[i];
+        vt_f += (xa_f[i] + ua_f[i]) * tang[js] / SSB_PI;
       }
     }
-    SSB_FC(f, ground_dn) = s_dn;
-    SSB_FC(f, ground_net) = s_dn - s_up;
+    SSB_FC(fint, ground_dn) = dn_i;
+    SSB_FC(fint, ground_net) = dn_i - up_i;
+    SSB_FC(fnorm, ground_dn) = dn_f;
+    SSB_FC(fnorm, ground_net) = dn_f - up_f;
     // forest_lw:687-694 accumulates the normalised pass into lw_internal as well
-    if (internal) {
-      gvd_internal = s_vert;
-      SSB_FC(f, ground_vertical_diff) = s_vert;
-    } else if (URBAN) {
-      SSB_FC(f, ground_vertical_diff) = s_vert;
+    if (URBAN) {
+      SSB_FC(fint, ground_vertical_diff) = vt_i;
+      SSB_FC(fnorm, ground_vertical_diff) = vt_f;
     } else {
-      SSB_FC(fint, ground_vertical_diff) = gvd_internal + s_vert;
+      SSB_FC(fint, ground_vertical_diff) = vt_i + vt_f;
     }
   }
 }

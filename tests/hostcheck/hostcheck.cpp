@@ -64,11 +64,13 @@ struct HostBackend {
   }
   template <int NS, bool LW, int NREG, bool URBAN>
   void fast_sweeps(const ssb::ClassArgs &a, long nt) {
+    double state[64];
+    const ssb::StateMem st{state, 1};
     for (long t = 0; t < nt; ++t) {
       if (LW)
-        ssb::fast_column_sweeps_lw<NREG, (NS <= 2 ? NS : 1), URBAN>(a, (int)t);
+        ssb::fast_column_sweeps_lw<NREG, (NS <= 2 ? NS : 1), URBAN>(a, (int)t, st);
       else
-        ssb::fast_column_sweeps_sw<NREG, (NS <= 2 ? NS : 1), URBAN>(a, (int)t);
+        ssb::fast_column_sweeps_sw<NREG, (NS <= 2 ? NS : 1), URBAN>(a, (int)t, st);
     }
   }
   template <int NS, bool LW>
