@@ -143,7 +143,7 @@ struct Context {
   ssb::Plan plan;
   bool plan_uploaded = false;
   long uploaded_generation = -1;
-  DevBuf d_nlay, d_istart, d_irep, d_cols, d_scratch, d_status, d_lay2col;
+  DevBuf d_nlay, d_istart, d_irep, d_cols, d_scratch, d_status, d_lay2col, d_perm;
   std::vector<DevBuf> stage;  // staging mirrors of host arrays for ssb200_radsurf
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -154,6 +154,7 @@ struct Context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaError_t first_error = cudaSuccess;
   int fast_mode = 1;
+  int partition = 1;  // group layer problems by solved sub-block before the fast layer kernels
   int fast_minblocks = 3, fast_minblocks_sweeps = 2;  // __launch_bounds__ min blocks of the fast kernels
 };
 Context g_ctx;
@@ -202,7 +203,13 @@ struct CudaBackend {
   void layer_sw(const ssb::ClassArgs &a, long nt) {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(0, true);
-      const bool done = ssb::fast_layer_sw<NS>(a, nt, cx.stream, cx.fast_minblocks);
+      ssb::ClassArgs b = a;
+      if (cx.partition && cx.d_perm.reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
+        b.perm_count = (int *)cx.d_perm.p;
+        b.perm = b.perm_count + 4;
+      }
+      const bool done = ssb::fast_layer_sw<NS>(b, nt, cx.stream, cx.fast_minblocks);
+      if (done && b.perm) g_launches += 4;
       if (done) check_launch();
       tick(0, false);
       if (done) return;
@@ -213,7 +220,13 @@ struct CudaBackend {
   void layer_lw(const ssb::ClassArgs &a, long nt) {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(2, true);
-      const bool done = ssb::fast_layer_lw<NS>(a, nt, cx.stream, cx.fast_minblocks);
+      ssb::ClassArgs b = a;
+      if (cx.partition && cx.d_perm.reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
+        b.perm_count = (int *)cx.d_perm.p;
+        b.perm = b.perm_count + 4;
+      }
+      const bool done = ssb::fast_layer_lw<NS>(b, nt, cx.stream, cx.fast_minblocks);
+      if (done && b.perm) g_launches += 4;
       if (done) check_launch();
       tick(2, false);
       if (done) return;
@@ -670,6 +683,10 @@ int ssb200_set_option(const char *name, int64_t value) {
     g_ctx.fast_mode = value != 0;
     return 0;
   }
+  if (n == "partition_layers") {
+    g_ctx.partition = value != 0;
+    return 0;
+  }
   if (n == "fast_minblocks") {
     g_ctx.fast_minblocks = (int)value;
     return 0;
@@ -686,7 +703,7 @@ int ssb200_release(void) {
   Context &cx = g_ctx;
   if (ssb200_device_count() > 0) {
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&cx.d_nlay, &cx.d_istart, &cx.d_irep, &cx.d_cols, &cx.d_scratch, &cx.d_status, &cx.d_lay2col})
+    for (DevBuf *b : {&cx.d_nlay, &cx.d_istart, &cx.d_irep, &cx.d_cols, &cx.d_scratch, &cx.d_status, &cx.d_lay2col, &cx.d_perm})
       b->release();
     for (DevBuf &b : cx.stage) b.release();
   }

@@ -10,6 +10,30 @@ namespace ssb {
 
 constexpr int kFastBlock = 128;
 
+// Groups the layer problems of a launch by the sub-block of regions they solve, so
+// that every warp of the layer kernels runs one code path.  Warp-aggregated
+// append: the order inside a segment is not deterministic, the results are
+// (every problem is independent).
+static __global__ void k_partition_layers(ClassArgs a, long nt, int sw) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  int seg = -1;
+  if (t < nt) {
+    const long width = (long)a.ncols * a.cfg.nspec;
+    seg = classify_layer_problem(a, (int)(t % width), (int)(t / width), sw != 0);
+  }
+  const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const unsigned mask = __ballot_sync(0xffffffffu, seg == k);
+    if (mask == 0u) continue;
+    int base = 0;
+    const int leader = __ffs(mask) - 1;
+    if ((int)lane == leader) base = atomicAdd(&a.perm_count[k], __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (seg == k) a.perm[(size_t)k * (size_t)nt + base + __popc(mask & ((1u << lane) - 1u))] = (int)t;
+  }
+}
+
 #ifdef SSB_KIND_SW
 template <int NREG, int NS, int MINB>
 __global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_sw(ClassArgs a, long nt) {
@@ -18,9 +42,25 @@ __global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_sw(ClassArgs a,
   const long width = (long)a.ncols * a.cfg.nspec;
   fast_layer_problem_sw<NREG, NS>(a, (int)(t % width), (int)(t / width));
 }
+template <int NREG, int NS, int SEG, int MINB>
+__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_sw_seg(ClassArgs a, long nt) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= a.perm_count[SEG]) return;
+  const long id = a.perm[(size_t)SEG * (size_t)nt + t];
+  const long width = (long)a.ncols * a.cfg.nspec;
+  fast_layer_problem_sw_seg<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width));
+}
 template <int NREG, int NS>
 static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
+  if (a.perm != nullptr) {
+    cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
+    k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt, 1);
+    k_fast_layer_sw_seg<NREG, NS, 0, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
+    if (NREG > 1) k_fast_layer_sw_seg<NREG, NS, 1, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
+    if (NREG > 1) k_fast_layer_sw_seg<NREG, NS, 2, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
+    return;
+  }
   if (minb >= 4)
     k_fast_layer_sw<NREG, NS, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
   else if (minb == 3)
@@ -84,9 +124,25 @@ __global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_lw(ClassArgs a,
   const long width = (long)a.ncols * a.cfg.nspec;
   fast_layer_problem_lw<NREG, NS>(a, (int)(t % width), (int)(t / width));
 }
+template <int NREG, int NS, int SEG, int MINB>
+__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_lw_seg(ClassArgs a, long nt) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= a.perm_count[SEG]) return;
+  const long id = a.perm[(size_t)SEG * (size_t)nt + t];
+  const long width = (long)a.ncols * a.cfg.nspec;
+  fast_layer_problem_lw_impl<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width));
+}
 template <int NREG, int NS>
 static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
+  if (a.perm != nullptr) {
+    cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
+    k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt, 0);
+    k_fast_layer_lw_seg<NREG, NS, 0, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
+    if (NREG > 1) k_fast_layer_lw_seg<NREG, NS, 1, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
+    if (NREG > 1) k_fast_layer_lw_seg<NREG, NS, 2, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
+    return;
+  }
   if (minb >= 4)
     k_fast_layer_lw<NREG, NS, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
   else if (minb == 3)

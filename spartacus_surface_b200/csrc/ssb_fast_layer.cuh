@@ -128,16 +128,23 @@ SSB_HDI void load_geometry_inputs(const ClassArgs &a, int il, double &bf, double
   vfsd = (c.nreg == 3) ? a.cp.veg_fsd[il] : 0.0;
 }
 
+// which sub-block of regions a layer solves: 0 = all regions, 1 = clear region only,
+// 2 = vegetated regions only (radsurf_urban_sw.F90:512-583)
+SSB_HDI int branch_segment(const LayerGeom &gm, int nreg) {
+  if (gm.nr == nreg) return 0;
+  return gm.r0 == 0 ? 1 : 2;
+}
+
+// inputs of one shortwave layer problem; false when the problem is skipped
 template <int NREG, int NS>
-SSB_HD inline void fast_layer_problem_sw(const ClassArgs &a, int q, int lev) {
+SSB_HDI bool fast_sw_prepare(const ClassArgs &a, int q, int lev, LayerGeom &gm, LayerOptics &op) {
   const SolveCfg &c = a.cfg;
   const int nspec = c.nspec;
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
-  if (lev >= a.nlay[col]) return;
-  LayerOptics op;
+  if (lev >= a.nlay[col]) return false;
   op.cos_sza = a.cp.cos_sza[col];
-  if (!(op.cos_sza > 0.0)) return;
+  if (!(op.cos_sza > 0.0)) return false;
   const int il = a.istartlay[col] - 1 + lev;
   op.zcos = c.urban ? dmax(op.cos_sza, 1.0e-6) : op.cos_sza;
   op.sin0 = 0.0;
@@ -150,7 +157,6 @@ SSB_HD inline void fast_layer_problem_sw(const ClassArgs &a, int q, int lev) {
   op.dz = a.cp.dz[il];
   double bf, bs, vf, vs, ve, vcf, vfsd;
   load_geometry_inputs(a, il, bf, bs, vf, vs, ve, vcf, vfsd);
-  LayerGeom gm;
   layer_geometry(c, bf, bs, vf, vs, vcf, vfsd, 1.0, gm);
   op.ext[0] = SSB_LAY(a.sw.air_ext, g, il);
   op.ssa[0] = SSB_LAY(a.sw.air_ssa, g, il);
@@ -168,13 +174,33 @@ SSB_HD inline void fast_layer_problem_sw(const ClassArgs &a, int q, int lev) {
     op.wall_ext = 1.0 - wa * wsf;
     op.wall_factor = wa * (1.0 - wsf);
   }
-  if (gm.nr == NREG) {
+  return true;
+}
+
+template <int NREG, int NS>
+SSB_HD inline void fast_layer_problem_sw(const ClassArgs &a, int q, int lev) {
+  LayerGeom gm;
+  LayerOptics op;
+  if (!fast_sw_prepare<NREG, NS>(a, q, lev, gm, op)) return;
+  const int seg = branch_segment(gm, NREG);
+  if (seg == 0) {
     fast_sw_branch<NREG, NS, NREG, 0>(a, q, lev, gm, op);
-  } else if (gm.r0 == 0) {
+  } else if (seg == 1) {
     fast_sw_branch<NREG, NS, 1, 0>(a, q, lev, gm, op);  // vegetation-free layer: clear region only
   } else {
     if (NREG > 1) fast_sw_branch<NREG, NS, (NREG > 1 ? NREG - 1 : 1), (NREG > 1 ? 1 : 0)>(a, q, lev, gm, op);
   }
+}
+
+// one pre-classified problem: SEG is known at compile time, so only one sub-block size is instantiated
+template <int NREG, int NS, int SEG>
+SSB_HDI void fast_layer_problem_sw_seg(const ClassArgs &a, int q, int lev) {
+  LayerGeom gm;
+  LayerOptics op;
+  if (!fast_sw_prepare<NREG, NS>(a, q, lev, gm, op)) return;
+  constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
+  constexpr int R0 = (SEG == 2 && NREG > 1) ? 1 : 0;
+  fast_sw_branch<NREG, NS, NR, R0>(a, q, lev, gm, op);
 }
 
 template <int NREG, int NS, int NR, int R0>
@@ -254,8 +280,9 @@ SSB_HDI void fast_lw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
   count_failure(a.status, bad ? 1 : 0);
 }
 
-template <int NREG, int NS>
-SSB_HD inline void fast_layer_problem_lw(const ClassArgs &a, int q, int lev) {
+// inputs of one longwave layer problem (also writes the emission bookkeeping terms); SEG < 0: dispatch at run time
+template <int NREG, int NS, int SEG>
+SSB_HDI void fast_layer_problem_lw_impl(const ClassArgs &a, int q, int lev) {
   const SolveCfg &c = a.cfg;
   const int nspec = c.nspec;
   const int ic = q / nspec, g = q % nspec;
@@ -313,14 +340,40 @@ SSB_HD inline void fast_layer_problem_lw(const ClassArgs &a, int q, int lev) {
   }
   a.layer[sidx(e_book + 3 * d, lev, nlev, width, q)] = c.urban ? (wsum * a.lg.vadjustment) * wall_emission : 0.0;
 
-  if (gm.nr == NREG) {
+  if (SEG >= 0) {
+    constexpr int NR = (SEG <= 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
+    constexpr int R0 = (SEG == 2 && NREG > 1) ? 1 : 0;
+    fast_lw_branch<NREG, NS, NR, R0>(a, q, lev, gm, op, wall_emission, g, il);
+    return;
+  }
+  const int seg = branch_segment(gm, NREG);
+  if (seg == 0) {
     fast_lw_branch<NREG, NS, NREG, 0>(a, q, lev, gm, op, wall_emission, g, il);
-  } else if (gm.r0 == 0) {
+  } else if (seg == 1) {
     fast_lw_branch<NREG, NS, 1, 0>(a, q, lev, gm, op, wall_emission, g, il);
   } else {
     if (NREG > 1)
       fast_lw_branch<NREG, NS, (NREG > 1 ? NREG - 1 : 1), (NREG > 1 ? 1 : 0)>(a, q, lev, gm, op, wall_emission, g, il);
   }
+}
+
+template <int NREG, int NS>
+SSB_HD inline void fast_layer_problem_lw(const ClassArgs &a, int q, int lev) {
+  fast_layer_problem_lw_impl<NREG, NS, -1>(a, q, lev);
+}
+
+// segment of a layer problem for the partition kernel; -1 when the problem is skipped
+SSB_HDI int classify_layer_problem(const ClassArgs &a, int q, int lev, bool sw) {
+  const SolveCfg &c = a.cfg;
+  const int col = a.cols[q / c.nspec];
+  if (lev >= a.nlay[col]) return -1;
+  if (sw && !(a.cp.cos_sza[col] > 0.0)) return -1;
+  const int il = a.istartlay[col] - 1 + lev;
+  double bf, bs, vf, vs, ve, vcf, vfsd;
+  load_geometry_inputs(a, il, bf, bs, vf, vs, ve, vcf, vfsd);
+  LayerGeom gm;
+  layer_geometry(c, bf, bs, vf, vs, vcf, vfsd, 1.0, gm);
+  return branch_segment(gm, c.nreg);
 }
 
 }  // namespace ssb

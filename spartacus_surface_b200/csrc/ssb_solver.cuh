@@ -47,6 +47,8 @@ struct ClassArgs {
   ssb200_canopy_flux f1, f2;  // SW: norm_dir, norm_diff ; LW: internal, norm
   double *layer;              // layer-matrix scratch
   double *sweep;              // interface scratch
+  int *perm;                  // fast path: layer problems grouped by solved sub-block (3 segments of nt)
+  int *perm_count;            // [3] problems per segment
   int *status;                // failure counter
 };
 
