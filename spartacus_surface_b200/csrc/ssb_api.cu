@@ -143,7 +143,11 @@ struct Context {
   ssb::Plan plan;
   bool plan_uploaded = false;
   long uploaded_generation = -1;
-  DevBuf d_nlay, d_istart, d_irep, d_cols, d_scratch, d_status, d_lay2col, d_perm;
+  DevBuf d_nlay, d_istart, d_irep, d_cols, d_status, d_lay2col;
+  static constexpr int kLanes = 3;  // lane 0: device entry / bulk path; lanes 0-2: pipelined host entry
+  DevBuf d_scratch[kLanes], d_perm[kLanes];
+  cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr};
+  int pipeline = 1;
   std::vector<DevBuf> stage;  // staging mirrors of host arrays for ssb200_radsurf
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -161,17 +165,20 @@ Context g_ctx;
 
 struct CudaBackend {
   Context &cx;
-  explicit CudaBackend(Context &c) : cx(c) {}
+  int lane;
+  size_t budget;
+  explicit CudaBackend(Context &c, int lane_ = 0, size_t budget_ = 0)
+      : cx(c), lane(lane_), budget(budget_ ? budget_ : c.budget_doubles) {}
   const int *dev_cols(const ssb::Plan &, size_t off) { return (const int *)cx.d_cols.p + off; }
   const int *dev_nlay() { return (const int *)cx.d_nlay.p; }
   const int *dev_istartlay() { return (const int *)cx.d_istart.p; }
   const int *dev_irep() { return (const int *)cx.d_irep.p; }
   int *dev_status() { return (int *)cx.d_status.p; }
-  size_t scratch_budget_doubles() { return cx.budget_doubles; }
+  size_t scratch_budget_doubles() { return budget; }
   double *scratch(size_t n) {
-    cudaError_t e = cx.d_scratch.reserve(n * sizeof(double));
+    cudaError_t e = cx.d_scratch[lane].reserve(n * sizeof(double));
     if (e != cudaSuccess && cx.first_error == cudaSuccess) cx.first_error = e;
-    return (double *)cx.d_scratch.p;
+    return (double *)cx.d_scratch[lane].p;
   }
   void tick(int family, bool start) {
     if (!cx.profiling) return;
@@ -204,8 +211,8 @@ struct CudaBackend {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(0, true);
       ssb::ClassArgs b = a;
-      if (cx.partition && cx.d_perm.reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
-        b.perm_count = (int *)cx.d_perm.p;
+      if (cx.partition && cx.d_perm[lane].reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
+        b.perm_count = (int *)cx.d_perm[lane].p;
         b.perm = b.perm_count + 4;
       }
       const bool done = ssb::fast_layer_sw<NS>(b, nt, cx.stream, cx.fast_minblocks);
@@ -221,8 +228,8 @@ struct CudaBackend {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(2, true);
       ssb::ClassArgs b = a;
-      if (cx.partition && cx.d_perm.reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
-        b.perm_count = (int *)cx.d_perm.p;
+      if (cx.partition && cx.d_perm[lane].reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
+        b.perm_count = (int *)cx.d_perm[lane].p;
         b.perm = b.perm_count + 4;
       }
       const bool done = ssb::fast_layer_lw<NS>(b, nt, cx.stream, cx.fast_minblocks);
@@ -294,8 +301,11 @@ int upload_plan(Context &cx, const ssb200_canopy_properties &cp) {
 }
 
 // Core of both entry points; all double arrays are device pointers here.
+// `blocks`: when non-null the call only prepares (plan, status, budget) and returns the
+// clamped 1-based column range in blocks[0..1]; the caller then dispatches column
+// windows itself with run_window().
 int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, int iendcol, cudaStream_t stream,
-                          int32_t *status_out) {
+                          int32_t *status_out, int *blocks = nullptr) {
   std::string err;
   int rc = ssb::validate_call(ca, err);
   if (rc) return fail(rc, err);
@@ -321,7 +331,7 @@ int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, i
   if (cx.budget_doubles == 0) {
     size_t free_b = 0, total_b = 0;
     SSB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t b = (free_b + cx.d_scratch.bytes) / 2;
+    size_t b = (free_b + cx.d_scratch[0].bytes + cx.d_scratch[1].bytes + cx.d_scratch[2].bytes) / 2;
     const size_t cap = (size_t)24 << 30;
     if (b > cap) b = cap;
     cx.budget_doubles = b / sizeof(double);
@@ -334,6 +344,11 @@ int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, i
     for (double &t : cx.times_ms) t = 0.0;
     for (long long &n : cx.counts) n = 0;
   }
+  if (blocks) {
+    blocks[0] = c1;
+    blocks[1] = c2;
+    return 0;
+  }
   CudaBackend be(cx);
   ssb::Dispatcher<CudaBackend> disp(be);
   rc = disp.run(ca, cx.plan, err);
@@ -345,41 +360,59 @@ int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, i
   return 0;
 }
 
+// dispatch the columns [col_lo, col_hi) (0-based) of the prepared plan on one lane
+int run_window(Context &cx, const ssb::CallArgs &ca, int lane, size_t budget, int col_lo, int col_hi) {
+  std::string err;
+  cx.stream = cx.lane_stream[lane];
+  CudaBackend be(cx, lane, budget);
+  ssb::Dispatcher<CudaBackend> disp(be);
+  disp.col_lo = col_lo;
+  disp.col_hi = col_hi;
+  const int rc = disp.run(ca, cx.plan, err);
+  if (rc) return fail(rc, err);
+  if (cx.first_error != cudaSuccess)
+    return fail(SSB200_ERR_CUDA, std::string("kernel launch / scratch allocation: ") + cudaGetErrorString(cx.first_error));
+  return 0;
+}
+
 // --- host-pointer staging --------------------------------------------------
 struct Stager {
   Context &cx;
   cudaStream_t stream;
   int next = 0;
   int rc = 0;
-  struct Out {
+  struct Arr {
     double *host;
     double *dev;
-    size_t off, cnt;
+    size_t width;    // doubles per column (per_layer = false) or per packed layer (true)
+    bool per_layer, upload, download;
   };
-  std::vector<Out> outs;
+  std::vector<Arr> arrs;
   Stager(Context &c, cudaStream_t s) : cx(c), stream(s) {}
-  // mirror `host[0 .. total)` on the device, copying only [off, off+cnt)
-  double *mirror(const double *host, size_t total, size_t off, size_t cnt, bool upload, bool download) {
+  // device mirror of `host` (total = rows * width doubles); copies are issued per window
+  double *mirror(const double *host, size_t rows, size_t width, bool per_layer, bool upload, bool download) {
     if (!host || rc) return nullptr;
     if ((size_t)next >= cx.stage.size()) cx.stage.resize((size_t)next + 16);
     DevBuf &b = cx.stage[next++];
+    const size_t total = rows * width;
     cudaError_t e = b.reserve((total > 0 ? total : 1) * sizeof(double));
     if (e != cudaSuccess) {
       rc = fail(SSB200_ERR_CUDA, std::string("staging allocation: ") + cudaGetErrorString(e));
       return nullptr;
     }
-    double *d = (double *)b.p;
-    if (upload && cnt > 0) {
-      e = cudaMemcpyAsync(d + off, host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, stream);
-      if (e != cudaSuccess) rc = fail(SSB200_ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
-    }
-    if (download && cnt > 0) outs.push_back(Out{const_cast<double *>(host), d, off, cnt});
-    return d;
+    arrs.push_back(Arr{const_cast<double *>(host), (double *)b.p, width, per_layer, upload, download});
+    return (double *)b.p;
   }
-  int download_all() {
-    for (const Out &o : outs) {
-      cudaError_t e = cudaMemcpyAsync(o.host + o.off, o.dev + o.off, o.cnt * sizeof(double), cudaMemcpyDeviceToHost, stream);
-      if (e != cudaSuccess) return fail(SSB200_ERR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+  // copy the slices of columns [c0, c1) / packed layers [l0, l1) on stream `st`
+  int copy_window(bool to_device, size_t c0, size_t c1, size_t l0, size_t l1, cudaStream_t st) {
+    for (const Arr &a : arrs) {
+      if (to_device ? !a.upload : !a.download) continue;
+      const size_t off = (a.per_layer ? l0 : c0) * a.width, cnt = ((a.per_layer ? l1 : c1) * a.width) - off;
+      if (cnt == 0) continue;
+      cudaError_t e = to_device ? cudaMemcpyAsync(a.dev + off, a.host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, st)
+                                : cudaMemcpyAsync(a.host + off, a.dev + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess)
+        return fail(SSB200_ERR_CUDA, std::string(to_device ? "H2D copy: " : "D2H copy: ") + cudaGetErrorString(e));
     }
     return 0;
   }
@@ -531,8 +564,8 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   const size_t cO = (size_t)(c1 - 1), cN = (size_t)(c2 - c1 + 1), lN = l2 - l1;
   Stager sg(cx, st);
   ssb200_canopy_properties dcp = *cp;
-  auto lay1 = [&](const double *h) { return (const double *)sg.mirror(h, ntot, l1, lN, true, false); };
-  dcp.cos_sza = sg.mirror(cp->cos_sza, ncol, cO, cN, true, false);
+  auto lay1 = [&](const double *h) { return (const double *)sg.mirror(h, ntot, 1, true, true, false); };
+  dcp.cos_sza = sg.mirror(cp->cos_sza, ncol, 1, false, true, false);
   dcp.dz = lay1(cp->dz);
   dcp.building_fraction = lay1(cp->building_fraction);
   dcp.building_scale = lay1(cp->building_scale);
@@ -547,8 +580,8 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   memset(&dlw, 0, sizeof(dlw));
   if (config->do_sw) {
     const size_t g = (size_t)config->nsw;
-    auto L = [&](const double *h) { return (const double *)sg.mirror(h, ntot * g, l1 * g, lN * g, true, false); };
-    auto Cc = [&](const double *h) { return (const double *)sg.mirror(h, ncol * g, cO * g, cN * g, true, false); };
+    auto L = [&](const double *h) { return (const double *)sg.mirror(h, ntot, g, true, true, false); };
+    auto Cc = [&](const double *h) { return (const double *)sg.mirror(h, ncol, g, false, true, false); };
     dsw.nspec = sw->nspec;
     dsw.air_ext = L(sw->air_ext);
     dsw.air_ssa = L(sw->air_ssa);
@@ -562,8 +595,8 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   }
   if (config->do_lw) {
     const size_t g = (size_t)config->nlw;
-    auto L = [&](const double *h) { return (const double *)sg.mirror(h, ntot * g, l1 * g, lN * g, true, false); };
-    auto Cc = [&](const double *h) { return (const double *)sg.mirror(h, ncol * g, cO * g, cN * g, true, false); };
+    auto L = [&](const double *h) { return (const double *)sg.mirror(h, ntot, g, true, true, false); };
+    auto Cc = [&](const double *h) { return (const double *)sg.mirror(h, ncol, g, false, true, false); };
     dlw.nspec = lw->nspec;
     dlw.air_ext = L(lw->air_ext);
     dlw.air_ssa = L(lw->air_ssa);
@@ -586,21 +619,21 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   {
     const size_t gs = (size_t)config->nsw, gl = (size_t)config->nlw;
     if (config->do_sw) {
-      dbc.sw_albedo = sg.mirror(bc->sw_albedo, ncol * gs, cO * gs, cN * gs, true, true);
-      dbc.sw_albedo_dir = sg.mirror(bc->sw_albedo_dir, ncol * gs, cO * gs, cN * gs, true, true);
+      dbc.sw_albedo = sg.mirror(bc->sw_albedo, ncol, gs, false, true, true);
+      dbc.sw_albedo_dir = sg.mirror(bc->sw_albedo_dir, ncol, gs, false, true, true);
     }
     if (config->do_lw) {
-      dbc.lw_emissivity = sg.mirror(bc->lw_emissivity, ncol * gl, cO * gl, cN * gl, true, true);
-      dbc.lw_emission = sg.mirror(bc->lw_emission, ncol * gl, cO * gl, cN * gl, true, true);
+      dbc.lw_emissivity = sg.mirror(bc->lw_emissivity, ncol, gl, false, true, true);
+      dbc.lw_emission = sg.mirror(bc->lw_emission, ncol, gl, false, true, true);
     }
   }
   auto stage_flux = [&](const ssb200_canopy_flux *h, ssb200_canopy_flux &d) {
     d = *h;
     const size_t g = (size_t)h->nspec;
-    auto Cc = [&](double *p) { return sg.mirror(p, ncol * g, cO * g, cN * g, true, true); };
-    auto L = [&](double *p) { return sg.mirror(p, ntot * g, l1 * g, lN * g, !contiguous, true); };
-    auto C1 = [&](double *p) { return sg.mirror(p, ncol, cO, cN, true, true); };
-    auto L1 = [&](double *p) { return sg.mirror(p, ntot, l1, lN, !contiguous, true); };
+    auto Cc = [&](double *p) { return sg.mirror(p, ncol, g, false, true, true); };
+    auto L = [&](double *p) { return sg.mirror(p, ntot, g, true, !contiguous, true); };
+    auto C1 = [&](double *p) { return sg.mirror(p, ncol, 1, false, true, true); };
+    auto L1 = [&](double *p) { return sg.mirror(p, ntot, 1, true, !contiguous, true); };
     d.ground_dn = Cc(h->ground_dn);
     d.ground_net = Cc(h->ground_net);
     d.ground_vertical_diff = Cc(h->ground_vertical_diff);
@@ -642,13 +675,46 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   ssb::CallArgs ca{config, &dcp, config->do_sw ? &dsw : nullptr, config->do_lw ? &dlw : nullptr, &dbc,
                    config->do_sw ? &d1 : nullptr, config->do_sw ? &d2 : nullptr,
                    config->do_lw ? &d3 : nullptr, config->do_lw ? &d4 : nullptr};
-  rc = radsurf_device_locked(cx, ca, c1, c2, st, nullptr);
+  // Pipeline: the column range is cut into blocks; block b uploads its input slices,
+  // runs its kernels and downloads its output slices on lane b % 3, so transfers of
+  // neighbouring blocks overlap the kernels (pinned host memory needed for true
+  // overlap).  Requires a contiguous packed-layer range; profiling serialises.
+  int range[2];
+  rc = radsurf_device_locked(cx, ca, c1, c2, st, nullptr, range);
   if (rc) return rc;
-  rc = sg.download_all();
-  if (rc) return rc;
+  SSB_CUDA(cudaStreamSynchronize(st));  // plan upload and status reset are visible to every lane
+  const size_t total_work = lN + cN;
+  int nblk = 1;
+  if (cx.pipeline && contiguous && !cx.profiling && total_work >= ((size_t)1 << 17)) {
+    nblk = (int)(total_work >> 16);
+    if (nblk > 12) nblk = 12;
+  }
+  const int nlanes = nblk > 1 ? Context::kLanes : 1;
+  for (int l = 0; l < nlanes; ++l)
+    if (!cx.lane_stream[l]) SSB_CUDA(cudaStreamCreateWithFlags(&cx.lane_stream[l], cudaStreamNonBlocking));
+  const size_t lane_budget = cx.budget_doubles / (size_t)nlanes;
+  // first packed layer of every column >= j (Flat tiles own no layers): block boundaries
+  auto layer_begin = [&](int j) -> size_t {
+    for (; j < c2; ++j)
+      if (cp->i_representation[j] != SSB200_TILE_FLAT && cp->nlay[j] > 0) return (size_t)cp->istartlay[j] - 1;
+    return l2;
+  };
+  for (int b = 0; b < nblk; ++b) {
+    const int lane = b % nlanes;
+    const int cb0 = (c1 - 1) + (int)(((long long)cN * b) / nblk), cb1 = (c1 - 1) + (int)(((long long)cN * (b + 1)) / nblk);
+    if (cb1 <= cb0) continue;
+    const size_t lb0 = (b == 0) ? l1 : layer_begin(cb0), lb1 = (b == nblk - 1) ? l2 : layer_begin(cb1);
+    cudaStream_t ls = cx.lane_stream[lane];
+    rc = sg.copy_window(true, (size_t)cb0, (size_t)cb1, lb0, lb1, ls);
+    if (rc) return rc;
+    rc = run_window(cx, ca, lane, lane_budget, cb0, cb1);
+    if (rc) return rc;
+    rc = sg.copy_window(false, (size_t)cb0, (size_t)cb1, lb0, lb1, ls);
+    if (rc) return rc;
+  }
+  for (int l = 0; l < nlanes; ++l) SSB_CUDA(cudaStreamSynchronize(cx.lane_stream[l]));
   int status = 0;
-  SSB_CUDA(cudaMemcpyAsync(&status, cx.d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  SSB_CUDA(cudaStreamSynchronize(st));
+  SSB_CUDA(cudaMemcpy(&status, cx.d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
   return status;
 }
 
@@ -683,6 +749,10 @@ int ssb200_set_option(const char *name, int64_t value) {
     g_ctx.fast_mode = value != 0;
     return 0;
   }
+  if (n == "pipeline") {
+    g_ctx.pipeline = value != 0;
+    return 0;
+  }
   if (n == "partition_layers") {
     g_ctx.partition = value != 0;
     return 0;
@@ -703,8 +773,11 @@ int ssb200_release(void) {
   Context &cx = g_ctx;
   if (ssb200_device_count() > 0) {
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&cx.d_nlay, &cx.d_istart, &cx.d_irep, &cx.d_cols, &cx.d_scratch, &cx.d_status, &cx.d_lay2col, &cx.d_perm})
-      b->release();
+    for (DevBuf *b : {&cx.d_nlay, &cx.d_istart, &cx.d_irep, &cx.d_cols, &cx.d_status, &cx.d_lay2col}) b->release();
+    for (int l = 0; l < Context::kLanes; ++l) {
+      cx.d_scratch[l].release();
+      cx.d_perm[l].release();
+    }
     for (DevBuf &b : cx.stage) b.release();
   }
   cx.plan = ssb::Plan();

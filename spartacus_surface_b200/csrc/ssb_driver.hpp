@@ -158,6 +158,9 @@ struct CallArgs {
 template <class Backend>
 struct Dispatcher {
   Backend &be;
+  // optional window of global column indices [col_lo, col_hi): lets the host entry
+  // pipeline transfers and kernels over blocks of columns without rebuilding the plan
+  int col_lo = 0, col_hi = 0x7fffffff;
   explicit Dispatcher(Backend &b) : be(b) {}
 
   template <int NS>
@@ -167,8 +170,9 @@ struct Dispatcher {
     const size_t el = lw ? lw_layer_elems(n, c.nreg) : sw_layer_elems(n, d);
     const size_t es = lw ? lw_sweep_elems(n, m, c.nreg, nrb) : sw_sweep_elems(n, d, m, nrb, c.nreg, nrb);
     const size_t budget = be.scratch_budget_doubles();
-    size_t pos = 0;
-    const size_t ntot = k.cols.size();
+    // class columns are ascending: restrict to the window by binary search
+    size_t pos = (size_t)(std::lower_bound(k.cols.begin(), k.cols.end(), col_lo) - k.cols.begin());
+    const size_t ntot = (size_t)(std::lower_bound(k.cols.begin(), k.cols.end(), col_hi) - k.cols.begin());
     while (pos < ntot) {
       // grow the chunk while its scratch (sized by the tallest column) fits the budget
       int lmax = 0;
@@ -253,10 +257,14 @@ struct Dispatcher {
       }
       col_offset += k.cols.size();
     }
-    if (!plan.surface_cols.empty()) {
+    const size_t s_lo = (size_t)(std::lower_bound(plan.surface_cols.begin(), plan.surface_cols.end(), col_lo) -
+                                 plan.surface_cols.begin());
+    const size_t s_hi = (size_t)(std::lower_bound(plan.surface_cols.begin(), plan.surface_cols.end(), col_hi) -
+                                 plan.surface_cols.begin());
+    if (s_hi > s_lo) {
       SurfaceArgs s;
       std::memset(&s, 0, sizeof(s));
-      s.ncols = (int)plan.surface_cols.size();
+      s.ncols = (int)(s_hi - s_lo);
       s.nsw = cfg.nsw;
       s.nlw = cfg.nlw;
       s.do_sw = cfg.do_sw;
@@ -264,7 +272,7 @@ struct Dispatcher {
       s.use_sw_direct_albedo = cfg.use_sw_direct_albedo;
       s.min_veg = cfg.min_vegetation_fraction;
       s.min_bld = cfg.min_building_fraction;
-      s.cols = be.dev_cols(plan, col_offset);
+      s.cols = be.dev_cols(plan, col_offset + s_lo);
       s.nlay = be.dev_nlay();
       s.istartlay = be.dev_istartlay();
       s.irep = be.dev_irep();
