@@ -38,6 +38,21 @@ FLOPS = {
 }
 # Compulsory HBM bytes per (column, layer): 25 input + 40 output doubles + per-column terms (§8d)
 ALGO_BYTES_PER_COL_LAYER = 540.0
+# Bytes a sweep kernel must move per (column, layer) given the layer/sweep kernel split (nreg = 3):
+# layer matrices streamed in the upward sweep (R, T twice each, S_up, S_dn, E) and in the fused downward
+# sweep, interface state (a_above, d_above / source_above, LU) written and read once, flux outputs.
+def _sweep_bytes(ns):
+    n, d = 3 * ns, 3
+    sw_up = 4 * n * n + 2 * n * d + d * d
+    sw_dn = 7 * n * n + 4 * n * d + 2 * d * d
+    sw_if = 2 * n * n + n * d
+    lw_up = 4 * n * n + n
+    lw_dn = 7 * n * n + 3 * n + 3 * d + 1
+    lw_if = 2 * n * n + n
+    return {"sw": 8.0 * (sw_up + sw_dn + 2 * sw_if + 26), "lw": 8.0 * (lw_up + lw_dn + 2 * lw_if + 14)}
+
+
+SWEEP_BYTES = {2: _sweep_bytes(2), 4: _sweep_bytes(4)}
 
 
 def make_config(streams):
@@ -264,27 +279,50 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         fl_tab = FLOPS.get(args.streams)
-        roofline = roofline_hbm = None
+        roofline = roofline_hbm = roofline_kernels = None
+        step_ms = ms_max / args.steps
         if fl_tab:
-            dom = max(("sw_layer", "lw_layer", "sw_sweep", "lw_sweep"), key=lambda k: kt[k]["ms"])
-            per_launch_ms = kt[dom]["ms"] / max(1, kt[dom]["launches"])
-            flops_per_launch = fl_tab[dom] * ncol * NLAY / max(1, kt[dom]["launches"])
-            achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
-            roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                        "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
-                        "peak_source": "measured in this run: register-resident independent DFMA chains on all SMs "
-                                       "(ssb200_measure_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
-                        "avg_launch_ms": per_launch_ms, "launches_per_step": kt[dom]["launches"],
-                        "algorithmic_flops_per_column_layer": fl_tab[dom]}
+            # per kernel family: layer kernels are FP64-bound, sweeps stream the layer matrices (HBM-bound)
+            fam_bytes = {"sw_sweep": SWEEP_BYTES[args.streams]["sw"], "lw_sweep": SWEEP_BYTES[args.streams]["lw"]}
+            roofline_kernels = {}
+            for k in ("sw_layer", "lw_layer", "sw_sweep", "lw_sweep"):
+                n_l = max(1, kt[k]["launches"])
+                per_ms = kt[k]["ms"] / n_l
+                tf = fl_tab[k] * ncol * NLAY / n_l / (per_ms * 1e-3) / 1e12
+                ent = {"avg_launch_ms": per_ms, "launches_per_step": kt[k]["launches"],
+                       "algorithmic_flops_per_column_layer": fl_tab[k], "fp64_tflops": tf,
+                       "fp64_frac": tf / fp64_peak if fp64_peak > 0 else None}
+                if k in fam_bytes:
+                    gb = fam_bytes[k] * ncol * NLAY / n_l / (per_ms * 1e-3) / 1e9
+                    ent.update({"bound": "hbm", "kernel_bytes_per_column_layer": fam_bytes[k], "gbs": gb,
+                                "hbm_frac": gb / hbm_peak})
+                else:
+                    ent["bound"] = "fp64"
+                roofline_kernels[k] = ent
+            dom = max(roofline_kernels, key=lambda k: kt[k]["ms"])
+            e = roofline_kernels[dom]
+            if e["bound"] == "fp64":
+                roofline = {"bound": "fp64", "kernel": dom, "achieved": e["fp64_tflops"], "peak": fp64_peak,
+                            "unit": "TFLOP/s", "frac": e["fp64_frac"], "traffic": None}
+            else:
+                roofline = {"bound": "hbm", "kernel": dom, "achieved": e["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                            "frac": e["hbm_frac"], "traffic": None,
+                            "bytes_note": "bytes the kernel must move given the layer/sweep split: layer matrices read in "
+                                          "the upward and in the fused downward sweep, interface state written and read "
+                                          "once, flux outputs (DESIGN.md section 4.3)"}
+            roofline.update({"avg_launch_ms": e["avg_launch_ms"], "launches_per_step": e["launches_per_step"],
+                             "fp64_peak_source": "measured in this run: register-resident independent DFMA chains on "
+                                                 "all SMs (ssb200_measure_fp64_peak_tflops); MEASURED_PEAKS.json has "
+                                                 "no FP64 entry",
+                             "hbm_peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"})
             all_flops = sum(fl_tab.values()) * ncol * NLAY
-            step_ms = ms_max / args.steps
-            roofline["whole_step"] = {"achieved": all_flops / (step_ms * 1e-3) / 1e12,
+            roofline["whole_step"] = {"bound": "fp64", "achieved": all_flops / (step_ms * 1e-3) / 1e12,
                                       "frac": all_flops / (step_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
-                                      "algorithmic_flops_per_column_layer": sum(fl_tab.values())}
+                                      "algorithmic_flops_per_column_layer": sum(fl_tab.values()),
+                                      "note": "SURVEY 8(d) flop count of the reference formulation / step time"}
             gbs = ALGO_BYTES_PER_COL_LAYER * ncol * NLAY / (step_ms * 1e-3) / 1e9
             roofline_hbm = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                            "note": "compulsory input+output bytes only; the path is FP64-bound, shown for context"}
+                            "note": "compulsory input+output bytes of the whole path only (540 B per column-layer)"}
 
         # ---- end to end through the host-pointer C ABI entry (pinned host buffers) --------------
         e2e = None
@@ -350,7 +388,20 @@ def main():
             exp = {n: {k: getattr(f, k) for k in ALL_FIELDS if getattr(f, k) is not None} for n, f in zip(names, cfl)}
             errs = parity.field_errors(got, exp)
             flux_fields = [k for k in errs if "sunlit" not in k[1]]
-            parity_err = {"max_rel_err_fluxes": max(errs[k] for k in flux_fields),
+            # verdict with the tolerance of tests/parity.py on a 4096-column subsample (needs the no-FMA oracle)
+            ns_ = min(4096, nc)
+            scp, ssw, slw = make_synthetic(cfg, ns_, NLAY, col_offset=rank * ncol)
+            outs = []
+            for nofma in (False, True):
+                sbc, sfl = allocate_outputs(cfg, ns_, scp.ntotlay)
+                oracle_lib.make_solver(nofma=nofma)(cfg, scp, ssw, slw, sbc, None, None, *sfl)
+                outs.append({n: {k: getattr(f, k) for k in ALL_FIELDS if getattr(f, k) is not None}
+                             for n, f in zip(names, sfl)})
+            gsub = {n: {k: v[:ns_ * (NLAY if v.shape[0] != nc else 1)] for k, v in f.items()} for n, f in got.items()}
+            ok, worst, lines = parity.check(gsub, outs[0], outs[1])
+            parity_err = {"within_tolerance": bool(ok), "max_err_over_bound": worst,
+                          "tolerance": "per field max(1e-9, 50 x oracle FMA/no-FMA sensitivity), tests/parity.py",
+                          "max_rel_err_fluxes": max(errs[k] for k in flux_fields),
                           "max_rel_err_sunlit_fractions": max([errs[k] for k in errs if "sunlit" in k[1]] or [0.0]),
                           "columns": nc, "definition": "max|gpu-oracle| / max|oracle| per field"}
 
@@ -358,7 +409,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, ncol),
-            "roofline": roofline, "roofline_hbm": roofline_hbm, "kernel_times_one_step": kt,
+            "roofline": roofline, "roofline_kernels": roofline_kernels, "roofline_hbm": roofline_hbm,
+            "kernel_times_one_step": kt,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "conservation_max_abs_residual_over_top_flux": res, "nonfinite_outputs": nonfinite,
             "parity_vs_oracle": parity_err, "library": lib.ssb200_version().decode(),

@@ -77,6 +77,39 @@ SSB_HDI void smv1(const Scr &S, int e0, int lev, const double *x, double *y) {
   }
 }
 
+// Solve D x = b for four right-hand sides at once with the LU factors streamed from
+// scratch (each factor element is loaded once and used four times; nothing is kept)
+template <int n>
+SSB_HDI void lu_solve4_streamed(const Scr &W, int oLU, int lev, double *a, double *b, double *c, double *d) {
+  SSB_UNROLL
+  for (int i = 1; i < n; ++i) {
+    SSB_UNROLL
+    for (int k = 0; k < i; ++k) {
+      const double l = W.ld(oLU + i + n * k, lev);
+      a[i] = fma(-l, a[k], a[i]);
+      b[i] = fma(-l, b[k], b[i]);
+      c[i] = fma(-l, c[k], c[i]);
+      d[i] = fma(-l, d[k], d[i]);
+    }
+  }
+  SSB_UNROLL
+  for (int i = n - 1; i >= 0; --i) {
+    SSB_UNROLL
+    for (int k = i + 1; k < n; ++k) {
+      const double u = W.ld(oLU + i + n * k, lev);
+      a[i] = fma(-u, a[k], a[i]);
+      b[i] = fma(-u, b[k], b[i]);
+      c[i] = fma(-u, c[k], c[i]);
+      d[i] = fma(-u, d[k], d[i]);
+    }
+    const double inv = W.ld(oLU + i + n * i, lev);
+    a[i] *= inv;
+    b[i] *= inv;
+    c[i] *= inv;
+    d[i] *= inv;
+  }
+}
+
 // One step of the upward adding sweep shared by SW and LW: given a_above (in
 // `st`, n x n at offset 0) and the layer's R, T in scratch, produce
 //   LU  = factors of I - a_above R           (returned in registers, stored to scratch at oLU)
@@ -87,9 +120,8 @@ SSB_HDI void smv1(const Scr &S, int e0, int lev, const double *x, double *y) {
 template <int n, int NW>
 SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl, int oR, int oT, int oWa, int oLU,
                          double *LU, double *X, double *rhs_extra) {
-  double Aa[n * n];
-  SSB_UNROLL
-  for (int i = 0; i < n * n; ++i) Aa[i] = st(i);
+  // a_above is read from the state slice (shared memory) where it is used: keeping a register copy
+  // next to LU and X would spill
   SSB_UNROLL
   for (int j = 0; j < n; ++j) {
     SSB_UNROLL
@@ -98,7 +130,7 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
     for (int k = 0; k < n; ++k) {
       const double r = L.ld(oR + k + n * j, jl);
       SSB_UNROLL
-      for (int i = 0; i < n; ++i) LU[i + n * j] = fma(-Aa[i + n * k], r, LU[i + n * j]);
+      for (int i = 0; i < n; ++i) LU[i + n * j] = fma(-st(i + n * k), r, LU[i + n * j]);
     }
   }
   sm_lu<n>(LU);
@@ -112,7 +144,7 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
     for (int k = 0; k < n; ++k) {
       const double t = L.ld(oT + k + n * j, jl);
       SSB_UNROLL
-      for (int i = 0; i < n; ++i) X[i + n * j] = fma(Aa[i + n * k], t, X[i + n * j]);
+      for (int i = 0; i < n; ++i) X[i + n * j] = fma(st(i + n * k), t, X[i + n * j]);
     }
   }
   SSB_UNROLL
@@ -121,7 +153,7 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
     for (int k = 0; k < n; ++k) {
       const double w = L.ld(oWa + k + n * j, jl);
       SSB_UNROLL
-      for (int i = 0; i < n; ++i) rhs_extra[i + n * j] = fma(Aa[i + n * k], w, rhs_extra[i + n * j]);
+      for (int i = 0; i < n; ++i) rhs_extra[i + n * j] = fma(st(i + n * k), w, rhs_extra[i + n * j]);
     }
   }
   sm_lu_solve_left<n, n>(LU, X);
@@ -164,6 +196,82 @@ SSB_HDI void overlap_matrix(const double *Ab, const double *rb, const double *U,
   }
 }
 
+// canopy_flux%zero semantics without writing twice: the sweeps assign every member they
+// own, so only the members of OTHER tile types (and the direct-only members of the
+// diffuse object) are cleared here (radsurf_canopy_flux.F90:286-341).
+template <int NREG, bool URBAN>
+SSB_HDI void zero_unwritten_sw(const ssb200_canopy_flux &f, int nspec, int g, int col, int il1, int nlay, bool own,
+                               bool direct) {
+  auto zl = [&](double *p) {
+    if (p)
+      for (int l = 0; l < nlay; ++l) p[(size_t)g + (size_t)nspec * (il1 + l)] = 0.0;
+  };
+  auto zs = [&](double *p) {
+    if (p && own)
+      for (int l = 0; l < nlay; ++l) p[il1 + l] = 0.0;
+  };
+  if (!URBAN) {
+    zl(f.roof_in);
+    zl(f.roof_net);
+    zl(f.wall_in);
+    zl(f.wall_net);
+    zl(f.roof_in_dir);
+    zl(f.wall_in_dir);
+    zs(f.roof_sunlit_frac);
+    zs(f.wall_sunlit_frac);
+  }
+  if (NREG == 1) {
+    zl(f.veg_abs);
+    zl(f.veg_air_abs);
+    zl(f.veg_abs_dir);
+    zs(f.veg_sunlit_frac);
+  }
+  if (!direct) {
+    zl(f.roof_in_dir);
+    zl(f.wall_in_dir);
+    zl(f.veg_abs_dir);
+    zl(f.flux_dn_dir_layer_top);
+    zl(f.flux_dn_dir_layer_base);
+    zs(f.roof_sunlit_frac);
+    zs(f.wall_sunlit_frac);
+    zs(f.veg_sunlit_frac);
+    if (own && f.ground_sunlit_frac) f.ground_sunlit_frac[col] = 0.0;
+  }
+}
+template <int NREG, bool URBAN>
+SSB_HDI void zero_unwritten_lw(const ssb200_canopy_flux &f, int nspec, int g, int col, int il1, int nlay) {
+  auto zl = [&](double *p) {
+    if (p)
+      for (int l = 0; l < nlay; ++l) p[(size_t)g + (size_t)nspec * (il1 + l)] = 0.0;
+  };
+  if (!URBAN) {
+    zl(f.roof_in);
+    zl(f.roof_net);
+    zl(f.wall_in);
+    zl(f.wall_net);
+  }
+  if (NREG == 1) {
+    zl(f.veg_abs);
+    zl(f.veg_air_abs);
+  }
+  // direct-only members exist only if the caller allocated a LW object with use_direct
+  zl(f.roof_in_dir);
+  zl(f.wall_in_dir);
+  zl(f.veg_abs_dir);
+  zl(f.flux_dn_dir_layer_top);
+  zl(f.flux_dn_dir_layer_base);
+  if (f.ground_dn_dir) f.ground_dn_dir[(size_t)g + (size_t)nspec * col] = 0.0;
+  if (f.top_dn_dir) f.top_dn_dir[(size_t)g + (size_t)nspec * col] = 0.0;
+  if (g == 0) {
+    if (f.ground_sunlit_frac) f.ground_sunlit_frac[col] = 0.0;
+    for (int l = 0; l < nlay; ++l) {
+      if (f.roof_sunlit_frac) f.roof_sunlit_frac[il1 + l] = 0.0;
+      if (f.wall_sunlit_frac) f.wall_sunlit_frac[il1 + l] = 0.0;
+      if (f.veg_sunlit_frac) f.veg_sunlit_frac[il1 + l] = 0.0;
+    }
+  }
+}
+
 // ===========================================================================
 // Shortwave
 // ===========================================================================
@@ -201,9 +309,13 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
     }
   }
   const bool own = (g == itransp);
-  zero_column(fdir, nspec, g, col, il1, nlay, own);
-  zero_column(fdif, nspec, g, col, il1, nlay, own);
-  if (!(cos_sza > 0.0)) return;
+  if (!(cos_sza > 0.0)) {  // night: every member of the column is zero (radsurf_interface.F90:193-196)
+    zero_column(fdir, nspec, g, col, il1, nlay, own);
+    zero_column(fdif, nspec, g, col, il1, nlay, own);
+    return;
+  }
+  zero_unwritten_sw<NREG, URBAN>(fdir, nspec, g, col, il1, nlay, own, true);
+  zero_unwritten_sw<NREG, URBAN>(fdif, nspec, g, col, il1, nlay, own, false);
   const double zcos = URBAN ? dmax(cos_sza, 1.0e-6) : cos_sza;
   const double sin0 = URBAN ? sqrt(1.0 - zcos * zcos) : 0.0;
   const double galb = a.sw.ground_albedo[(size_t)g + (size_t)nspec * col];
@@ -406,15 +518,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
         ub_f[i] = fma(r, xb_f[j], ub_f[i]);
       }
     }
-    {
-      double LU[n * n];
-      SSB_UNROLL
-      for (int i = 0; i < n * n; ++i) LU[i] = W.ld(Lay::oLU + i, jl);
-      sm_lu_solve_left<n, 1>(LU, z1_d);
-      sm_lu_solve_left<n, 1>(LU, z1_f);
-      sm_lu_solve_left<n, 1>(LU, z2_d);
-      sm_lu_solve_left<n, 1>(LU, z2_f);
-    }
+    lu_solve4_streamed<n>(W, Lay::oLU, jl, z1_d, z1_f, z2_d, z2_f);
     smv2<n, n>(L, Lay::oT, jl, z1_d, z1_f, ub_d, ub_f);
     smv1<n, d>(L, Lay::oSup, jl, dir_below, ub_d);
     if (URBAN) {
@@ -626,8 +730,8 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
   const int width = a.ncols * nspec;
   const ssb200_canopy_flux &fint = a.f1, &fnorm = a.f2;
-  zero_column(fint, nspec, g, col, il1, nlay, g == 0);
-  zero_column(fnorm, nspec, g, col, il1, nlay, g == 0);
+  zero_unwritten_lw<NREG, URBAN>(fint, nspec, g, col, il1, nlay);
+  zero_unwritten_lw<NREG, URBAN>(fnorm, nspec, g, col, il1, nlay);
   double hw[NS], mu_inv[NS], tang[NS];
   SSB_UNROLL
   for (int js = 0; js < NS; ++js) {
@@ -792,15 +896,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
         ub_f[i] = fma(r, xb_f[j], ub_f[i]);
       }
     }
-    {
-      double LU[n * n];
-      SSB_UNROLL
-      for (int i = 0; i < n * n; ++i) LU[i] = W.ld(Lay::oLU + i, jl);
-      sm_lu_solve_left<n, 1>(LU, z1_i);
-      sm_lu_solve_left<n, 1>(LU, z1_f);
-      sm_lu_solve_left<n, 1>(LU, z2_i);
-      sm_lu_solve_left<n, 1>(LU, z2_f);
-    }
+    lu_solve4_streamed<n>(W, Lay::oLU, jl, z1_i, z1_f, z2_i, z2_f);
     smv2<n, n>(L, Lay::oT, jl, z1_i, z1_f, ub_i, ub_f);
     if (URBAN) {
       const double bfj = a.cp.building_fraction[il];
@@ -942,6 +1038,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       SSB_FC(fnorm, ground_vertical_diff) = vt_f;
     } else {
       SSB_FC(fint, ground_vertical_diff) = vt_i + vt_f;
+      SSB_FC(fnorm, ground_vertical_diff) = 0.0;
     }
   }
 }
