@@ -77,39 +77,6 @@ SSB_HDI void smv1(const Scr &S, int e0, int lev, const double *x, double *y) {
   }
 }
 
-// Solve D x = b for four right-hand sides at once with the LU factors streamed from
-// scratch (each factor element is loaded once and used four times; nothing is kept)
-template <int n>
-SSB_HDI void lu_solve4_streamed(const Scr &W, int oLU, int lev, double *a, double *b, double *c, double *d) {
-  SSB_UNROLL
-  for (int i = 1; i < n; ++i) {
-    SSB_UNROLL
-    for (int k = 0; k < i; ++k) {
-      const double l = W.ld(oLU + i + n * k, lev);
-      a[i] = fma(-l, a[k], a[i]);
-      b[i] = fma(-l, b[k], b[i]);
-      c[i] = fma(-l, c[k], c[i]);
-      d[i] = fma(-l, d[k], d[i]);
-    }
-  }
-  SSB_UNROLL
-  for (int i = n - 1; i >= 0; --i) {
-    SSB_UNROLL
-    for (int k = i + 1; k < n; ++k) {
-      const double u = W.ld(oLU + i + n * k, lev);
-      a[i] = fma(-u, a[k], a[i]);
-      b[i] = fma(-u, b[k], b[i]);
-      c[i] = fma(-u, c[k], c[i]);
-      d[i] = fma(-u, d[k], d[i]);
-    }
-    const double inv = W.ld(oLU + i + n * i, lev);
-    a[i] *= inv;
-    b[i] *= inv;
-    c[i] *= inv;
-    d[i] *= inv;
-  }
-}
-
 // One step of the upward adding sweep shared by SW and LW: given a_above (in
 // `st`, n x n at offset 0) and the layer's R, T in scratch, produce
 //   LU  = factors of I - a_above R           (returned in registers, stored to scratch at oLU)
@@ -120,8 +87,9 @@ SSB_HDI void lu_solve4_streamed(const Scr &W, int oLU, int lev, double *a, doubl
 template <int n, int NW>
 SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl, int oR, int oT, int oWa, int oLU,
                          double *LU, double *X, double *rhs_extra) {
-  // a_above is read from the state slice (shared memory) where it is used: keeping a register copy
-  // next to LU and X would spill
+  double Aa[n * n];
+  SSB_UNROLL
+  for (int i = 0; i < n * n; ++i) Aa[i] = st(i);
   SSB_UNROLL
   for (int j = 0; j < n; ++j) {
     SSB_UNROLL
@@ -130,7 +98,7 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
     for (int k = 0; k < n; ++k) {
       const double r = L.ld(oR + k + n * j, jl);
       SSB_UNROLL
-      for (int i = 0; i < n; ++i) LU[i + n * j] = fma(-st(i + n * k), r, LU[i + n * j]);
+      for (int i = 0; i < n; ++i) LU[i + n * j] = fma(-Aa[i + n * k], r, LU[i + n * j]);
     }
   }
   sm_lu<n>(LU);
@@ -144,7 +112,7 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
     for (int k = 0; k < n; ++k) {
       const double t = L.ld(oT + k + n * j, jl);
       SSB_UNROLL
-      for (int i = 0; i < n; ++i) X[i + n * j] = fma(st(i + n * k), t, X[i + n * j]);
+      for (int i = 0; i < n; ++i) X[i + n * j] = fma(Aa[i + n * k], t, X[i + n * j]);
     }
   }
   SSB_UNROLL
@@ -153,7 +121,7 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
     for (int k = 0; k < n; ++k) {
       const double w = L.ld(oWa + k + n * j, jl);
       SSB_UNROLL
-      for (int i = 0; i < n; ++i) rhs_extra[i + n * j] = fma(st(i + n * k), w, rhs_extra[i + n * j]);
+      for (int i = 0; i < n; ++i) rhs_extra[i + n * j] = fma(Aa[i + n * k], w, rhs_extra[i + n * j]);
     }
   }
   sm_lu_solve_left<n, n>(LU, X);
@@ -518,7 +486,15 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
         ub_f[i] = fma(r, xb_f[j], ub_f[i]);
       }
     }
-    lu_solve4_streamed<n>(W, Lay::oLU, jl, z1_d, z1_f, z2_d, z2_f);
+    {
+      double LU[n * n];
+      SSB_UNROLL
+      for (int i = 0; i < n * n; ++i) LU[i] = W.ld(Lay::oLU + i, jl);
+      sm_lu_solve_left<n, 1>(LU, z1_d);
+      sm_lu_solve_left<n, 1>(LU, z1_f);
+      sm_lu_solve_left<n, 1>(LU, z2_d);
+      sm_lu_solve_left<n, 1>(LU, z2_f);
+    }
     smv2<n, n>(L, Lay::oT, jl, z1_d, z1_f, ub_d, ub_f);
     smv1<n, d>(L, Lay::oSup, jl, dir_below, ub_d);
     if (URBAN) {
@@ -896,7 +872,15 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
         ub_f[i] = fma(r, xb_f[j], ub_f[i]);
       }
     }
-    lu_solve4_streamed<n>(W, Lay::oLU, jl, z1_i, z1_f, z2_i, z2_f);
+    {
+      double LU[n * n];
+      SSB_UNROLL
+      for (int i = 0; i < n * n; ++i) LU[i] = W.ld(Lay::oLU + i, jl);
+      sm_lu_solve_left<n, 1>(LU, z1_i);
+      sm_lu_solve_left<n, 1>(LU, z1_f);
+      sm_lu_solve_left<n, 1>(LU, z2_i);
+      sm_lu_solve_left<n, 1>(LU, z2_f);
+    }
     smv2<n, n>(L, Lay::oT, jl, z1_i, z1_f, ub_i, ub_f);
     if (URBAN) {
       const double bfj = a.cp.building_fraction[il];

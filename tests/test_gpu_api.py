@@ -1,0 +1,184 @@
+"""GPU tests of the rest of the C ABI: device-resident entry, option switches
+(kernel family, layer partition, pipelined host entry), column sub-ranges,
+the fused scale / sum / check follow-on steps, error codes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import golden_io
+import oracle_lib
+import parity
+from spartacus_surface_b200 import (radsurf, RadsurfError, config_type, canopy_flux_type,
+                                    boundary_conds_out_type)
+from spartacus_surface_b200._lib import load
+from spartacus_surface_b200.radsurf_canopy_flux import ALL_FIELDS
+from spartacus_surface_b200.synthetic import make_synthetic
+
+pytestmark = pytest.mark.gpu
+
+NCOL, NLAY = 3000, 9
+
+
+def _cfg(streams=2):
+    return config_type(n_vegetation_region_urban=2, n_vegetation_region_forest=2, n_stream_sw_urban=streams,
+                       n_stream_lw_urban=streams, n_stream_sw_forest=streams, n_stream_lw_forest=streams).consolidate()
+
+
+def _outputs(cfg, ncol, ntot, device=None, profile=True):
+    bc = boundary_conds_out_type().allocate(ncol, 1, 1, device=device)
+    fl = [canopy_flux_type().allocate(cfg, ncol, ntot, 1, use_direct=d, do_save_flux_profile=profile, device=device)
+          for d in (True, True, False, False)]
+    return bc, fl
+
+
+def _as_dict(fl, bc):
+    names = ("sw_norm_dir", "sw_norm_diff", "lw_internal", "lw_norm")
+    get = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else a
+    out = {n: {k: get(getattr(f, k)) for k in ALL_FIELDS if getattr(f, k) is not None} for n, f in zip(names, fl)}
+    out["bc"] = {k: get(getattr(bc, k)) for k in golden_io.BC_FIELDS}
+    return out
+
+
+def _solve_host(cfg, cp, sw, lw, c1=None, c2=None):
+    bc, fl = _outputs(cfg, cp.ncol, cp.ntotlay)
+    assert radsurf(cfg, cp, sw, lw, bc, c1, c2, *fl) == 0
+    return _as_dict(fl, bc)
+
+
+def _same(a, b):
+    for n, f in a.items():
+        for k, v in f.items():
+            assert np.array_equal(v, b[n][k]), (n, k, float(np.abs(v - b[n][k]).max()))
+
+
+def test_device_entry_equals_host_entry():
+    import torch
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, NCOL, NLAY)
+    host = _solve_host(cfg, cp, sw, lw)
+    dcp, dsw, dlw = make_synthetic(cfg, NCOL, NLAY, device="cuda:0")
+    bc, fl = _outputs(cfg, NCOL, dcp.ntotlay, device="cuda:0")
+    assert radsurf(cfg, dcp, dsw, dlw, bc, None, None, *fl) == 0
+    torch.cuda.synchronize()
+    _same(host, _as_dict(fl, bc))
+
+
+def test_kernel_families_agree_and_match_oracle():
+    lib = load()
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, 512, NLAY)
+    res = {}
+    for fast in (0, 1):
+        lib.ssb200_set_option(b"fast_kernels", fast)
+        res[fast] = _solve_host(cfg, cp, sw, lw)
+    lib.ssb200_set_option(b"fast_kernels", 1)
+    ora = []
+    for nofma in (False, True):
+        bc, fl = _outputs(cfg, cp.ncol, cp.ntotlay)
+        oracle_lib.make_solver(nofma=nofma)(cfg, cp, sw, lw, bc, None, None, *fl)
+        ora.append(_as_dict(fl, bc))
+    for fast in (0, 1):
+        ok, worst, lines = parity.check(res[fast], ora[0], ora[1])
+        assert ok, (fast, lines[:5])
+
+
+def test_partition_and_pipeline_do_not_change_results():
+    lib = load()
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, 70000, 4)  # large enough for the pipelined path (several blocks)
+    base = _solve_host(cfg, cp, sw, lw)
+    for opt in (b"partition_layers", b"pipeline"):
+        lib.ssb200_set_option(opt, 0)
+        try:
+            _same(base, _solve_host(cfg, cp, sw, lw))
+        finally:
+            lib.ssb200_set_option(opt, 1)
+    lib.ssb200_set_option(b"scratch_budget_bytes", 64 << 20)  # forces many chunks
+    try:
+        _same(base, _solve_host(cfg, cp, sw, lw))
+    finally:
+        lib.ssb200_set_option(b"scratch_budget_bytes", 0)
+
+
+def test_column_range_untouched_outside():
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, 200, NLAY)
+    full = _solve_host(cfg, cp, sw, lw)
+    bc, fl = _outputs(cfg, cp.ncol, cp.ntotlay)
+    for f in fl:
+        f.fill(7.0)
+    for k in golden_io.BC_FIELDS:
+        getattr(bc, k)[...] = 7.0
+    assert radsurf(cfg, cp, sw, lw, bc, 51, 120, *fl) == 0
+    part = _as_dict(fl, bc)
+    for n, fields in part.items():
+        for k, v in fields.items():
+            rows = cp.ncol if v.shape[0] == cp.ncol else cp.ntotlay
+            lo, hi = (50, 120) if rows == cp.ncol else (50 * NLAY, 120 * NLAY)
+            assert np.array_equal(v[lo:hi], full[n][k][lo:hi]), (n, k)
+            assert np.all(v[:lo] == 7.0) and np.all(v[hi:] == 7.0), (n, k)
+
+
+def test_scale_sum_check_on_device():
+    import torch
+    lib = load()
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, 400, NLAY)
+    bc, fl = _outputs(cfg, cp.ncol, cp.ntotlay)
+    assert radsurf(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+    rng = np.random.default_rng(1)
+    top_dir = rng.uniform(100, 800, size=(cp.ncol, 1))
+    top_dif = rng.uniform(10, 200, size=(cp.ncol, 1))
+    # host (numpy) versions = the reference's scale / sum (radsurf_canopy_flux.F90:212-282,399-460)
+    import copy
+    h_dir, h_dif = copy.deepcopy(fl[0]), copy.deepcopy(fl[1])
+    h_dir.scale(cp.nlay, top_dir)
+    h_dif.scale(cp.nlay, top_dif)
+    h_sum = canopy_flux_type().allocate(cfg, cp.ncol, cp.ntotlay, 1, use_direct=True)
+    h_sum.sum(h_dir, h_dif)
+    # device versions through the C ABI
+    def to_dev(f):
+        g = canopy_flux_type().allocate(cfg, cp.ncol, cp.ntotlay, 1, use_direct=True, device="cuda:0")
+        for k in ALL_FIELDS:
+            a = getattr(f, k)
+            if a is not None:
+                getattr(g, k).copy_(torch.from_numpy(a))
+        return g
+    d_dir, d_dif = to_dev(fl[0]), to_dev(fl[1])
+    d_dir.scale(cp.nlay, torch.from_numpy(top_dir).cuda())
+    d_dif.scale(cp.nlay, torch.from_numpy(top_dif).cuda())
+    d_sum = canopy_flux_type().allocate(cfg, cp.ncol, cp.ntotlay, 1, use_direct=True, device="cuda:0")
+    d_sum.sum(d_dir, d_dif)
+    torch.cuda.synchronize()
+    for k in ALL_FIELDS:
+        a = getattr(h_sum, k)
+        if a is not None:
+            assert np.array_equal(a, getattr(d_sum, k).cpu().numpy()), k
+    # energy budget residual per column (radsurf_canopy_flux.F90:534-535)
+    res = torch.zeros(cp.ncol, dtype=torch.float64, device="cuda:0")
+    s, c = d_sum.as_struct(), cp.as_struct()
+    assert lib.ssb200_canopy_flux_check_device(C.byref(s), C.byref(c), C.c_void_p(res.data_ptr()), None) == 0
+    torch.cuda.synchronize()
+    tab = h_sum.check(cp, iverbose=0)
+    assert np.allclose(res.cpu().numpy(), tab[:, 7], rtol=0, atol=1e-9)
+    assert np.abs(tab[:, 7]).max() < 1e-9 * np.abs(tab[:, 6]).max()
+
+
+def test_error_codes():
+    lib = load()
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, 8, 1)
+    cp.i_representation[:] = 4  # simple urban with one layer is fine ...
+    bc, fl = _outputs(cfg, cp.ncol, cp.ntotlay)
+    assert radsurf(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+    cp2, sw2, lw2 = make_synthetic(cfg, 8, 2)
+    cp2.i_representation[:] = 5   # ... with two layers it is the reference's abort (radsurf_interface.F90:281-284)
+    bc2, fl2 = _outputs(cfg, cp2.ncol, cp2.ntotlay)
+    with pytest.raises(RadsurfError, match="more than one layer"):
+        radsurf(cfg, cp2, sw2, lw2, bc2, None, None, *fl2)
+    bad = _cfg()
+    bad.nswinternal = 3  # spectral resolution mismatch
+    with pytest.raises(RadsurfError, match="spectral resolution"):
+        radsurf(bad, cp, sw, lw, bc, None, None, *fl)
+    assert lib.ssb200_measure_fp64_peak_tflops(1 << 12) > 1.0
