@@ -224,7 +224,8 @@ int ssb200_last_kernel_counts(int64_t out[5]);
  * 0 = automatic: half of the free memory, at most 24 GiB) and "fast_kernels"
  * (1 = use the sub-warp kernels where a configuration has one, 0 = generic
  * one-thread-per-problem kernels everywhere; results agree to rounding),
- * "partition_layers" (1 = group layer problems by solved sub-block first),
+ * "partition_layers" (1 = group layer problems by solved sub-block so that the
+ * register-resident layer kernels run; 0 = generic layer kernels),
  * "pipeline" (1 = ssb200_radsurf overlaps H2D, kernels and D2H over blocks of
  * columns; effective with pinned host memory), "fast_minblocks[_sweeps]"
  * (launch-bounds variant of the register-resident kernels). */

@@ -10,7 +10,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libspartacus_b200.so")
+# SSB200_LIB: alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("SSB200_LIB") or os.path.join(_HERE, "csrc", "libspartacus_b200.so")
 
 _lib = None
 

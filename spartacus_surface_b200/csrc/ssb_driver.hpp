@@ -180,7 +180,8 @@ struct Dispatcher {
       while (pos + cnt < ntot) {
         const int nl = plan.nlay[k.cols[pos + cnt]];
         const int lm = std::max(lmax, nl);
-        const size_t need = (el * (size_t)lm + es * (size_t)(lm + 1)) * (cnt + 1) * (size_t)c.nspec;
+        const size_t wd = (cnt + 1) * (size_t)c.nspec;
+        const size_t need = scratch_doubles(el, (size_t)lm, wd) + scratch_doubles(es, (size_t)lm + 1, wd);
         if (need > budget && cnt > 0) break;
         lmax = lm;
         ++cnt;
@@ -189,9 +190,11 @@ struct Dispatcher {
       a.lmax = lmax;
       a.cols = be.dev_cols(plan, col_offset + pos);
       const size_t width = cnt * (size_t)c.nspec;
-      double *s = be.scratch((el * (size_t)lmax + es * (size_t)(lmax + 1)) * width);
+      double *s = be.scratch(scratch_doubles(el, (size_t)lmax, width) + scratch_doubles(es, (size_t)lmax + 1, width));
       a.layer = s;
-      a.sweep = s + el * (size_t)lmax * width;
+      a.sweep = s + scratch_doubles(el, (size_t)lmax, width);
+      a.ne_layer = (int)el;
+      a.ne_sweep = (int)es;
       if (lmax > 0) {
         if (lw)
           be.template layer_lw<NS>(a, (long)width * lmax);

@@ -8,7 +8,18 @@
 
 namespace ssb {
 
-constexpr int kFastBlock = 128;
+constexpr int kFastBlock = 128;  // sweeps: one thread per (column, interval)
+// layer kernels: block size and the resident threads per SM that the register budget is
+// set for (__launch_bounds__).  Measured on B200: aligning the warps of a block with
+// barriers at phase boundaries (one 384-thread block per SM) does not pay.
+#ifndef SSB_LAYER_BLOCK
+#define SSB_LAYER_BLOCK 128
+#endif
+#ifndef SSB_LAYER_THREADS
+#define SSB_LAYER_THREADS 384
+#endif
+constexpr int kLayerBlock = SSB_LAYER_BLOCK;
+constexpr int kLayerMinB = SSB_LAYER_THREADS / SSB_LAYER_BLOCK;
 
 // Groups the layer problems of a launch by the sub-block of regions they solve, so
 // that every warp of the layer kernels runs one code path.  Warp-aggregated
@@ -35,15 +46,8 @@ static __global__ void k_partition_layers(ClassArgs a, long nt, int sw) {
 }
 
 #ifdef SSB_KIND_SW
-template <int NREG, int NS, int MINB>
-__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_sw(ClassArgs a, long nt) {
-  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (t >= nt) return;
-  const long width = (long)a.ncols * a.cfg.nspec;
-  fast_layer_problem_sw<NREG, NS>(a, (int)(t % width), (int)(t / width));
-}
-template <int NREG, int NS, int SEG, int MINB>
-__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_sw_seg(ClassArgs a, long nt) {
+template <int NREG, int NS, int SEG>
+__global__ void __launch_bounds__(kLayerBlock, kLayerMinB) k_fast_layer_sw_seg(ClassArgs a, long nt) {
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= a.perm_count[SEG]) return;
   const long id = a.perm[(size_t)SEG * (size_t)nt + t];
@@ -51,30 +55,21 @@ __global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_sw_seg(ClassArg
   fast_layer_problem_sw_seg<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width));
 }
 template <int NREG, int NS>
-static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
-  const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
-  if (a.perm != nullptr) {
-    cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
-    k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt, 1);
-    k_fast_layer_sw_seg<NREG, NS, 0, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
-    if (NREG > 1) k_fast_layer_sw_seg<NREG, NS, 1, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
-    if (NREG > 1) k_fast_layer_sw_seg<NREG, NS, 2, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
-    return;
-  }
-  if (minb >= 4)
-    k_fast_layer_sw<NREG, NS, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
-  else if (minb == 3)
-    k_fast_layer_sw<NREG, NS, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
-  else
-    k_fast_layer_sw<NREG, NS, 2><<<grid, kFastBlock, 0, st>>>(a, nt);
+static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st) {
+  const unsigned grid = (unsigned)((nt + kLayerBlock - 1) / kLayerBlock);
+  cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
+  k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt, 1);
+  k_fast_layer_sw_seg<NREG, NS, 0><<<grid, kLayerBlock, 0, st>>>(a, nt);
+  if (NREG > 1) k_fast_layer_sw_seg<NREG, NS, 1><<<grid, kLayerBlock, 0, st>>>(a, nt);
+  if (NREG > 1) k_fast_layer_sw_seg<NREG, NS, 2><<<grid, kLayerBlock, 0, st>>>(a, nt);
 }
 template <>
-bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
-  if (a.cfg.ns != SSB_NS) return false;
+bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int) {
+  if (a.cfg.ns != SSB_NS || a.perm == nullptr) return false;
   switch (a.cfg.nreg) {
-    case 1: launch_fast_layer_sw<1, SSB_NS>(a, nt, st, minb); return true;
-    case 2: launch_fast_layer_sw<2, SSB_NS>(a, nt, st, minb); return true;
-    case 3: launch_fast_layer_sw<3, SSB_NS>(a, nt, st, minb); return true;
+    case 1: launch_fast_layer_sw<1, SSB_NS>(a, nt, st); return true;
+    case 2: launch_fast_layer_sw<2, SSB_NS>(a, nt, st); return true;
+    case 3: launch_fast_layer_sw<3, SSB_NS>(a, nt, st); return true;
     default: return false;
   }
 }
@@ -117,15 +112,8 @@ bool fast_sweeps_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int mi
 #endif
 
 #ifdef SSB_KIND_LW
-template <int NREG, int NS, int MINB>
-__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_lw(ClassArgs a, long nt) {
-  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (t >= nt) return;
-  const long width = (long)a.ncols * a.cfg.nspec;
-  fast_layer_problem_lw<NREG, NS>(a, (int)(t % width), (int)(t / width));
-}
-template <int NREG, int NS, int SEG, int MINB>
-__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_lw_seg(ClassArgs a, long nt) {
+template <int NREG, int NS, int SEG>
+__global__ void __launch_bounds__(kLayerBlock, kLayerMinB) k_fast_layer_lw_seg(ClassArgs a, long nt) {
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= a.perm_count[SEG]) return;
   const long id = a.perm[(size_t)SEG * (size_t)nt + t];
@@ -133,30 +121,21 @@ __global__ void __launch_bounds__(kFastBlock, MINB) k_fast_layer_lw_seg(ClassArg
   fast_layer_problem_lw_impl<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width));
 }
 template <int NREG, int NS>
-static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
-  const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
-  if (a.perm != nullptr) {
-    cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
-    k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt, 0);
-    k_fast_layer_lw_seg<NREG, NS, 0, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
-    if (NREG > 1) k_fast_layer_lw_seg<NREG, NS, 1, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
-    if (NREG > 1) k_fast_layer_lw_seg<NREG, NS, 2, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
-    return;
-  }
-  if (minb >= 4)
-    k_fast_layer_lw<NREG, NS, 4><<<grid, kFastBlock, 0, st>>>(a, nt);
-  else if (minb == 3)
-    k_fast_layer_lw<NREG, NS, 3><<<grid, kFastBlock, 0, st>>>(a, nt);
-  else
-    k_fast_layer_lw<NREG, NS, 2><<<grid, kFastBlock, 0, st>>>(a, nt);
+static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st) {
+  const unsigned grid = (unsigned)((nt + kLayerBlock - 1) / kLayerBlock);
+  cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
+  k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt, 0);
+  k_fast_layer_lw_seg<NREG, NS, 0><<<grid, kLayerBlock, 0, st>>>(a, nt);
+  if (NREG > 1) k_fast_layer_lw_seg<NREG, NS, 1><<<grid, kLayerBlock, 0, st>>>(a, nt);
+  if (NREG > 1) k_fast_layer_lw_seg<NREG, NS, 2><<<grid, kLayerBlock, 0, st>>>(a, nt);
 }
 template <>
-bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
-  if (a.cfg.ns != SSB_NS) return false;
+bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int) {
+  if (a.cfg.ns != SSB_NS || a.perm == nullptr) return false;
   switch (a.cfg.nreg) {
-    case 1: launch_fast_layer_lw<1, SSB_NS>(a, nt, st, minb); return true;
-    case 2: launch_fast_layer_lw<2, SSB_NS>(a, nt, st, minb); return true;
-    case 3: launch_fast_layer_lw<3, SSB_NS>(a, nt, st, minb); return true;
+    case 1: launch_fast_layer_lw<1, SSB_NS>(a, nt, st); return true;
+    case 2: launch_fast_layer_lw<2, SSB_NS>(a, nt, st); return true;
+    case 3: launch_fast_layer_lw<3, SSB_NS>(a, nt, st); return true;
     default: return false;
   }
 }

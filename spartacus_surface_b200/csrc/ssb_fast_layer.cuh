@@ -98,8 +98,7 @@ SSB_HDI void fast_sw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
 
   double R[N * N], T[N * N], Idiff[N * N], Sup[N * NR], Sdn[N * NR], Idd[N * NR], E[NR * NR], Idir[NR * NR];
   fast_layer_sw_math<NR, NS>(op.dz, g0, Dm, Sm, g3, nsc, ninv, frac, R, T, Sup, Sdn, E, Idir, Idiff, Idd);
-
-  const int nlev = a.lmax, width = a.ncols * c.nspec;
+  const int nlev = a.lmax, width = a.ne_layer;
   int e = 0;
   put_block<NREG, NS, NR, R0, true, true>(a.layer, e, R, lev, nlev, width, q);
   put_block<NREG, NS, NR, R0, true, true>(a.layer, e, T, lev, nlev, width, q);
@@ -259,9 +258,8 @@ SSB_HDI void fast_lw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
 
   double R[N * N], T[N * N], IF[N * N], src[N], isrc[N];
   fast_layer_lw_math<NR, NS>(op.dz, Dm, Sm, brate, nsc, ninv, R, T, src, IF, isrc);
-
   constexpr int n = NREG * NS;
-  const int nlev = a.lmax, width = a.ncols * c.nspec;
+  const int nlev = a.lmax, width = a.ne_layer;
   int e = 0;
   put_block<NREG, NS, NR, R0, true, true>(a.layer, e, R, lev, nlev, width, q);
   put_block<NREG, NS, NR, R0, true, true>(a.layer, e, T, lev, nlev, width, q);
@@ -322,7 +320,7 @@ SSB_HDI void fast_layer_problem_lw_impl(const ClassArgs &a, int q, int lev) {
   SSB_UNROLL
   for (int js = 0; js < NS; ++js) emiss_factor += a.lg.hweight[js] / a.lg.mu[js];
   emiss_factor = 2.0 * emiss_factor;
-  const int nlev = a.lmax, width = a.ncols * nspec;
+  const int nlev = a.lmax, width = a.ne_layer;
   const int e_book = 3 * n * n + 2 * n;
   double wsum = 0.0;
   SSB_UNROLL

@@ -34,7 +34,7 @@ struct FastDiffuse {
   double Ldinv[N], lam[N], lam2[N], e[N];
 };
 
-constexpr int kJacobiSweeps(int n) { return n <= 2 ? 4 : 12; }
+SSB_HD constexpr int kJacobiSweeps(int n) { return n <= 2 ? 4 : 12; }
 
 // Eigen-system of P = D S with D = G1-G2, S = G1+G2 (both N-symmetric), then
 // R and T from the sum and difference problems.  `ninv[i]` = 1/N_i = w mu frac,

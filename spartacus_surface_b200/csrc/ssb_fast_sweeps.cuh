@@ -32,12 +32,16 @@ struct StateMem {
   SSB_HDI double &operator()(int e) const { return p[(size_t)e * stride]; }
 };
 
-struct Scr {  // one scratch area (layer or interface) of the calling problem
-  const double *base;
-  double *wbase;
-  int nlev, width, q;
-  SSB_HDI double ld(int e, int lev) const { return base[sidx(e, lev, nlev, width, q)]; }
-  SSB_HDI void st(int e, int lev, double v) const { wbase[sidx(e, lev, nlev, width, q)] = v; }
+// One scratch area (layer or interface) as seen by the calling problem: `base` points at
+// element 0 of level 0, levels are `lev_stride` doubles apart and element e sits at the
+// compile-time offset e * kScratchTile, so a layer is addressed from one register pair.
+struct Scr {
+  double *base;
+  size_t lev_stride;
+  SSB_HDI Scr(double *area, int nlev, int nelem, int q)
+      : base(area + sidx(0, 0, nlev, nelem, q)), lev_stride((size_t)nelem * kScratchTile) {}
+  SSB_HDI double ld(int e, int lev) const { return base[(size_t)lev * lev_stride + (size_t)e * kScratchTile]; }
+  SSB_HDI void st(int e, int lev, double v) const { base[(size_t)lev * lev_stride + (size_t)e * kScratchTile] = v; }
 };
 
 // (V (x) I_NS) x : below-interface vector (NRB*NS) from the above-interface one (NREG*NS)
@@ -261,7 +265,6 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
   const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
-  const int width = a.ncols * nspec;
   const ssb200_canopy_flux &fdir = a.f1, &fdif = a.f2;
   const double cos_sza = a.cp.cos_sza[col];
   int itransp = 0;
@@ -296,8 +299,8 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
     mu_inv[js] = 1.0 / a.lg.mu[js];
     tang[js] = a.lg.tan_ang[js];
   }
-  const Scr L{a.layer, a.layer, a.lmax, width, q};
-  const Scr W{a.sweep, a.sweep, a.lmax + 1, width, q};
+  const Scr L(a.layer, a.lmax, a.ne_layer, q);
+  const Scr W(a.sweep, a.lmax + 1, a.ne_sweep, q);
 
   // ---- upward sweep: state = [a_above (n x n) | d_above (n x d)] ------------
   SSB_UNROLL
@@ -704,7 +707,6 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
   const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
-  const int width = a.ncols * nspec;
   const ssb200_canopy_flux &fint = a.f1, &fnorm = a.f2;
   zero_unwritten_lw<NREG, URBAN>(fint, nspec, g, col, il1, nlay);
   zero_unwritten_lw<NREG, URBAN>(fnorm, nspec, g, col, il1, nlay);
@@ -715,8 +717,8 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
     mu_inv[js] = 1.0 / a.lg.mu[js];
     tang[js] = a.lg.tan_ang[js];
   }
-  const Scr L{a.layer, a.layer, a.lmax, width, q};
-  const Scr W{a.sweep, a.sweep, a.lmax + 1, width, q};
+  const Scr L(a.layer, a.lmax, a.ne_layer, q);
+  const Scr W(a.sweep, a.lmax + 1, a.ne_sweep, q);
   const double gemis = a.lw.ground_emissivity[(size_t)g + (size_t)nspec * col];
   const double gemission = a.lw.ground_emission[(size_t)g + (size_t)nspec * col];
 

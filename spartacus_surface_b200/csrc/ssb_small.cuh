@@ -137,7 +137,8 @@ SSB_HDI void sm_cholesky(double *A, double *dinv) {
   }
 }
 
-// warp-uniform "everybody converged" vote (plain value on the host)
+// warp-wide "everybody converged" vote (plain value on the host).  Only used to leave a
+// loop early; results never depend on it.
 SSB_HDI bool all_lanes(bool pred) {
 #if defined(__CUDA_ARCH__)
   return __all_sync(__activemask(), pred);
@@ -159,9 +160,12 @@ SSB_HDI double rsqrt_pos(double x) {
 // eigenvectors (columns).  The rotation parameters come from two reciprocal
 // square roots (no division):  with alpha = (aqq-app)/2, beta = apq,
 // h = sqrt(alpha^2+beta^2):  cos^2 = (1 + |alpha|/h)/2,
-// sin = sign(alpha) beta / (2 h cos).  Sweeps stop when every lane of the warp
-// has converged (off-diagonal mass below eps^2 of the diagonal mass) or after
-// `max_sweeps`; the pair loops are unrolled so all indices stay static.
+// sin = sign(alpha) beta / (2 h cos).  A problem is converged when its
+// off-diagonal mass is below eps^2 of the diagonal mass; from then on it only
+// applies identity rotations, so its result does not depend on how many more
+// sweeps its warp (or block) neighbours need - the sweeps stop when all of them
+// have converged or after `max_sweeps`.  The pair loops are unrolled so all
+// indices stay static.
 template <int N>
 SSB_HDI void sm_jacobi(double *A, double *U, double *eval, int max_sweeps) {
   SSB_UNROLL
@@ -177,7 +181,8 @@ SSB_HDI void sm_jacobi(double *A, double *U, double *eval, int max_sweeps) {
       SSB_UNROLL
       for (int q = p + 1; q < N; ++q) off = fma(A[p + N * q], A[p + N * q], off);
     }
-    if (all_lanes(off <= 1.0e-33 * diag)) break;
+    const bool converged = off <= 1.0e-33 * diag;
+    if (all_lanes(converged)) break;
     SSB_UNROLL
     for (int p = 0; p < N - 1; ++p) {
       SSB_UNROLL
@@ -187,7 +192,7 @@ SSB_HDI void sm_jacobi(double *A, double *U, double *eval, int max_sweeps) {
         const double alpha = 0.5 * (aqq - app);
         const double h2 = fma(alpha, alpha, beta * beta);
         // negligible pivot (or an exactly zero 2x2 block): identity rotation
-        const bool skip = !(beta * beta > 1.0e-40 * h2);
+        const bool skip = converged || !(beta * beta > 1.0e-40 * h2);
         const double rh = rsqrt_pos(skip ? 1.0 : h2);
         const double x = fma(0.5 * fabs(alpha), rh, 0.5);
         const double rc = rsqrt_pos(x);

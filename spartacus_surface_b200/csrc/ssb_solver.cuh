@@ -13,10 +13,13 @@
 // The bodies are SSB_HD so that tests can run the identical code on the host;
 // the kernels in ssb_kernels.cu are thin index wrappers around them.
 //
-// Scratch layout (device, per chunk of columns): element e of level l of
-// problem q = (column_in_chunk * nspec + interval) lives at
-//   base[((size_t)e * nlev + l) * width + q],   width = ncols_chunk * nspec,
-// i.e. adjacent threads touch adjacent doubles in every access.
+// Scratch layout (device, per chunk of columns): problems q = column_in_chunk *
+// nspec + interval are tiled by kScratchTile = 128 (one thread block of the sweep
+// kernels); element e of level l of problem q lives at
+//   base[(((q / 128) * nlev + l) * nelem + e) * 128 + q % 128],
+// i.e. adjacent threads touch adjacent doubles in every access and, for a given
+// problem and level, element e sits at the compile-time offset e * 128 doubles, so
+// the register-resident kernels address a whole layer from one base pointer.
 #pragma once
 #include "../../include/spartacus_b200.h"
 #include "ssb_geometry.cuh"
@@ -45,15 +48,22 @@ struct ClassArgs {
   int use_sw_direct_albedo;
   ssb200_boundary_conds_out bc;
   ssb200_canopy_flux f1, f2;  // SW: norm_dir, norm_diff ; LW: internal, norm
-  double *layer;              // layer-matrix scratch
-  double *sweep;              // interface scratch
+  double *layer;              // layer-matrix scratch (ne_layer elements x lmax levels)
+  double *sweep;              // interface scratch (ne_sweep elements x lmax+1 levels)
+  int ne_layer, ne_sweep;
   int *perm;                  // fast path: layer problems grouped by solved sub-block (3 segments of nt)
   int *perm_count;            // [3] problems per segment
   int *status;                // failure counter
 };
 
-SSB_HDI size_t sidx(int e, int lev, int nlev, int width, int q) {
-  return ((size_t)e * (size_t)nlev + (size_t)lev) * (size_t)width + (size_t)q;
+constexpr int kScratchTile = 128;
+SSB_HDI size_t sidx(int e, int lev, int nlev, int nelem, int q) {
+  return (((size_t)(q / kScratchTile) * (size_t)nlev + (size_t)lev) * (size_t)nelem + (size_t)e) * kScratchTile +
+         (size_t)(q % kScratchTile);
+}
+// doubles of a scratch area of `nelem` elements x `nlev` levels for `width` problems
+SSB_HDI size_t scratch_doubles(size_t nelem, size_t nlev, size_t width) {
+  return ((width + kScratchTile - 1) / kScratchTile) * kScratchTile * nelem * nlev;
 }
 
 // element counts of the two scratch areas
@@ -89,7 +99,7 @@ SSB_HD inline void layer_problem_sw(const ClassArgs &a, int q, int lev) {
   const double cos_sza = a.cp.cos_sza[col];
   if (!(cos_sza > 0.0)) return;
   const int il = a.istartlay[col] - 1 + lev;
-  const int width = a.ncols * nspec;
+  const int width = a.ne_layer;  // element count of the layer scratch (sidx)
   const double zcos = c.urban ? dmax(cos_sza, 1.0e-6) : cos_sza;
   double sin0 = 0.0, tan0;
   if (c.urban) {
@@ -249,7 +259,7 @@ SSB_HD inline void layer_problem_lw(const ClassArgs &a, int q, int lev) {
   const int col = a.cols[ic];
   if (lev >= a.nlay[col]) return;
   const int il = a.istartlay[col] - 1 + lev;
-  const int width = a.ncols * nspec;
+  const int width = a.ne_layer;  // element count of the layer scratch (sidx)
   const double bf = c.urban ? a.cp.building_fraction[il] : 0.0;
   const double bs = c.urban ? a.cp.building_scale[il] : 0.0;
   const bool veg = nreg > 1 || !c.urban;
@@ -400,12 +410,12 @@ SSB_HD inline void layer_problem_lw(const ClassArgs &a, int q, int lev) {
 // ---------------------------------------------------------------------------
 struct ScratchIO {
   double *base;
-  int nlev, width, q;
+  int nlev, nelem, q;
   SSB_HDI void load(int e0, int cnt, int lev, double *dst) const {
-    for (int i = 0; i < cnt; ++i) dst[i] = base[sidx(e0 + i, lev, nlev, width, q)];
+    for (int i = 0; i < cnt; ++i) dst[i] = base[sidx(e0 + i, lev, nlev, nelem, q)];
   }
   SSB_HDI void store(int e0, int cnt, int lev, const double *src) const {
-    for (int i = 0; i < cnt; ++i) base[sidx(e0 + i, lev, nlev, width, q)] = src[i];
+    for (int i = 0; i < cnt; ++i) base[sidx(e0 + i, lev, nlev, nelem, q)] = src[i];
   }
 };
 
@@ -545,7 +555,6 @@ SSB_HD inline void column_sweeps_sw(const ClassArgs &a, int q) {
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
   const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
-  const int width = a.ncols * nspec;
   const ssb200_canopy_flux &fdir = a.f1, &fdif = a.f2;
   const double cos_sza = a.cp.cos_sza[col];
 
@@ -572,8 +581,8 @@ SSB_HD inline void column_sweeps_sw(const ClassArgs &a, int q) {
   const double galb = a.sw.ground_albedo[(size_t)g + (size_t)nspec * col];
   const double galb_dir = (a.use_sw_direct_albedo ? a.sw.ground_albedo_dir : a.sw.ground_albedo)[(size_t)g + (size_t)nspec * col];
 
-  const ScratchIO L{a.layer, a.lmax, width, q};
-  const ScratchIO W{a.sweep, a.lmax + 1, width, q};
+  const ScratchIO L{a.layer, a.lmax, a.ne_layer, q};
+  const ScratchIO W{a.sweep, a.lmax + 1, a.ne_sweep, q};
   // layer scratch offsets
   const int oR = 0, oT = n * n, oIdiff = 2 * n * n, oSup = 3 * n * n, oSdn = oSup + n * d, oIdd = oSdn + n * d,
             oE = oIdd + n * d, oIdir = oE + d * d;
@@ -869,13 +878,12 @@ SSB_HD inline void column_sweeps_lw(const ClassArgs &a, int q) {
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
   const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
-  const int width = a.ncols * nspec;
   const ssb200_canopy_flux &fint = a.f1, &fnorm = a.f2;
   zero_column(fint, nspec, g, col, il1, nlay, g == 0);
   zero_column(fnorm, nspec, g, col, il1, nlay, g == 0);
 
-  const ScratchIO L{a.layer, a.lmax, width, q};
-  const ScratchIO W{a.sweep, a.lmax + 1, width, q};
+  const ScratchIO L{a.layer, a.lmax, a.ne_layer, q};
+  const ScratchIO W{a.sweep, a.lmax + 1, a.ne_sweep, q};
   const int oR = 0, oT = n * n, oIF = 2 * n * n, oSrc = 3 * n * n, oIsrc = oSrc + n, oBook = oIsrc + n;
   const int oAa = 0, oSa = n * n, oDen = oSa + n, oAb = oDen + n * n, oSb = oAb + m * m, oU = oSb + m,
             oV = oU + nreg * nrb;
