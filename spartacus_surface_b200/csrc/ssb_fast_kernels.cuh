@@ -16,7 +16,7 @@ constexpr int kFastBlock = 128;  // sweeps: one thread per (column, interval)
 #define SSB_LAYER_BLOCK 128
 #endif
 #ifndef SSB_LAYER_THREADS
-#define SSB_LAYER_THREADS 384
+#define SSB_LAYER_THREADS 256
 #endif
 constexpr int kLayerBlock = SSB_LAYER_BLOCK;
 constexpr int kLayerMinB = SSB_LAYER_THREADS / SSB_LAYER_BLOCK;
@@ -48,20 +48,29 @@ static __global__ void k_partition_layers(ClassArgs a, long nt, int sw) {
 #ifdef SSB_KIND_SW
 template <int NREG, int NS, int SEG>
 __global__ void __launch_bounds__(kLayerBlock, kLayerMinB) k_fast_layer_sw_seg(ClassArgs a, long nt) {
+  extern __shared__ double ssb_stack[];  // [stack element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= a.perm_count[SEG]) return;
   const long id = a.perm[(size_t)SEG * (size_t)nt + t];
   const long width = (long)a.ncols * a.cfg.nspec;
-  fast_layer_problem_sw_seg<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width));
+  const StateMem st{ssb_stack + threadIdx.x, kLayerBlock};
+  fast_layer_problem_sw_seg<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width), st);
+}
+template <int NREG, int NS, int SEG>
+static void launch_fast_layer_sw_seg(const ClassArgs &a, long nt, unsigned grid, cudaStream_t st) {
+  constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
+  const size_t smem = sizeof(double) * LayerStack<NR, NS>::sw_doubles * kLayerBlock;
+  cudaFuncSetAttribute(k_fast_layer_sw_seg<NREG, NS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fast_layer_sw_seg<NREG, NS, SEG><<<grid, kLayerBlock, smem, st>>>(a, nt);
 }
 template <int NREG, int NS>
 static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kLayerBlock - 1) / kLayerBlock);
   cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
   k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt, 1);
-  k_fast_layer_sw_seg<NREG, NS, 0><<<grid, kLayerBlock, 0, st>>>(a, nt);
-  if (NREG > 1) k_fast_layer_sw_seg<NREG, NS, 1><<<grid, kLayerBlock, 0, st>>>(a, nt);
-  if (NREG > 1) k_fast_layer_sw_seg<NREG, NS, 2><<<grid, kLayerBlock, 0, st>>>(a, nt);
+  launch_fast_layer_sw_seg<NREG, NS, 0>(a, nt, grid, st);
+  if (NREG > 1) launch_fast_layer_sw_seg<NREG, NS, 1>(a, nt, grid, st);
+  if (NREG > 1) launch_fast_layer_sw_seg<NREG, NS, 2>(a, nt, grid, st);
 }
 template <>
 bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int) {
@@ -78,7 +87,7 @@ __global__ void __launch_bounds__(kFastBlock, MINB) k_fast_sweeps_sw(ClassArgs a
   extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
-  const StateMem st{ssb_state + threadIdx.x, (int)blockDim.x};
+  const StateMem st{ssb_state + threadIdx.x, kFastBlock};
   fast_column_sweeps_sw<NREG, NS, URBAN>(a, (int)t, st);
 }
 template <int NREG, int NS, bool URBAN>
@@ -114,20 +123,29 @@ bool fast_sweeps_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int mi
 #ifdef SSB_KIND_LW
 template <int NREG, int NS, int SEG>
 __global__ void __launch_bounds__(kLayerBlock, kLayerMinB) k_fast_layer_lw_seg(ClassArgs a, long nt) {
+  extern __shared__ double ssb_stack[];  // [stack element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= a.perm_count[SEG]) return;
   const long id = a.perm[(size_t)SEG * (size_t)nt + t];
   const long width = (long)a.ncols * a.cfg.nspec;
-  fast_layer_problem_lw_impl<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width));
+  const StateMem st{ssb_stack + threadIdx.x, kLayerBlock};
+  fast_layer_problem_lw_impl<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width), st);
+}
+template <int NREG, int NS, int SEG>
+static void launch_fast_layer_lw_seg(const ClassArgs &a, long nt, unsigned grid, cudaStream_t st) {
+  constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
+  const size_t smem = sizeof(double) * LayerStack<NR, NS>::lw_doubles * kLayerBlock;
+  cudaFuncSetAttribute(k_fast_layer_lw_seg<NREG, NS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fast_layer_lw_seg<NREG, NS, SEG><<<grid, kLayerBlock, smem, st>>>(a, nt);
 }
 template <int NREG, int NS>
 static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kLayerBlock - 1) / kLayerBlock);
   cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
   k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt, 0);
-  k_fast_layer_lw_seg<NREG, NS, 0><<<grid, kLayerBlock, 0, st>>>(a, nt);
-  if (NREG > 1) k_fast_layer_lw_seg<NREG, NS, 1><<<grid, kLayerBlock, 0, st>>>(a, nt);
-  if (NREG > 1) k_fast_layer_lw_seg<NREG, NS, 2><<<grid, kLayerBlock, 0, st>>>(a, nt);
+  launch_fast_layer_lw_seg<NREG, NS, 0>(a, nt, grid, st);
+  if (NREG > 1) launch_fast_layer_lw_seg<NREG, NS, 1>(a, nt, grid, st);
+  if (NREG > 1) launch_fast_layer_lw_seg<NREG, NS, 2>(a, nt, grid, st);
 }
 template <>
 bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int) {
@@ -144,7 +162,7 @@ __global__ void __launch_bounds__(kFastBlock, MINB) k_fast_sweeps_lw(ClassArgs a
   extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
-  const StateMem st{ssb_state + threadIdx.x, (int)blockDim.x};
+  const StateMem st{ssb_state + threadIdx.x, kFastBlock};
   fast_column_sweeps_lw<NREG, NS, URBAN>(a, (int)t, st);
 }
 template <int NREG, int NS, bool URBAN>

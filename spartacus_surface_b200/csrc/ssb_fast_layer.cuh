@@ -4,7 +4,7 @@
 // ssb_solver.cuh (radsurf_urban_sw.F90:335-585, radsurf_urban_lw.F90:296-546
 // and the forest equivalents); the layer matrices come from ssb_fast_math.cuh.
 #pragma once
-#include "ssb_fast_math.cuh"
+#include "ssb_layer_math.cuh"
 #include "ssb_solver.cuh"
 
 namespace ssb {
@@ -16,102 +16,43 @@ struct LayerOptics {
   double vssa, vplanck, vaplanck, ve;
 };
 
-// scatter a solved block (NR regions starting at region R0) into the full-size
-// scratch matrix, zeros elsewhere; every index is a compile-time constant
-template <int NREG, int NS, int NR, int R0, bool ROWS_STREAMS, bool COLS_STREAMS>
-SSB_HDI void put_block(double *S, int &e, const double *M, int lev, int nlev, int width, int q) {
-  constexpr int n = NREG * NS, d = NREG;
-  constexpr int R = ROWS_STREAMS ? n : d, C = COLS_STREAMS ? n : d;
-  constexpr int br = ROWS_STREAMS ? NR * NS : NR, bc = COLS_STREAMS ? NR * NS : NR;
-  constexpr int i0 = ROWS_STREAMS ? R0 * NS : R0, j0 = COLS_STREAMS ? R0 * NS : R0;
-  SSB_UNROLL
-  for (int j = 0; j < C; ++j) {
-    SSB_UNROLL
-    for (int i = 0; i < R; ++i) {
-      const int bi = i - i0, bj = j - j0;
-      const bool in = bi >= 0 && bi < br && bj >= 0 && bj < bc;
-      S[sidx(e + i + R * j, lev, nlev, width, q)] = in ? M[in ? bi + br * bj : 0] : 0.0;
-    }
-  }
-  e += R * C;
-}
-
+// scalar description of the Gamma matrices of the solved block (regions R0 .. R0+NR-1)
 template <int NREG, int NS, int NR, int R0>
-SSB_HDI void fast_sw_branch(const ClassArgs &a, int q, int lev, const LayerGeom &gm, const LayerOptics &op) {
-  constexpr int N = NR * NS;
-  const SolveCfg &c = a.cfg;
-  constexpr int r0 = R0;
-  // D = G1-G2 (exchange and loss, no scattering), S = G1+G2 = D + 2 G2
-  double g0[NR * NR], Dm[N * N], Sm[N * N], g3[N * NR], nsc[N], ninv[N], frac[NR];
-  SSB_UNROLL
-  for (int i = 0; i < NR * NR; ++i) g0[i] = 0.0;
-  SSB_UNROLL
-  for (int i = 0; i < N * N; ++i) {
-    Dm[i] = 0.0;
-    Sm[i] = 0.0;
-  }
-  SSB_UNROLL
-  for (int i = 0; i < N * NR; ++i) g3[i] = 0.0;
+SSB_HDI void fill_layer_coef(const ClassArgs &a, const LayerGeom &gm, const LayerOptics &op, LayerCoef<NR, NS> &k) {
+  k.set_streams(&a.lg);
   SSB_UNROLL
   for (int rf = 0; rf < NR; ++rf) {
-    const int Rf = r0 + rf;
-    frac[rf] = (NR == 1) ? 1.0 : gm.frac[Rf];
+    const int Rf = R0 + rf;
+    double loss = 0.0;
     SSB_UNROLL
     for (int Rt = 0; Rt < NREG; ++Rt) {
       if (Rt == Rf) continue;
       const double fx = gm.f_exchange[Rt + 3 * Rf];
-      g0[rf + NR * rf] -= op.tan0 * fx;
-      SSB_UNROLL
-      for (int js = 0; js < NS; ++js) Dm[(js + rf * NS) * (N + 1)] -= a.lg.tan_ang[js] * fx;
-      SSB_UNROLL
-      for (int rt = 0; rt < NR; ++rt) {
-        if (rt + r0 == Rt) {
-          g0[rt + NR * rf] = op.tan0 * fx;
-          SSB_UNROLL
-          for (int js = 0; js < NS; ++js) Dm[(js + rt * NS) + N * (js + rf * NS)] = a.lg.tan_ang[js] * fx;
-        }
-      }
+      loss += fx;
+      if (Rt >= R0 && Rt < R0 + NR) k.dx[(Rt - R0) + NR * rf] = fx;
     }
+    k.loss[rf] = loss;
+    k.ext[rf] = op.ext[Rf];
+    k.es[rf] = op.ext[Rf] * op.ssa[Rf];
+    k.fw[rf] = a.cfg.urban ? gm.f_wall[Rf] : 0.0;
+    k.frac[rf] = (NR == 1) ? 1.0 : gm.frac[Rf];
+    k.rfrac[rf] = (NR == 1) ? 1.0 : 1.0 / gm.frac[Rf];
   }
-  SSB_UNROLL
-  for (int r = 0; r < NR; ++r) {
-    const int Rr = r0 + r;
-    const double ext = op.ext[Rr], es = op.ext[Rr] * op.ssa[Rr];
-    const double fw = c.urban ? gm.f_wall[Rr] : 0.0;
-    g0[r + NR * r] = g0[r + NR * r] - ext / (c.urban ? op.zcos : op.cos_sza) - op.tan0 * fw * op.wall_ext;
-    SSB_UNROLL
-    for (int js = 0; js < NS; ++js) {
-      const int i = js + r * NS;
-      const double rmu = 1.0 / a.lg.mu[js];
-      Dm[i + N * i] = Dm[i + N * i] - ext * rmu - a.lg.tan_ang[js] * fw * op.wall_ext;
-      ninv[i] = a.lg.weight[js] * a.lg.mu[js] * ((NR == 1) ? 1.0 : gm.frac[Rr]);
-      nsc[i] = 1.0 / ninv[i];
-      g3[i + N * r] = 0.5 * (a.lg.weight[js] * es + a.lg.vweight[js] * op.sin0 * fw * op.wall_factor);
-      SSB_UNROLL
-      for (int jt = 0; jt < NS; ++jt)
-        Sm[(jt + r * NS) + N * i] =
-            a.lg.weight[jt] * es * rmu + a.lg.vweight[jt] * a.lg.tan_ang[js] * fw * op.wall_factor;  // 2 G2
-    }
-  }
-  SSB_UNROLL
-  for (int i = 0; i < N * N; ++i) Sm[i] += Dm[i];
+  k.wall_ext = op.wall_ext;
+  k.wall_factor = op.wall_factor;
+}
 
-  double R[N * N], T[N * N], Idiff[N * N], Sup[N * NR], Sdn[N * NR], Idd[N * NR], E[NR * NR], Idir[NR * NR];
-  fast_layer_sw_math<NR, NS>(op.dz, g0, Dm, Sm, g3, nsc, ninv, frac, R, T, Sup, Sdn, E, Idir, Idiff, Idd);
-  const int nlev = a.lmax, width = a.ne_layer;
-  int e = 0;
-  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, R, lev, nlev, width, q);
-  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, T, lev, nlev, width, q);
-  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, Idiff, lev, nlev, width, q);
-  put_block<NREG, NS, NR, R0, true, false>(a.layer, e, Sup, lev, nlev, width, q);
-  put_block<NREG, NS, NR, R0, true, false>(a.layer, e, Sdn, lev, nlev, width, q);
-  put_block<NREG, NS, NR, R0, true, false>(a.layer, e, Idd, lev, nlev, width, q);
-  put_block<NREG, NS, NR, R0, false, false>(a.layer, e, E, lev, nlev, width, q);
-  put_block<NREG, NS, NR, R0, false, false>(a.layer, e, Idir, lev, nlev, width, q);
-  bool bad = false;
-  SSB_UNROLL
-  for (int i = 0; i < N * N; ++i) bad = bad || !(fabs(R[i]) < 1.0e300) || !(fabs(T[i]) < 1.0e300);
-  count_failure(a.status, bad ? 1 : 0);
+template <int NREG, int NS, int NR, int R0>
+SSB_HDI void fast_sw_branch(const ClassArgs &a, int q, int lev, const LayerGeom &gm, const LayerOptics &op,
+                            const StateMem &st) {
+  LayerCoef<NR, NS> k;
+  fill_layer_coef<NREG, NS, NR, R0>(a, gm, op, k);
+  k.tan0 = op.tan0;
+  k.sin0 = op.sin0;
+  k.rcos = 1.0 / (a.cfg.urban ? op.zcos : op.cos_sza);
+  double *P = a.layer + sidx(0, lev, a.lmax, a.ne_layer, q);
+  const bool ok = layer_sw_solve<NREG, NS, NR, R0>(k, op.dz, P, st);
+  count_failure(a.status, ok ? 0 : 1);
 }
 
 SSB_HDI void load_geometry_inputs(const ClassArgs &a, int il, double &bf, double &bs, double &vf, double &vs,
@@ -177,110 +118,56 @@ SSB_HDI bool fast_sw_prepare(const ClassArgs &a, int q, int lev, LayerGeom &gm, 
 }
 
 template <int NREG, int NS>
-SSB_HD inline void fast_layer_problem_sw(const ClassArgs &a, int q, int lev) {
+SSB_HD inline void fast_layer_problem_sw(const ClassArgs &a, int q, int lev, const StateMem &st) {
   LayerGeom gm;
   LayerOptics op;
   if (!fast_sw_prepare<NREG, NS>(a, q, lev, gm, op)) return;
   const int seg = branch_segment(gm, NREG);
   if (seg == 0) {
-    fast_sw_branch<NREG, NS, NREG, 0>(a, q, lev, gm, op);
+    fast_sw_branch<NREG, NS, NREG, 0>(a, q, lev, gm, op, st);
   } else if (seg == 1) {
-    fast_sw_branch<NREG, NS, 1, 0>(a, q, lev, gm, op);  // vegetation-free layer: clear region only
+    fast_sw_branch<NREG, NS, 1, 0>(a, q, lev, gm, op, st);  // vegetation-free layer: clear region only
   } else {
-    if (NREG > 1) fast_sw_branch<NREG, NS, (NREG > 1 ? NREG - 1 : 1), (NREG > 1 ? 1 : 0)>(a, q, lev, gm, op);
+    if (NREG > 1) fast_sw_branch<NREG, NS, (NREG > 1 ? NREG - 1 : 1), (NREG > 1 ? 1 : 0)>(a, q, lev, gm, op, st);
   }
 }
 
 // one pre-classified problem: SEG is known at compile time, so only one sub-block size is instantiated
 template <int NREG, int NS, int SEG>
-SSB_HDI void fast_layer_problem_sw_seg(const ClassArgs &a, int q, int lev) {
+SSB_HDI void fast_layer_problem_sw_seg(const ClassArgs &a, int q, int lev, const StateMem &st) {
   LayerGeom gm;
   LayerOptics op;
   if (!fast_sw_prepare<NREG, NS>(a, q, lev, gm, op)) return;
   constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
   constexpr int R0 = (SEG == 2 && NREG > 1) ? 1 : 0;
-  fast_sw_branch<NREG, NS, NR, R0>(a, q, lev, gm, op);
+  fast_sw_branch<NREG, NS, NR, R0>(a, q, lev, gm, op, st);
 }
 
 template <int NREG, int NS, int NR, int R0>
 SSB_HDI void fast_lw_branch(const ClassArgs &a, int q, int lev, const LayerGeom &gm, const LayerOptics &op,
-                            double wall_emission, int g, int il) {
+                            double wall_emission, const StateMem &st) {
   constexpr int N = NR * NS;
-  const SolveCfg &c = a.cfg;
-  constexpr int r0 = R0;
-  double Dm[N * N], Sm[N * N], nsc[N], ninv[N], brate[N];
-  SSB_UNROLL
-  for (int i = 0; i < N * N; ++i) {
-    Dm[i] = 0.0;
-    Sm[i] = 0.0;
-  }
-  SSB_UNROLL
-  for (int rf = 0; rf < NR; ++rf) {
-    const int Rf = r0 + rf;
-    SSB_UNROLL
-    for (int Rt = 0; Rt < NREG; ++Rt) {
-      if (Rt == Rf) continue;
-      const double fx = gm.f_exchange[Rt + 3 * Rf];
-      SSB_UNROLL
-      for (int js = 0; js < NS; ++js) Dm[(js + rf * NS) * (N + 1)] -= a.lg.tan_ang[js] * fx;
-      SSB_UNROLL
-      for (int rt = 0; rt < NR; ++rt) {
-        if (rt + r0 == Rt) {
-          SSB_UNROLL
-          for (int js = 0; js < NS; ++js) Dm[(js + rt * NS) + N * (js + rf * NS)] = a.lg.tan_ang[js] * fx;
-        }
-      }
-    }
-  }
+  LayerCoef<NR, NS> k;
+  fill_layer_coef<NREG, NS, NR, R0>(a, gm, op, k);
+  k.tan0 = k.sin0 = k.rcos = 0.0;
+  double brate[N];
   SSB_UNROLL
   for (int r = 0; r < NR; ++r) {
-    const int Rr = r0 + r;
-    const double ext = op.ext[Rr], es = op.ext[Rr] * op.ssa[Rr];
-    const double fw = c.urban ? gm.f_wall[Rr] : 0.0;
-    const double volume_emiss = gm.frac[Rr] * (ext * (1.0 - op.ssa[Rr]) * op.planck[Rr]);
-    const double wall_emiss = c.urban ? gm.norm_perim_wall[Rr] * a.lg.vadjustment * wall_emission : 0.0;
+    const int Rr = R0 + r;
+    const double volume_emiss = gm.frac[Rr] * (op.ext[Rr] * (1.0 - op.ssa[Rr]) * op.planck[Rr]);
+    const double wall_emiss = a.cfg.urban ? gm.norm_perim_wall[Rr] * a.lg.vadjustment * wall_emission : 0.0;
     SSB_UNROLL
-    for (int js = 0; js < NS; ++js) {
-      const int i = js + r * NS;
-      const double rmu = 1.0 / a.lg.mu[js];
-      Dm[i + N * i] = Dm[i + N * i] - ext * rmu - a.lg.tan_ang[js] * fw * op.wall_ext;
-      ninv[i] = a.lg.weight[js] * a.lg.mu[js] * ((NR == 1) ? 1.0 : gm.frac[Rr]);
-      nsc[i] = 1.0 / ninv[i];
-      brate[i] = (a.lg.hweight[js] * rmu) * volume_emiss + (0.5 * a.lg.vweight[js]) * wall_emiss;
-      SSB_UNROLL
-      for (int jt = 0; jt < NS; ++jt)
-        Sm[(jt + r * NS) + N * i] =
-            a.lg.weight[jt] * es * rmu + a.lg.vweight[jt] * a.lg.tan_ang[js] * fw * op.wall_factor;  // 2 G2
-    }
+    for (int js = 0; js < NS; ++js)
+      brate[js + r * NS] = (a.lg.hweight[js] / a.lg.mu[js]) * volume_emiss + (0.5 * a.lg.vweight[js]) * wall_emiss;
   }
-  SSB_UNROLL
-  for (int i = 0; i < N * N; ++i) Sm[i] += Dm[i];
-
-  double R[N * N], T[N * N], IF[N * N], src[N], isrc[N];
-  fast_layer_lw_math<NR, NS>(op.dz, Dm, Sm, brate, nsc, ninv, R, T, src, IF, isrc);
-  constexpr int n = NREG * NS;
-  const int nlev = a.lmax, width = a.ne_layer;
-  int e = 0;
-  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, R, lev, nlev, width, q);
-  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, T, lev, nlev, width, q);
-  put_block<NREG, NS, NR, R0, true, true>(a.layer, e, IF, lev, nlev, width, q);
-  constexpr int i0 = R0 * NS;
-  SSB_UNROLL
-  for (int i = 0; i < n; ++i) {
-    const int bi = i - i0;
-    const bool in = bi >= 0 && bi < N;
-    a.layer[sidx(e + i, lev, nlev, width, q)] = in ? src[in ? bi : 0] : 0.0;
-    a.layer[sidx(e + n + i, lev, nlev, width, q)] = in ? isrc[in ? bi : 0] : 0.0;
-  }
-  bool bad = false;
-  SSB_UNROLL
-  for (int i = 0; i < N * N; ++i) bad = bad || !(fabs(R[i]) < 1.0e300) || !(fabs(T[i]) < 1.0e300);
-  count_failure(a.status, bad ? 1 : 0);
+  double *P = a.layer + sidx(0, lev, a.lmax, a.ne_layer, q);
+  const bool ok = layer_lw_solve<NREG, NS, NR, R0>(k, brate, op.dz, P, st);
+  count_failure(a.status, ok ? 0 : 1);
 }
 
 // inputs of one longwave layer problem (also writes the emission bookkeeping terms); SEG < 0: dispatch at run time
 template <int NREG, int NS, int SEG>
-SSB_HDI void fast_layer_problem_lw_impl(const ClassArgs &a, int q, int lev) {
+SSB_HDI void fast_layer_problem_lw_impl(const ClassArgs &a, int q, int lev, const StateMem &st) {
   const SolveCfg &c = a.cfg;
   const int nspec = c.nspec;
   const int ic = q / nspec, g = q % nspec;
@@ -341,23 +228,23 @@ SSB_HDI void fast_layer_problem_lw_impl(const ClassArgs &a, int q, int lev) {
   if (SEG >= 0) {
     constexpr int NR = (SEG <= 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
     constexpr int R0 = (SEG == 2 && NREG > 1) ? 1 : 0;
-    fast_lw_branch<NREG, NS, NR, R0>(a, q, lev, gm, op, wall_emission, g, il);
+    fast_lw_branch<NREG, NS, NR, R0>(a, q, lev, gm, op, wall_emission, st);
     return;
   }
   const int seg = branch_segment(gm, NREG);
   if (seg == 0) {
-    fast_lw_branch<NREG, NS, NREG, 0>(a, q, lev, gm, op, wall_emission, g, il);
+    fast_lw_branch<NREG, NS, NREG, 0>(a, q, lev, gm, op, wall_emission, st);
   } else if (seg == 1) {
-    fast_lw_branch<NREG, NS, 1, 0>(a, q, lev, gm, op, wall_emission, g, il);
+    fast_lw_branch<NREG, NS, 1, 0>(a, q, lev, gm, op, wall_emission, st);
   } else {
     if (NREG > 1)
-      fast_lw_branch<NREG, NS, (NREG > 1 ? NREG - 1 : 1), (NREG > 1 ? 1 : 0)>(a, q, lev, gm, op, wall_emission, g, il);
+      fast_lw_branch<NREG, NS, (NREG > 1 ? NREG - 1 : 1), (NREG > 1 ? 1 : 0)>(a, q, lev, gm, op, wall_emission, st);
   }
 }
 
 template <int NREG, int NS>
-SSB_HD inline void fast_layer_problem_lw(const ClassArgs &a, int q, int lev) {
-  fast_layer_problem_lw_impl<NREG, NS, -1>(a, q, lev);
+SSB_HD inline void fast_layer_problem_lw(const ClassArgs &a, int q, int lev, const StateMem &st) {
+  fast_layer_problem_lw_impl<NREG, NS, -1>(a, q, lev, st);
 }
 
 // segment of a layer problem for the partition kernel; -1 when the problem is skipped

@@ -24,14 +24,6 @@
 
 namespace ssb {
 
-// per-thread state slice: element e at p[e * stride] (shared memory, stride =
-// blockDim.x, on the device; a plain local array on the host)
-struct StateMem {
-  double *p;
-  int stride;
-  SSB_HDI double &operator()(int e) const { return p[(size_t)e * stride]; }
-};
-
 // One scratch area (layer or interface) as seen by the calling problem: `base` points at
 // element 0 of level 0, levels are `lev_stride` doubles apart and element e sits at the
 // compile-time offset e * kScratchTile, so a layer is addressed from one register pair.

@@ -34,14 +34,16 @@ struct HostBackend {
   void layer_sw(const ssb::ClassArgs &a, long nt) {
     const long width = (long)a.ncols * a.cfg.nspec;
     const bool f = fast && a.cfg.ns == NS && NS <= 2;
+    double stack[128];
+    const ssb::StateMem st{stack, 1};
     for (long t = 0; t < nt; ++t) {
       const int q = (int)(t % width), lev = (int)(t / width);
       if (f && a.cfg.nreg == 1)
-        ssb::fast_layer_problem_sw<1, (NS <= 2 ? NS : 1)>(a, q, lev);
+        ssb::fast_layer_problem_sw<1, (NS <= 2 ? NS : 1)>(a, q, lev, st);
       else if (f && a.cfg.nreg == 2)
-        ssb::fast_layer_problem_sw<2, (NS <= 2 ? NS : 1)>(a, q, lev);
+        ssb::fast_layer_problem_sw<2, (NS <= 2 ? NS : 1)>(a, q, lev, st);
       else if (f && a.cfg.nreg == 3)
-        ssb::fast_layer_problem_sw<3, (NS <= 2 ? NS : 1)>(a, q, lev);
+        ssb::fast_layer_problem_sw<3, (NS <= 2 ? NS : 1)>(a, q, lev, st);
       else
         ssb::layer_problem_sw<NS>(a, q, lev);
     }
@@ -50,14 +52,16 @@ struct HostBackend {
   void layer_lw(const ssb::ClassArgs &a, long nt) {
     const long width = (long)a.ncols * a.cfg.nspec;
     const bool f = fast && a.cfg.ns == NS && NS <= 2;
+    double stack[128];
+    const ssb::StateMem st{stack, 1};
     for (long t = 0; t < nt; ++t) {
       const int q = (int)(t % width), lev = (int)(t / width);
       if (f && a.cfg.nreg == 1)
-        ssb::fast_layer_problem_lw<1, (NS <= 2 ? NS : 1)>(a, q, lev);
+        ssb::fast_layer_problem_lw<1, (NS <= 2 ? NS : 1)>(a, q, lev, st);
       else if (f && a.cfg.nreg == 2)
-        ssb::fast_layer_problem_lw<2, (NS <= 2 ? NS : 1)>(a, q, lev);
+        ssb::fast_layer_problem_lw<2, (NS <= 2 ? NS : 1)>(a, q, lev, st);
       else if (f && a.cfg.nreg == 3)
-        ssb::fast_layer_problem_lw<3, (NS <= 2 ? NS : 1)>(a, q, lev);
+        ssb::fast_layer_problem_lw<3, (NS <= 2 ? NS : 1)>(a, q, lev, st);
       else
         ssb::layer_problem_lw<NS>(a, q, lev);
     }
