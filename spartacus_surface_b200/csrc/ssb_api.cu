@@ -167,6 +167,7 @@ struct CudaBackend {
   Context &cx;
   int lane;
   size_t budget;
+  bool layer_was_fast = false;  // the chunk's layer kernels were the register-resident ones
   explicit CudaBackend(Context &c, int lane_ = 0, size_t budget_ = 0)
       : cx(c), lane(lane_), budget(budget_ ? budget_ : c.budget_doubles) {}
   const int *dev_cols(const ssb::Plan &, size_t off) { return (const int *)cx.d_cols.p + off; }
@@ -216,6 +217,7 @@ struct CudaBackend {
         b.perm = b.perm_count + 4;
       }
       const bool done = ssb::fast_layer_sw<NS>(b, nt, cx.stream, cx.fast_minblocks);
+      layer_was_fast = done;
       if (done && b.perm) g_launches += 4;
       if (done) check_launch();
       tick(0, false);
@@ -233,6 +235,7 @@ struct CudaBackend {
         b.perm = b.perm_count + 4;
       }
       const bool done = ssb::fast_layer_lw<NS>(b, nt, cx.stream, cx.fast_minblocks);
+      layer_was_fast = done;
       if (done && b.perm) g_launches += 4;
       if (done) check_launch();
       tick(2, false);
@@ -242,7 +245,8 @@ struct CudaBackend {
   }
   template <int NS>
   void sweeps_sw(const ssb::ClassArgs &a, long nt) {
-    if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
+    // the register-resident sweeps read what the partition pass of the layer kernels prepared
+    if (cx.fast_mode && (layer_was_fast || a.lmax == 0) && nt > 0 && cx.first_error == cudaSuccess) {
       tick(1, true);
       const bool done = ssb::fast_sweeps_sw<NS>(a, nt, cx.stream, cx.fast_minblocks_sweeps);
       if (done) check_launch();
@@ -253,7 +257,7 @@ struct CudaBackend {
   }
   template <int NS>
   void sweeps_lw(const ssb::ClassArgs &a, long nt) {
-    if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
+    if (cx.fast_mode && (layer_was_fast || a.lmax == 0) && nt > 0 && cx.first_error == cudaSuccess) {
       tick(3, true);
       const bool done = ssb::fast_sweeps_lw<NS>(a, nt, cx.stream, cx.fast_minblocks_sweeps);
       if (done) check_launch();

@@ -33,8 +33,31 @@ struct Scr {
   SSB_HDI Scr(double *area, int nlev, int nelem, int q)
       : base(area + sidx(0, 0, nlev, nelem, q)), lev_stride((size_t)nelem * kScratchTile) {}
   SSB_HDI double ld(int e, int lev) const { return base[(size_t)lev * lev_stride + (size_t)e * kScratchTile]; }
+  SSB_HDI double ldp(int e, int lev, bool keep) const {  // structural zeros are not loaded
+    double v = 0.0;
+    if (keep) v = base[(size_t)lev * lev_stride + (size_t)e * kScratchTile];
+    return v;
+  }
   SSB_HDI void st(int e, int lev, double v) const { base[(size_t)lev * lev_stride + (size_t)e * kScratchTile] = v; }
 };
+
+// A layer that solves only a sub-block of its regions ("segment" 1: clear region, 2: vegetated
+// regions; radsurf_urban_sw.F90:512-583) leaves the rest of its matrices zero.  The layer
+// kernels do not write those zeros and the sweeps do not load them: an element is loaded when
+// the segment keeps its class (0: couples the clear region with a vegetated one, 1: inside the
+// clear block, 2: inside the vegetated block).  KIND: 0 = streams x streams (n x n),
+// 1 = streams x regions (n x d), 2 = regions x regions (d x d), 3 = vector over streams.
+struct SegKeep {
+  bool k[3];
+};
+SSB_HDI SegKeep seg_keep(int seg) { return SegKeep{{seg == 0, seg != 2, seg != 1}}; }
+template <int KIND, int NS>
+SSB_HD constexpr int seg_class(int i, int j) {
+  return KIND == 3 ? (i / NS == 0 ? 1 : 2)
+                   : ((KIND == 2 ? i : i / NS) == 0 && (KIND == 0 ? j / NS : j) == 0)
+                         ? 1
+                         : ((KIND == 2 ? i : i / NS) > 0 && (KIND == 0 ? j / NS : j) > 0) ? 2 : 0;
+}
 
 // (V (x) I_NS) x : below-interface vector (NRB*NS) from the above-interface one (NREG*NS)
 template <int NREG, int NRB, int NS>
@@ -52,24 +75,31 @@ SSB_HDI void expand_down(const double *V, const double *x, double *y) {
 }
 
 // y1 += A x1, y2 += A x2 with A (R x C) streamed once from scratch
-template <int R, int C>
-SSB_HDI void smv2(const Scr &S, int e0, int lev, const double *x1, const double *x2, double *y1, double *y2) {
+template <int R, int C, int KIND = -1, int NS = 1>
+SSB_HDI void smv2(const Scr &S, int e0, int lev, const double *x1, const double *x2, double *y1, double *y2,
+                  const SegKeep &sk = SegKeep{{true, true, true}}) {
   SSB_UNROLL
   for (int j = 0; j < C; ++j) {
     SSB_UNROLL
     for (int i = 0; i < R; ++i) {
-      const double a = S.ld(e0 + i + R * j, lev);
+      const double a = (KIND < 0) ? S.ld(e0 + i + R * j, lev)
+                                  : S.ldp(e0 + i + R * j, lev, sk.k[seg_class<(KIND < 0 ? 0 : KIND), NS>(i, j)]);
       y1[i] = fma(a, x1[j], y1[i]);
       y2[i] = fma(a, x2[j], y2[i]);
     }
   }
 }
-template <int R, int C>
-SSB_HDI void smv1(const Scr &S, int e0, int lev, const double *x, double *y) {
+template <int R, int C, int KIND = -1, int NS = 1>
+SSB_HDI void smv1(const Scr &S, int e0, int lev, const double *x, double *y,
+                  const SegKeep &sk = SegKeep{{true, true, true}}) {
   SSB_UNROLL
   for (int j = 0; j < C; ++j) {
     SSB_UNROLL
-    for (int i = 0; i < R; ++i) y[i] = fma(S.ld(e0 + i + R * j, lev), x[j], y[i]);
+    for (int i = 0; i < R; ++i) {
+      const double a = (KIND < 0) ? S.ld(e0 + i + R * j, lev)
+                                  : S.ldp(e0 + i + R * j, lev, sk.k[seg_class<(KIND < 0 ? 0 : KIND), NS>(i, j)]);
+      y[i] = fma(a, x[j], y[i]);
+    }
   }
 }
 
@@ -80,9 +110,9 @@ SSB_HDI void smv1(const Scr &S, int e0, int lev, const double *x, double *y) {
 //   Wx  = D^-1 (a_above Wa + Wb)             (n x NW extra right-hand sides supplied by the caller
 //                                             through `rhs_extra`, already holding Wb on entry;
 //                                             Wa is streamed from the layer scratch at oWa)
-template <int n, int NW>
+template <int n, int NW, int NS, int WKIND>
 SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl, int oR, int oT, int oWa, int oLU,
-                         double *LU, double *X, double *rhs_extra) {
+                         double *LU, double *X, double *rhs_extra, const SegKeep &sk) {
   double Aa[n * n];
   SSB_UNROLL
   for (int i = 0; i < n * n; ++i) Aa[i] = st(i);
@@ -92,7 +122,7 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
     for (int i = 0; i < n; ++i) LU[i + n * j] = (i == j) ? 1.0 : 0.0;
     SSB_UNROLL
     for (int k = 0; k < n; ++k) {
-      const double r = L.ld(oR + k + n * j, jl);
+      const double r = L.ldp(oR + k + n * j, jl, sk.k[seg_class<0, NS>(k, j)]);
       SSB_UNROLL
       for (int i = 0; i < n; ++i) LU[i + n * j] = fma(-Aa[i + n * k], r, LU[i + n * j]);
     }
@@ -106,7 +136,7 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
     for (int i = 0; i < n; ++i) X[i + n * j] = 0.0;
     SSB_UNROLL
     for (int k = 0; k < n; ++k) {
-      const double t = L.ld(oT + k + n * j, jl);
+      const double t = L.ldp(oT + k + n * j, jl, sk.k[seg_class<0, NS>(k, j)]);
       SSB_UNROLL
       for (int i = 0; i < n; ++i) X[i + n * j] = fma(Aa[i + n * k], t, X[i + n * j]);
     }
@@ -115,13 +145,23 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
   for (int j = 0; j < NW; ++j) {
     SSB_UNROLL
     for (int k = 0; k < n; ++k) {
-      const double w = L.ld(oWa + k + n * j, jl);
+      const double w = L.ldp(oWa + k + n * j, jl, sk.k[seg_class<WKIND, NS>(k, j)]);
       SSB_UNROLL
       for (int i = 0; i < n; ++i) rhs_extra[i + n * j] = fma(Aa[i + n * k], w, rhs_extra[i + n * j]);
     }
   }
   sm_lu_solve_left<n, n>(LU, X);
   sm_lu_solve_left<n, NW>(LU, rhs_extra);
+}
+
+// overlap matrices of interface k from the interface scratch (written by fast_prepare_level)
+template <int NREG, int NRB>
+SSB_HDI void load_overlap(const Scr &W, int oU, int k, double *U, double *V) {
+  SSB_UNROLL
+  for (int i = 0; i < NREG * NRB; ++i) {
+    U[i] = W.ld(oU + i, k);
+    V[i] = W.ld(oU + NREG * NRB + i, k);
+  }
 }
 
 // a_above(next)[(u,jt),(up,js)] = sum_{lo,lo'} U[u,lo] V[lo',up] Ab[(lo,jt),(lo',js)] + roof term,
@@ -244,7 +284,10 @@ struct SwSweepLayout {
   static constexpr int n = NREG * NS, d = NREG;
   static constexpr int oR = 0, oT = n * n, oIdiff = 2 * n * n, oSup = 3 * n * n, oSdn = oSup + n * d,
                        oIdd = oSdn + n * d, oE = oIdd + n * d, oIdir = oE + d * d;
+  static constexpr int oGeo = oIdir + d * d;                      // geometry block (fast_prepare_level)
   static constexpr int oAa = 0, oDa = n * n, oLU = oDa + n * d;  // interface scratch of the fast path
+  static constexpr int NRB = URBAN ? NREG + 1 : NREG, m = NRB * NS;
+  static constexpr int oU = 2 * n * n + n * d + m * m + m * NRB, oV = oU + NREG * NRB;  // overlap matrices
   static constexpr int state_doubles = n * n + n * d;
 };
 
@@ -310,6 +353,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, 0, st(i));
   for (int jl = 0; jl < nlay; ++jl) {
     const int il = il1 + jl;
+    const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
     double X[n * n], Wd[n * d];
     {
       double LU[n * n];
@@ -320,24 +364,30 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
         for (int i = 0; i < n; ++i) Wd[i + n * j] = 0.0;
         SSB_UNROLL
         for (int k = 0; k < d; ++k) {
-          const double e = L.ld(Lay::oE + k + d * j, jl);
+          const double e = L.ldp(Lay::oE + k + d * j, jl, sk.k[seg_class<2, NS>(k, j)]);
           SSB_UNROLL
           for (int i = 0; i < n; ++i) Wd[i + n * j] = fma(st(Lay::oDa + i + n * k), e, Wd[i + n * j]);
         }
       }
-      adding_core<n, d>(st, L, W, jl, Lay::oR, Lay::oT, Lay::oSdn, Lay::oLU, LU, X, Wd);
+      adding_core<n, d, NS, 1>(st, L, W, jl, Lay::oR, Lay::oT, Lay::oSdn, Lay::oLU, LU, X, Wd, sk);
     }
     // [a_below | d_below] (street part) = [R | Sup] + T [X | Wd]
     double Ab[n * n], Db[n * d];
     SSB_UNROLL
-    for (int i = 0; i < n * n; ++i) Ab[i] = L.ld(Lay::oR + i, jl);
+    for (int j = 0; j < n; ++j) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) Ab[i + n * j] = L.ldp(Lay::oR + i + n * j, jl, sk.k[seg_class<0, NS>(i, j)]);
+    }
     SSB_UNROLL
-    for (int i = 0; i < n * d; ++i) Db[i] = L.ld(Lay::oSup + i, jl);
+    for (int j = 0; j < d; ++j) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) Db[i + n * j] = L.ldp(Lay::oSup + i + n * j, jl, sk.k[seg_class<1, NS>(i, j)]);
+    }
     SSB_UNROLL
     for (int k = 0; k < n; ++k) {
       SSB_UNROLL
       for (int i = 0; i < n; ++i) {
-        const double t = L.ld(Lay::oT + i + n * k, jl);
+        const double t = L.ldp(Lay::oT + i + n * k, jl, sk.k[seg_class<0, NS>(i, k)]);
         SSB_UNROLL
         for (int j = 0; j < n; ++j) Ab[i + n * j] = fma(t, X[k + n * j], Ab[i + n * j]);
         SSB_UNROLL
@@ -357,7 +407,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
       }
     }
     double U[12], V[12];
-    overlap_at(a, il1, nlay, jl + 1, U, V);
+    load_overlap<NREG, NRB>(W, Lay::oU, jl + 1, U, V);
     overlap_matrix<NREG, NRB, NS>(Ab, rb, U, V, st, Lay::oAa);
     // d_above(next)[(u,jt), up] = sum U[u,lo] (Db V)[(lo,jt), up] + roof
     SSB_UNROLL
@@ -424,13 +474,22 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   double flux_dn_dir_clear = 1.0 / zcos;
   for (int jl = nlay - 1; jl >= 0; --jl) {
     const int il = il1 + jl;
-    LayerGeom gm;
-    double bf, vf, ve;
-    geometry_of_layer(a, il, 1.0, gm, bf, vf, ve);
+    const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
+    double f_wall[3], od_scaling[3];
+    SSB_UNROLL
+    for (int r = 0; r < 3; ++r) {
+      f_wall[r] = L.ld(Lay::oGeo + r, jl);
+      od_scaling[r] = L.ld(Lay::oGeo + 3 + r, jl);
+    }
+    const double f_wall_dir_clear = L.ld(Lay::oGeo + 6, jl);
+    const bool veg = NREG > 1 || !URBAN;
+    const double bf = URBAN ? a.cp.building_fraction[il] : 0.0;
+    const double vf = (veg && a.cp.veg_fraction) ? a.cp.veg_fraction[il] : 0.0;
+    const double ve = (veg && a.cp.veg_ext) ? a.cp.veg_ext[il] : 0.0;
     double xb_d[m], xb_f[m], dir_below[NRB];
     {
       double U[12], V[12];
-      overlap_at(a, il1, nlay, jl + 1, U, V);
+      load_overlap<NREG, NRB>(W, Lay::oU, jl + 1, U, V);
       expand_down<NREG, NRB, NS>(V, xa_d, xb_d);
       expand_down<NREG, NRB, NS>(V, xa_f, xb_f);
       SSB_UNROLL
@@ -445,13 +504,13 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
     double y_d[n], y_f[n], refl[n], ddir[d];
     SSB_UNROLL
     for (int i = 0; i < n; ++i) y_d[i] = y_f[i] = refl[i] = 0.0;
-    smv2<n, n>(L, Lay::oT, jl, xb_d, xb_f, y_d, y_f);
-    smv1<n, d>(L, Lay::oSdn, jl, dir_below, y_d);
+    smv2<n, n, 0, NS>(L, Lay::oT, jl, xb_d, xb_f, y_d, y_f, sk);
+    smv1<n, d, 1, NS>(L, Lay::oSdn, jl, dir_below, y_d, sk);
     {
       double da_new[d];
       SSB_UNROLL
       for (int i = 0; i < d; ++i) da_new[i] = 0.0;
-      smv1<d, d>(L, Lay::oE, jl, dir_below, da_new);
+      smv1<d, d, 2, NS>(L, Lay::oE, jl, dir_below, da_new, sk);
       SSB_UNROLL
       for (int i = 0; i < d; ++i) {
         ddir[i] = dir_below[i] - da_new[i];
@@ -475,7 +534,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
     for (int j = 0; j < n; ++j) {
       SSB_UNROLL
       for (int i = 0; i < n; ++i) {
-        const double r = L.ld(Lay::oR + i + n * j, jl);
+        const double r = L.ldp(Lay::oR + i + n * j, jl, sk.k[seg_class<0, NS>(i, j)]);
         z2_d[i] = fma(r, refl[j], z2_d[i]);
         ub_d[i] = fma(r, xb_d[j], ub_d[i]);
         ub_f[i] = fma(r, xb_f[j], ub_f[i]);
@@ -490,8 +549,8 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
       sm_lu_solve_left<n, 1>(LU, z2_d);
       sm_lu_solve_left<n, 1>(LU, z2_f);
     }
-    smv2<n, n>(L, Lay::oT, jl, z1_d, z1_f, ub_d, ub_f);
-    smv1<n, d>(L, Lay::oSup, jl, dir_below, ub_d);
+    smv2<n, n, 0, NS>(L, Lay::oT, jl, z1_d, z1_f, ub_d, ub_f, sk);
+    smv1<n, d, 1, NS>(L, Lay::oSup, jl, dir_below, ub_d, sk);
     if (URBAN) {
       const double ralb = SSB_LAY(a.sw.roof_albedo, g, il);
       const double ralb_dir = a.sw.roof_albedo_dir ? SSB_LAY(a.sw.roof_albedo_dir, g, il) : ralb;
@@ -568,9 +627,9 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
       }
       SSB_UNROLL
       for (int i = 0; i < d; ++i) idir[i] = 0.0;
-      smv2<n, n>(L, Lay::oIdiff, jl, cv_d, cv_f, if_d, if_f);
-      smv1<d, d>(L, Lay::oIdir, jl, ddir, idir);
-      smv1<n, d>(L, Lay::oIdd, jl, ddir, if_d);
+      smv2<n, n, 0, NS>(L, Lay::oIdiff, jl, cv_d, cv_f, if_d, if_f, sk);
+      smv1<d, d, 2, NS>(L, Lay::oIdir, jl, ddir, idir, sk);
+      smv1<n, d, 1, NS>(L, Lay::oIdd, jl, ddir, if_d, sk);
     }
     double smu_d[NREG], smu_f[NREG], stan_d[NREG], stan_f[NREG];
     SSB_UNROLL
@@ -594,10 +653,10 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
       SSB_UNROLL
       for (int r = 1; r < NREG; ++r) {
         air_d += air_abs * (idir[r] + smu_d[r]);
-        vdir += vabs * idir[r] * gm.od_scaling[r];
-        veg_d += vabs * (idir[r] + smu_d[r]) * gm.od_scaling[r];
+        vdir += vabs * idir[r] * od_scaling[r];
+        veg_d += vabs * (idir[r] + smu_d[r]) * od_scaling[r];
         air_f += air_abs * smu_f[r];
-        veg_f += vabs * smu_f[r] * gm.od_scaling[r];
+        veg_f += vabs * smu_f[r] * od_scaling[r];
       }
       SSB_FL(fdir, veg_air_abs, il) = air_d;
       SSB_FL(fdir, veg_abs, il) = veg_d;
@@ -610,9 +669,9 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
       double win_dir = 0.0, win_d = 0.0, win_f = 0.0;
       SSB_UNROLL
       for (int r = 0; r < NREG; ++r) {
-        win_dir += gm.f_wall[r] * sin0 * idir[r];
-        win_d += gm.f_wall[r] * stan_d[r];
-        win_f += gm.f_wall[r] * stan_f[r];
+        win_dir += f_wall[r] * sin0 * idir[r];
+        win_d += f_wall[r] * stan_d[r];
+        win_f += f_wall[r] * stan_f[r];
       }
       SSB_FL(fdir, wall_in_dir, il) = win_dir;
       SSB_FL(fdir, wall_in, il) = win_dir + win_d;
@@ -644,7 +703,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
         }
         if (URBAN && fdir.wall_sunlit_frac)
           fdir.wall_sunlit_frac[il] =
-              0.5 * SSB_FL(fdir, wall_in_dir, il) / dmax(SSB_EPS, (gm.f_wall_dir_clear * sin0 * int_flux_dir_clear));
+              0.5 * SSB_FL(fdir, wall_in_dir, il) / dmax(SSB_EPS, (f_wall_dir_clear * sin0 * int_flux_dir_clear));
       }
       flux_dn_dir_clear = flux_dn_dir_clear * trans_dir_clear;
     }
@@ -686,7 +745,10 @@ template <int NREG, int NS, bool URBAN>
 struct LwSweepLayout {
   static constexpr int n = NREG * NS, d = NREG;
   static constexpr int oR = 0, oT = n * n, oIF = 2 * n * n, oSrc = 3 * n * n, oIsrc = oSrc + n, oBook = oIsrc + n;
+  static constexpr int oGeo = oBook + 3 * d + 1;  // geometry block (fast_prepare_level)
   static constexpr int oAa = 0, oSa = n * n, oLU = oSa + n;
+  static constexpr int NRB = URBAN ? NREG + 1 : NREG, m = NRB * NS;
+  static constexpr int oU = 2 * n * n + n + m * m + m, oV = oU + NREG * NRB;  // overlap matrices
   static constexpr int state_doubles = n * n + n;
 };
 
@@ -738,24 +800,28 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, 0, st(i));
   for (int jl = 0; jl < nlay; ++jl) {
     const int il = il1 + jl;
+    const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
     double X[n * n], v1[n];
     {
       double LU[n * n];
       // v1 <- source_above, then adding_core adds a_above src and applies D^-1
       SSB_UNROLL
       for (int i = 0; i < n; ++i) v1[i] = st(Lay::oSa + i);
-      adding_core<n, 1>(st, L, W, jl, Lay::oR, Lay::oT, Lay::oSrc, Lay::oLU, LU, X, v1);
+      adding_core<n, 1, NS, 3>(st, L, W, jl, Lay::oR, Lay::oT, Lay::oSrc, Lay::oLU, LU, X, v1, sk);
     }
     double Ab[n * n], Sb[n];
     SSB_UNROLL
-    for (int i = 0; i < n * n; ++i) Ab[i] = L.ld(Lay::oR + i, jl);
+    for (int j = 0; j < n; ++j) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) Ab[i + n * j] = L.ldp(Lay::oR + i + n * j, jl, sk.k[seg_class<0, NS>(i, j)]);
+    }
     SSB_UNROLL
-    for (int i = 0; i < n; ++i) Sb[i] = L.ld(Lay::oSrc + i, jl);
+    for (int i = 0; i < n; ++i) Sb[i] = L.ldp(Lay::oSrc + i, jl, sk.k[seg_class<3, NS>(i, 0)]);
     SSB_UNROLL
     for (int k = 0; k < n; ++k) {
       SSB_UNROLL
       for (int i = 0; i < n; ++i) {
-        const double t = L.ld(Lay::oT + i + n * k, jl);
+        const double t = L.ldp(Lay::oT + i + n * k, jl, sk.k[seg_class<0, NS>(i, k)]);
         SSB_UNROLL
         for (int j = 0; j < n; ++j) Ab[i + n * j] = fma(t, X[k + n * j], Ab[i + n * j]);
         Sb[i] = fma(t, v1[k], Sb[i]);
@@ -775,7 +841,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       }
     }
     double U[12], V[12];
-    overlap_at(a, il1, nlay, jl + 1, U, V);
+    load_overlap<NREG, NRB>(W, Lay::oU, jl + 1, U, V);
     overlap_matrix<NREG, NRB, NS>(Ab, rb, U, V, st, Lay::oAa);
     SSB_UNROLL
     for (int u = 0; u < NREG; ++u) {
@@ -819,20 +885,26 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   SSB_FC(fnorm, top_net) = top_emissivity;
   for (int jl = nlay - 1; jl >= 0; --jl) {
     const int il = il1 + jl;
-    LayerGeom gm;
-    double bf, vf, ve;
-    geometry_of_layer(a, il, a.lg.vadjustment2, gm, bf, vf, ve);
+    const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
+    double f_wall[3], od_scaling[3];
+    SSB_UNROLL
+    for (int r = 0; r < 3; ++r) {
+      f_wall[r] = L.ld(Lay::oGeo + r, jl);
+      od_scaling[r] = L.ld(Lay::oGeo + 3 + r, jl);
+    }
+    const bool veg = NREG > 1 || !URBAN;
+    const double ve = (veg && a.cp.veg_ext) ? a.cp.veg_ext[il] : 0.0;
     double xb_i[m], xb_f[m];
     {
       double U[12], V[12];
-      overlap_at(a, il1, nlay, jl + 1, U, V);
+      load_overlap<NREG, NRB>(W, Lay::oU, jl + 1, U, V);
       expand_down<NREG, NRB, NS>(V, xa_i, xb_i);
       expand_down<NREG, NRB, NS>(V, xa_f, xb_f);
     }
     double src[n], sa[n];
     SSB_UNROLL
     for (int i = 0; i < n; ++i) {
-      src[i] = L.ld(Lay::oSrc + i, jl);
+      src[i] = L.ldp(Lay::oSrc + i, jl, sk.k[seg_class<3, NS>(i, 0)]);
       sa[i] = W.ld(Lay::oSa + i, jl);
     }
     // y = T x (+ src) ; z1 = D^-1 (a_above y + sa) ; z2 = D^-1 (y + R sa) ; ub = R x + src
@@ -842,7 +914,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       y_i[i] = src[i];
       y_f[i] = 0.0;
     }
-    smv2<n, n>(L, Lay::oT, jl, xb_i, xb_f, y_i, y_f);
+    smv2<n, n, 0, NS>(L, Lay::oT, jl, xb_i, xb_f, y_i, y_f, sk);
     double z1_i[n], z1_f[n], z2_i[n], z2_f[n], ub_i[m], ub_f[m];
     SSB_UNROLL
     for (int i = 0; i < n; ++i) {
@@ -860,7 +932,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
     for (int j = 0; j < n; ++j) {
       SSB_UNROLL
       for (int i = 0; i < n; ++i) {
-        const double r = L.ld(Lay::oR + i + n * j, jl);
+        const double r = L.ldp(Lay::oR + i + n * j, jl, sk.k[seg_class<0, NS>(i, j)]);
         z2_i[i] = fma(r, sa[j], z2_i[i]);
         ub_i[i] = fma(r, xb_i[j], ub_i[i]);
         ub_f[i] = fma(r, xb_f[j], ub_f[i]);
@@ -875,7 +947,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       sm_lu_solve_left<n, 1>(LU, z2_i);
       sm_lu_solve_left<n, 1>(LU, z2_f);
     }
-    smv2<n, n>(L, Lay::oT, jl, z1_i, z1_f, ub_i, ub_f);
+    smv2<n, n, 0, NS>(L, Lay::oT, jl, z1_i, z1_f, ub_i, ub_f, sk);
     if (URBAN) {
       const double bfj = a.cp.building_fraction[il];
       const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + 1]) : bfj;
@@ -939,10 +1011,10 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       for (int i = 0; i < n; ++i) {
         tv_i[i] = xb_i[i] + ua_i[i];
         tv_f[i] = xb_f[i] + ua_f[i];
-        if_i[i] = L.ld(Lay::oIsrc + i, jl);
+        if_i[i] = L.ldp(Lay::oIsrc + i, jl, sk.k[seg_class<3, NS>(i, 0)]);
         if_f[i] = 0.0;
       }
-      smv2<n, n>(L, Lay::oIF, jl, tv_i, tv_f, if_i, if_f);
+      smv2<n, n, 0, NS>(L, Lay::oIF, jl, tv_i, tv_f, if_i, if_f, sk);
       SSB_UNROLL
       for (int i = 0; i < 3 * d + 1; ++i) book[i] = L.ld(Lay::oBook + i, jl);
     }
@@ -968,9 +1040,9 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       SSB_UNROLL
       for (int r = 1; r < NREG; ++r) {
         air_i += air_abs * smu_i[r] - book[d + r] * dz;
-        veg_i += vabs * smu_i[r] * gm.od_scaling[r] - book[2 * d + r] * dz;
+        veg_i += vabs * smu_i[r] * od_scaling[r] - book[2 * d + r] * dz;
         air_f += air_abs * smu_f[r];
-        veg_f += vabs * smu_f[r] * gm.od_scaling[r];
+        veg_f += vabs * smu_f[r] * od_scaling[r];
       }
       SSB_FL(fint, veg_air_abs, il) = air_i;
       SSB_FL(fint, veg_abs, il) = veg_i;
@@ -981,8 +1053,8 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       double win_i = 0.0, win_f = 0.0;
       SSB_UNROLL
       for (int r = 0; r < NREG; ++r) {
-        win_i += gm.f_wall[r] * stan_i[r];
-        win_f += gm.f_wall[r] * stan_f[r];
+        win_i += f_wall[r] * stan_i[r];
+        win_f += f_wall[r] * stan_f[r];
       }
       const double wemis = SSB_LAY(a.lw.wall_emissivity, g, il);
       SSB_FL(fint, wall_in, il) = win_i;

@@ -334,8 +334,9 @@ SSB_HDI void layer_solve_row(const double *A, const double *Pr, int eB, int i, d
 }
 
 // Shortwave layer of the solved block (NR regions starting at region R0 of NREG): writes
-// R, T, int_diff, S_up, S_dn, int_dir_diff, E, int_dir (radsurf_urban_sw.F90:512-583
-// scatter them into full-size matrices) to the layer scratch at P.  Returns false when
+// R, T, int_diff, S_up, S_dn, int_dir_diff, E, int_dir to the layer scratch at P, at their
+// positions in the full-size matrices (radsurf_urban_sw.F90:512-583); the zeros outside the
+// block are not written - the sweeps know the segment of the layer and do not load them.  Returns false when
 // R or T is not finite.
 template <int NREG, int NS, int NR, int R0>
 SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, const StateMem &st_in) {
@@ -344,37 +345,6 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
   constexpr int eR = 0, eT = n * n, eIdiff = 2 * n * n, eSup = 3 * n * n, eSdn = eSup + n * d, eIdd = eSdn + n * d,
                 eE = eIdd + n * d, eIdir = eE + d * d;
   constexpr int oU0 = Stk::oX, oEps = oU0 + D * D, oSq = oEps + D, oRsq = oSq + D;
-  if (NR < NREG) {  // zeros outside the solved block
-    SSB_UNROLL
-    for (int j = 0; j < n; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        if (i >= i0 && i < i0 + N && j >= i0 && j < i0 + N) continue;
-        SSB_OUT(P, eR + i + n * j) = 0.0;
-        SSB_OUT(P, eT + i + n * j) = 0.0;
-        SSB_OUT(P, eIdiff + i + n * j) = 0.0;
-      }
-    }
-    SSB_UNROLL
-    for (int j = 0; j < d; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        if (i >= i0 && i < i0 + N && j >= r0 && j < r0 + D) continue;
-        SSB_OUT(P, eSup + i + n * j) = 0.0;
-        SSB_OUT(P, eSdn + i + n * j) = 0.0;
-        SSB_OUT(P, eIdd + i + n * j) = 0.0;
-      }
-    }
-    SSB_UNROLL
-    for (int j = 0; j < d; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < d; ++i) {
-        if (i >= r0 && i < r0 + D && j >= r0 && j < r0 + D) continue;
-        SSB_OUT(P, eE + i + d * j) = 0.0;
-        SSB_OUT(P, eIdir + i + d * j) = 0.0;
-      }
-    }
-  }
   // ---- direct beam: g0 = B0 diag(1/frac) with B0 symmetric -> symmetric Jacobi ----------
   double g0inv[D * D];
   {
@@ -459,34 +429,29 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
   const StateMem st = opaque(st_in);
   bool bad = false;
   {
+    // sum (sigma = +1) then difference (-1) problem; rows of B pass through the T slot, X+ is
+    // parked in the R slot.  Rolled loops: the same code serves both stages and all rows.
     double A[N * N];
-    // sum problem: X+ = R + T, parked in the R slot (B+ rows pass through the T slot)
-    layer_stage_factor<NREG, NS, NR, R0>(c, st, 1.0, lam, e, A, P, eT, nullptr, 0);
-    {
+    SSB_ROLLED
+    for (int sg = 0; sg < 2; ++sg) {
+      layer_stage_factor<NREG, NS, NR, R0>(c, st, sg ? -1.0 : 1.0, lam, e, A, P, eT, nullptr, 0);
       const double *Pr = opaque_ptr(P);
-      SSB_UNROLL
+      SSB_ROLLED
       for (int i = 0; i < N; ++i) {
         double x[N];
         layer_solve_row<NREG, NS, NR, R0>(A, Pr, eT, i, x);
-        SSB_UNROLL
-        for (int k = 0; k < N; ++k) SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = x[k];
-      }
-    }
-    // difference problem: X- = R - T
-    layer_stage_factor<NREG, NS, NR, R0>(c, st, -1.0, lam, e, A, P, eT, nullptr, 0);
-    {
-      const double *Pr = opaque_ptr(P);
-      SSB_UNROLL
-      for (int i = 0; i < N; ++i) {
-        double x[N];
-        layer_solve_row<NREG, NS, NR, R0>(A, Pr, eT, i, x);
-        SSB_UNROLL
-        for (int k = 0; k < N; ++k) {
-          const double xp = SSB_OUT(Pr, eR + (i + i0) + n * (k + i0));
-          const double r = 0.5 * (xp + x[k]), t = 0.5 * (xp - x[k]);
-          bad = bad || !(fabs(r) < 1.0e300) || !(fabs(t) < 1.0e300);
-          SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = r;
-          SSB_OUT(P, eT + (i + i0) + n * (k + i0)) = t;
+        if (sg == 0) {
+          SSB_UNROLL
+          for (int k = 0; k < N; ++k) SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = x[k];
+        } else {
+          SSB_UNROLL
+          for (int k = 0; k < N; ++k) {
+            const double xp = SSB_OUT(Pr, eR + (i + i0) + n * (k + i0));
+            const double r = 0.5 * (xp + x[k]), t = 0.5 * (xp - x[k]);
+            bad = bad || !(fabs(r) < 1.0e300) || !(fabs(t) < 1.0e300);
+            SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = r;
+            SSB_OUT(P, eT + (i + i0) + n * (k + i0)) = t;
+          }
         }
       }
     }
@@ -494,8 +459,8 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
   // ---- particular solutions per direct eigen-mode:
   //   a = g3p + g4p = 2 V (eps^2 - Lambda)^-1 V^-1 D c ,  b = g3p - g4p = -(S a + 2c)/eps,
   // source terms S_up +- S_dn = +-(R+-T)(r1+-r2) + (G3p +- G4p e0) G0^-1
-  double g3p[N * D], g4p[N * D];
-  SSB_UNROLL
+  // (rolled over the modes; G3p, G4p are parked in the S_up / S_dn slots)
+  SSB_ROLLED
   for (int jd = 0; jd < D; ++jd) {
     const double eps = st(oEps + jd);
     double a[N], cc[N];
@@ -550,16 +515,22 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
         if (k % NS == i % NS || k / NS == i / NS) s = fma(c.S(i, k), a[k], s);
       }
       const double b = s * mreps;
-      g3p[i + N * jd] = 0.5 * (a[i] + b);
-      g4p[i + N * jd] = 0.5 * (a[i] - b);
+      SSB_OUT(P, eSup + (i + i0) + n * (jd + r0)) = 0.5 * (a[i] + b);
+      SSB_OUT(P, eSdn + (i + i0) + n * (jd + r0)) = 0.5 * (a[i] - b);
     }
   }
   // S_up + S_dn = (R+T) rp + qp ; S_up - S_dn = (T-R) rm + qm, row by row from the scratch, with
   //   rp = -(G3p e0 + G4p) G0^-1, rm = -(G3p e0 - G4p) G0^-1, qp = (G3p + G4p e0) G0^-1, qm = (G3p - G4p e0) G0^-1
   {
-    double G0i[D * D], e0[D], rp[N * D], rm[N * D];
+    double G0i[D * D], e0[D], rp[N * D], rm[N * D], g3p[N * D], g4p[N * D];
+    const double *Ps = opaque_ptr(P);
     SSB_UNROLL
     for (int jd = 0; jd < D; ++jd) {
+      SSB_UNROLL
+      for (int i = 0; i < N; ++i) {
+        g3p[i + N * jd] = SSB_OUT(Ps, eSup + (i + i0) + n * (jd + r0));
+        g4p[i + N * jd] = SSB_OUT(Ps, eSdn + (i + i0) + n * (jd + r0));
+      }
       e0[jd] = exp(st(oEps + jd) * dz);
       SSB_UNROLL
       for (int j = 0; j < D; ++j) G0i[jd + D * j] = st(oU0 + j + D * jd) * st(oRsq + j);
@@ -579,8 +550,8 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
         rm[i + N * j] = sm;
       }
     }
-    const double *Ps = opaque_ptr(P);
-    SSB_UNROLL
+    // rows are independent: rolled loop, G3p / G4p of the row re-read from their parking slots
+    SSB_ROLLED
     for (int i = 0; i < N; ++i) {
       double xp[N], xm[N];
       SSB_UNROLL
@@ -589,14 +560,19 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
         xp[k] = r + t;
         xm[k] = t - r;
       }
+      double g3r[D], g4r[D];
+      SSB_UNROLL
+      for (int jd = 0; jd < D; ++jd) {
+        g3r[jd] = SSB_OUT(Ps, eSup + (i + i0) + n * (jd + r0));
+        g4r[jd] = SSB_OUT(Ps, eSdn + (i + i0) + n * (jd + r0)) * e0[jd];
+      }
       SSB_UNROLL
       for (int j = 0; j < D; ++j) {
         double sum = 0.0, dif = 0.0;
         SSB_UNROLL
         for (int jd = 0; jd < D; ++jd) {
-          const double g4e = g4p[i + N * jd] * e0[jd];
-          sum = fma(g3p[i + N * jd] + g4e, G0i[jd + D * j], sum);
-          dif = fma(g3p[i + N * jd] - g4e, G0i[jd + D * j], dif);
+          sum = fma(g3r[jd] + g4r[jd], G0i[jd + D * j], sum);
+          dif = fma(g3r[jd] - g4r[jd], G0i[jd + D * j], dif);
         }
         SSB_UNROLL
         for (int k = 0; k < N; ++k) {
@@ -620,24 +596,6 @@ SSB_HDI bool layer_lw_solve(const LayerCoef<NR, NS> &c, const double *brate, dou
   typedef LayerStack<NR, NS> Stk;
   constexpr int N = NR * NS, n = NREG * NS, i0 = R0 * NS;
   constexpr int eR = 0, eT = n * n, eIF = 2 * n * n, eSrc = 3 * n * n, eIsrc = eSrc + n;
-  if (NR < NREG) {
-    SSB_UNROLL
-    for (int j = 0; j < n; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        if (i >= i0 && i < i0 + N && j >= i0 && j < i0 + N) continue;
-        SSB_OUT(P, eR + i + n * j) = 0.0;
-        SSB_OUT(P, eT + i + n * j) = 0.0;
-        SSB_OUT(P, eIF + i + n * j) = 0.0;
-      }
-    }
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      if (i >= i0 && i < i0 + N) continue;
-      SSB_OUT(P, eSrc + i) = 0.0;
-      SSB_OUT(P, eIsrc + i) = 0.0;
-    }
-  }
   {
     double LUs[N * N], y[N];
     SSB_UNROLL
@@ -656,52 +614,50 @@ SSB_HDI bool layer_lw_solve(const LayerCoef<NR, NS> &c, const double *brate, dou
   layer_eigen<NR, NS>(c, dz, st_in, lam2, lam, e);
   const StateMem st = opaque(st_in);
   bool bad = false;
-  double A[N * N];
   {
-    double z[N], y[N];
+    double A[N * N], z[N], y[N];
     SSB_UNROLL
     for (int k = 0; k < N; ++k) {
       z[k] = 2.0 * (1.0 - e[k]) / lam[k];
       y[k] = st(Stk::oX + k);
     }
-    // sum problem: X+ parked in the R slot; int_flux = (2 V Z) A+^-1 (its rows pass through the IF slot)
-    layer_stage_factor<NREG, NS, NR, R0>(c, st, 1.0, lam, e, A, P, eT, z, eIF);
-    const double *Pr = opaque_ptr(P);
-    SSB_UNROLL
-    for (int i = 0; i < N; ++i) {
-      double x[N];
-      layer_solve_row<NREG, NS, NR, R0>(A, Pr, eT, i, x);
-      double s = 0.0;
-      SSB_UNROLL
-      for (int k = 0; k < N; ++k) {
-        s = fma(x[k], y[k], s);
-        SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = x[k];
-      }
-      SSB_OUT(P, eSrc + i + i0) = y[i] - s;
-      layer_solve_row<NREG, NS, NR, R0>(A, Pr, eIF, i, x);
-      double f = 0.0;
-      SSB_UNROLL
-      for (int k = 0; k < N; ++k) {
-        f = fma(x[k], y[k], f);
-        SSB_OUT(P, eIF + (i + i0) + n * (k + i0)) = x[k];
-      }
-      SSB_OUT(P, eIsrc + i + i0) = 2.0 * (y[i] * dz - f);
-    }
-  }
-  layer_stage_factor<NREG, NS, NR, R0>(c, st, -1.0, lam, e, A, P, eT, nullptr, 0);
-  {
-    const double *Pr = opaque_ptr(P);
-    SSB_UNROLL
-    for (int i = 0; i < N; ++i) {
-      double x[N];
-      layer_solve_row<NREG, NS, NR, R0>(A, Pr, eT, i, x);
-      SSB_UNROLL
-      for (int k = 0; k < N; ++k) {
-        const double xp = SSB_OUT(Pr, eR + (i + i0) + n * (k + i0));
-        const double r = 0.5 * (xp + x[k]), t = 0.5 * (xp - x[k]);
-        bad = bad || !(fabs(r) < 1.0e300) || !(fabs(t) < 1.0e300);
-        SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = r;
-        SSB_OUT(P, eT + (i + i0) + n * (k + i0)) = t;
+    // sum then difference problem (rolled); in the sum stage also int_flux = (2 V Z) A+^-1, whose
+    // rows pass through the IF slot, and the two source vectors
+    SSB_ROLLED
+    for (int sg = 0; sg < 2; ++sg) {
+      layer_stage_factor<NREG, NS, NR, R0>(c, st, sg ? -1.0 : 1.0, lam, e, A, P, eT, sg ? nullptr : z, eIF);
+      const double *Pr = opaque_ptr(P);
+      SSB_ROLLED
+      for (int i = 0; i < N; ++i) {
+        double x[N];
+        layer_solve_row<NREG, NS, NR, R0>(A, Pr, eT, i, x);
+        if (sg == 0) {
+          const double yi = st(Stk::oX + i);
+          double s = 0.0;
+          SSB_UNROLL
+          for (int k = 0; k < N; ++k) {
+            s = fma(x[k], y[k], s);
+            SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = x[k];
+          }
+          SSB_OUT(P, eSrc + i + i0) = yi - s;
+          layer_solve_row<NREG, NS, NR, R0>(A, Pr, eIF, i, x);
+          double f = 0.0;
+          SSB_UNROLL
+          for (int k = 0; k < N; ++k) {
+            f = fma(x[k], y[k], f);
+            SSB_OUT(P, eIF + (i + i0) + n * (k + i0)) = x[k];
+          }
+          SSB_OUT(P, eIsrc + i + i0) = 2.0 * (yi * dz - f);
+        } else {
+          SSB_UNROLL
+          for (int k = 0; k < N; ++k) {
+            const double xp = SSB_OUT(Pr, eR + (i + i0) + n * (k + i0));
+            const double r = 0.5 * (xp + x[k]), t = 0.5 * (xp - x[k]);
+            bad = bad || !(fabs(r) < 1.0e300) || !(fabs(t) < 1.0e300);
+            SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = r;
+            SSB_OUT(P, eT + (i + i0) + n * (k + i0)) = t;
+          }
+        }
       }
     }
   }
