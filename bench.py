@@ -31,28 +31,55 @@ FULL_COLUMNS = 1 << 20
 UNIT = "column*g*layers/s"
 METRIC = "column_g_layers_per_s_SW+LW"
 
-# Algorithmic FLOPs per (column, layer), nreg = 3 (SURVEY.md §8d / App. C closed form)
-FLOPS = {
-    2: {"sw_layer": 24.5e3, "sw_sweep": 4.0e3, "lw_layer": 13.5e3, "lw_sweep": 3.5e3},
-    4: {"sw_layer": 176.3e3, "sw_sweep": 25.2e3, "lw_layer": 105.4e3, "lw_sweep": 23.2e3},
-}
-# Compulsory HBM bytes per (column, layer): 25 input + 40 output doubles + per-column terms (§8d)
+# Algorithmic FLOPs per (column, layer) (SURVEY.md section 8d / App. C closed form).  "full": every layer
+# charged the full-size (nreg = 3) count, the agreed numerator of SURVEY 8d; "seg": layers that solve only
+# a sub-block of their regions (no vegetation in the layer: clear region only) charged with the order they
+# actually solve - the reference does the same - while the sweeps stay full size.
+def _layer_flops(n, d):
+    N = 2 * n + d
+    sw = 25 * n**3 + (38.67 + 8 * d) * n**3 + 2 / 3 * N**3 + 2 * N * N * d + 4 * n * N * d + 8 * d * n * n
+    lw = 25 * n**3 + 34.67 * n**3 + 16 * n * n
+    return sw, lw
+
+
+def flop_table(ns, f_full, f_clear, f_veg):
+    """per (column, layer): kernel family -> (flops "full" count, flops segment-aware)"""
+    n, d, m = 3 * ns, 3, 4 * ns
+    sw_full, lw_full = _layer_flops(n, d)
+    sw_c, lw_c = _layer_flops(ns, 1)
+    sw_v, lw_v = _layer_flops(2 * ns, 2)
+    sw_sweep = 10.67 * n**3 + 22 * n * n + 4 * m * m + 6 * n * n * d
+    lw_sweep = 10.67 * n**3 + 26 * n * n + 4 * m * m
+    return {"sw_layer": (sw_full, f_full * sw_full + f_clear * sw_c + f_veg * sw_v),
+            "lw_layer": (lw_full, f_full * lw_full + f_clear * lw_c + f_veg * lw_v),
+            "sw_sweep": (sw_sweep, sw_sweep), "lw_sweep": (lw_sweep, lw_sweep)}
+
+
+# Compulsory HBM bytes per (column, layer): 25 input + 40 output doubles + per-column terms (section 8d)
 ALGO_BYTES_PER_COL_LAYER = 540.0
-# Bytes a sweep kernel must move per (column, layer) given the layer/sweep kernel split (nreg = 3):
-# layer matrices streamed in the upward sweep (R, T twice each, S_up, S_dn, E) and in the fused downward
-# sweep, interface state (a_above, d_above / source_above, LU) written and read once, flux outputs.
-def _sweep_bytes(ns):
+
+
+def sweep_bytes(ns, f_full, f_clear, f_veg):
+    """Bytes a sweep kernel must move per (column, layer) given the layer / sweep kernel split (nreg = 3,
+    urban): the layer matrices of the solved sub-block once in the upward and once in the fused downward
+    sweep, interface state (a_above, d_above / source_above, LU factors) written and read once, overlap
+    matrices and geometry block read in both sweeps, flux outputs."""
+    def one(nr):
+        n, d = nr * ns, nr
+        sw_up = 2 * n * n + 2 * n * d + d * d                # R, T, S_dn, S_up, E
+        sw_dn = 3 * n * n + 3 * n * d + 2 * d * d            # + int_diff, int_dir_diff, int_dir
+        lw_up = 2 * n * n + n                                # R, T, source
+        lw_dn = 3 * n * n + 2 * n + 10                       # + int_flux, int_flux_source, bookkeeping
+        return sw_up + sw_dn, lw_up + lw_dn
     n, d = 3 * ns, 3
-    sw_up = 4 * n * n + 2 * n * d + d * d
-    sw_dn = 7 * n * n + 4 * n * d + 2 * d * d
-    sw_if = 2 * n * n + n * d
-    lw_up = 4 * n * n + n
-    lw_dn = 7 * n * n + 3 * n + 3 * d + 1
-    lw_if = 2 * n * n + n
-    return {"sw": 8.0 * (sw_up + sw_dn + 2 * sw_if + 26), "lw": 8.0 * (lw_up + lw_dn + 2 * lw_if + 14)}
-
-
-SWEEP_BYTES = {2: _sweep_bytes(2), 4: _sweep_bytes(4)}
+    sw_if, lw_if = 2 * n * n + n * d, 2 * n * n + n         # per interface, written once and read once
+    uvg = 2 * (24 + 8)                                       # U, V and the geometry block, both sweeps
+    sw = lw = 0.0
+    for f, nr in ((f_full, 3), (f_clear, 1), (f_veg, 2)):
+        a, b = one(nr)
+        sw += f * a
+        lw += f * b
+    return {"sw_sweep": 8.0 * (sw + 2 * sw_if + uvg + 26 + 8), "lw_sweep": 8.0 * (lw + 2 * lw_if + uvg + 14 + 6)}
 
 
 def make_config(streams):
@@ -294,51 +321,78 @@ def main():
         except OSError:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        fl_tab = FLOPS.get(args.streams)
-        roofline = roofline_hbm = roofline_kernels = None
+        # segment mix of the layer problems (which sub-block of regions a layer solves), from the inputs
+        vfr, bfr = cp.veg_fraction, cp.building_fraction
+        min_veg = cfg.min_vegetation_fraction
+        f_clear = float((vfr <= min_veg).double().mean().item())
+        f_veg = float(((vfr > min_veg) & ((1.0 - bfr - vfr) <= min_veg)).double().mean().item())
+        f_full = 1.0 - f_clear - f_veg
+        fl_tab = flop_table(args.streams, f_full, f_clear, f_veg)
+        fam_bytes = sweep_bytes(args.streams, f_full, f_clear, f_veg)
+        traffic_tab = {}
+        try:  # DRAM bytes per (column, layer) of each kernel family from the committed ncu --set full capture
+            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+        except (OSError, ValueError):
+            pass
         step_ms = ms_max / args.steps
-        if fl_tab:
-            # per kernel family: layer kernels are FP64-bound, sweeps stream the layer matrices (HBM-bound)
-            fam_bytes = {"sw_sweep": SWEEP_BYTES[args.streams]["sw"], "lw_sweep": SWEEP_BYTES[args.streams]["lw"]}
-            roofline_kernels = {}
-            for k in ("sw_layer", "lw_layer", "sw_sweep", "lw_sweep"):
-                n_l = max(1, kt[k]["launches"])
-                per_ms = kt[k]["ms"] / n_l
-                tf = fl_tab[k] * ncol * NLAY / n_l / (per_ms * 1e-3) / 1e12
-                ent = {"avg_launch_ms": per_ms, "launches_per_step": kt[k]["launches"],
-                       "algorithmic_flops_per_column_layer": fl_tab[k], "fp64_tflops": tf,
-                       "fp64_frac": tf / fp64_peak if fp64_peak > 0 else None}
-                if k in fam_bytes:
-                    gb = fam_bytes[k] * ncol * NLAY / n_l / (per_ms * 1e-3) / 1e9
-                    ent.update({"bound": "hbm", "kernel_bytes_per_column_layer": fam_bytes[k], "gbs": gb,
-                                "hbm_frac": gb / hbm_peak})
-                else:
-                    ent["bound"] = "fp64"
-                roofline_kernels[k] = ent
-            dom = max(roofline_kernels, key=lambda k: kt[k]["ms"])
-            e = roofline_kernels[dom]
-            if e["bound"] == "fp64":
-                roofline = {"bound": "fp64", "kernel": dom, "achieved": e["fp64_tflops"], "peak": fp64_peak,
-                            "unit": "TFLOP/s", "frac": e["fp64_frac"], "traffic": None}
+        roofline_kernels = {}
+        for k in ("sw_layer", "lw_layer", "sw_sweep", "lw_sweep"):
+            n_l = max(1, kt[k]["launches"])
+            per_ms = kt[k]["ms"] / n_l
+            units = ncol * NLAY / n_l  # (column, layer) pairs of one launch (one chunk of columns)
+            tf_full = fl_tab[k][0] * units / (per_ms * 1e-3) / 1e12
+            tf_seg = fl_tab[k][1] * units / (per_ms * 1e-3) / 1e12
+            tr = traffic_tab.get(f"{k}_s{args.streams}")
+            ent = {"avg_launch_ms": per_ms, "launches_per_step": kt[k]["launches"],
+                   "column_layers_per_launch": units,
+                   "algorithmic_flops_per_column_layer": fl_tab[k][0],
+                   "algorithmic_flops_per_column_layer_segment_aware": fl_tab[k][1],
+                   "fp64_tflops": tf_full, "fp64_frac": tf_full / fp64_peak if fp64_peak > 0 else None,
+                   "fp64_frac_segment_aware": tf_seg / fp64_peak if fp64_peak > 0 else None,
+                   "traffic": tr["dram_bytes_per_column_layer"] * units if tr else None}
+            if k in fam_bytes:
+                gb = fam_bytes[k] * units / (per_ms * 1e-3) / 1e9
+                ent.update({"bound": "hbm", "algorithmic_bytes_per_column_layer": fam_bytes[k], "gbs": gb,
+                            "hbm_frac": gb / hbm_peak})
+                if ent["traffic"]:
+                    ent["dram_gbs_from_ncu_traffic"] = ent["traffic"] / (per_ms * 1e-3) / 1e9
             else:
-                roofline = {"bound": "hbm", "kernel": dom, "achieved": e["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                            "frac": e["hbm_frac"], "traffic": None,
-                            "bytes_note": "bytes the kernel must move given the layer/sweep split: layer matrices read in "
-                                          "the upward and in the fused downward sweep, interface state written and read "
-                                          "once, flux outputs (DESIGN.md section 4.3)"}
-            roofline.update({"avg_launch_ms": e["avg_launch_ms"], "launches_per_step": e["launches_per_step"],
-                             "fp64_peak_source": "measured in this run: register-resident independent DFMA chains on "
-                                                 "all SMs (ssb200_measure_fp64_peak_tflops); MEASURED_PEAKS.json has "
-                                                 "no FP64 entry",
-                             "hbm_peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"})
-            all_flops = sum(fl_tab.values()) * ncol * NLAY
-            roofline["whole_step"] = {"bound": "fp64", "achieved": all_flops / (step_ms * 1e-3) / 1e12,
-                                      "frac": all_flops / (step_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
-                                      "algorithmic_flops_per_column_layer": sum(fl_tab.values()),
-                                      "note": "SURVEY 8(d) flop count of the reference formulation / step time"}
-            gbs = ALGO_BYTES_PER_COL_LAYER * ncol * NLAY / (step_ms * 1e-3) / 1e9
-            roofline_hbm = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                            "note": "compulsory input+output bytes of the whole path only (540 B per column-layer)"}
+                ent["bound"] = "fp64"
+            roofline_kernels[k] = ent
+        dom = max(roofline_kernels, key=lambda k: kt[k]["ms"])
+        e = roofline_kernels[dom]
+        if e["bound"] == "fp64":
+            roofline = {"bound": "fp64", "kernel": dom, "achieved": e["fp64_tflops"], "peak": fp64_peak,
+                        "unit": "TFLOP/s", "frac": e["fp64_frac"], "traffic": e["traffic"],
+                        "frac_segment_aware": e["fp64_frac_segment_aware"],
+                        "flops_note": "achieved = SURVEY 8(d) algorithmic flops per (column, layer) x pairs per launch / "
+                                      "launch time; SURVEY charges every layer the full nreg=3 count - "
+                                      "frac_segment_aware charges layers without vegetation the order they solve"}
+        else:
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": e["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": e["hbm_frac"], "traffic": e["traffic"],
+                        "bytes_note": "algorithmic bytes: layer matrices of the solved sub-block read in the upward and "
+                                      "in the fused downward sweep, interface state written and read once, overlap "
+                                      "matrices and geometry block, flux outputs (DESIGN.md section 4.3)"}
+        roofline.update({"avg_launch_ms": e["avg_launch_ms"], "launches_per_step": e["launches_per_step"],
+                         "segment_mix": {"all_regions": f_full, "clear_only": f_clear, "vegetated_only": f_veg},
+                         "fp64_peak_source": "measured in this run: register-resident independent DFMA chains on "
+                                             "all SMs (ssb200_measure_fp64_peak_tflops); MEASURED_PEAKS.json has "
+                                             "no FP64 entry",
+                         "hbm_peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "traffic_source": "profiles/r01_dram_traffic.json (ncu dram__bytes_read+write per kernel "
+                                           "family, scaled to the launch)" if e["traffic"] else None})
+        all_full = sum(v[0] for v in fl_tab.values()) * ncol * NLAY
+        all_seg = sum(v[1] for v in fl_tab.values()) * ncol * NLAY
+        roofline["whole_step"] = {"bound": "fp64", "achieved": all_full / (step_ms * 1e-3) / 1e12,
+                                  "frac": all_full / (step_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
+                                  "frac_segment_aware": all_seg / (step_ms * 1e-3) / 1e12 / fp64_peak
+                                  if fp64_peak > 0 else None,
+                                  "algorithmic_flops_per_column_layer": sum(v[0] for v in fl_tab.values()),
+                                  "note": "SURVEY 8(d) flop count of the reference formulation / step time"}
+        gbs = ALGO_BYTES_PER_COL_LAYER * ncol * NLAY / (step_ms * 1e-3) / 1e9
+        roofline_hbm = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                        "note": "compulsory input+output bytes of the whole path only (540 B per column-layer)"}
 
         # ---- end to end through the host-pointer C ABI entry (pinned host buffers) --------------
         e2e = None

@@ -324,13 +324,14 @@ SSB_HDI void layer_stage_factor(const LayerCoef<NR, NS> &c, const StateMem &st, 
   }
   sm_lu<N>(A);
 }
-// row i of a parked matrix, solved against the factors: x = row A^-1
+// row i of a parked matrix (rows beyond the block read row N-1 again: the row loops fetch one
+// row ahead so that the L2 latency of the parked rows hides behind the solve of the previous one)
 template <int NREG, int NS, int NR, int R0>
-SSB_HDI void layer_solve_row(const double *A, const double *Pr, int eB, int i, double *x) {
+SSB_HDI void layer_load_row(const double *Pr, int eB, int i, double *x) {
   constexpr int N = NR * NS, n = NREG * NS, i0 = R0 * NS;
+  const int ii = (i < N ? i : N - 1) + i0;
   SSB_UNROLL
-  for (int k = 0; k < N; ++k) x[k] = SSB_OUT(Pr, eB + (i + i0) + n * (k + i0));
-  sm_lu_solve_right<1, N>(A, x);
+  for (int k = 0; k < N; ++k) x[k] = SSB_OUT(Pr, eB + ii + n * (k + i0));
 }
 
 // Shortwave layer of the solved block (NR regions starting at region R0 of NREG): writes
@@ -436,17 +437,27 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
     for (int sg = 0; sg < 2; ++sg) {
       layer_stage_factor<NREG, NS, NR, R0>(c, st, sg ? -1.0 : 1.0, lam, e, A, P, eT, nullptr, 0);
       const double *Pr = opaque_ptr(P);
+      double xn[N], xpn[N];
+      layer_load_row<NREG, NS, NR, R0>(Pr, eT, 0, xn);
+      layer_load_row<NREG, NS, NR, R0>(Pr, eR, 0, xpn);  // X+ (only meaningful in the second stage)
       SSB_ROLLED
       for (int i = 0; i < N; ++i) {
-        double x[N];
-        layer_solve_row<NREG, NS, NR, R0>(A, Pr, eT, i, x);
+        double x[N], xpr[N];
+        SSB_UNROLL
+        for (int k = 0; k < N; ++k) {
+          x[k] = xn[k];
+          xpr[k] = xpn[k];
+        }
+        layer_load_row<NREG, NS, NR, R0>(Pr, eT, i + 1, xn);
+        layer_load_row<NREG, NS, NR, R0>(Pr, eR, i + 1, xpn);
+        sm_lu_solve_right<1, N>(A, x);
         if (sg == 0) {
           SSB_UNROLL
           for (int k = 0; k < N; ++k) SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = x[k];
         } else {
           SSB_UNROLL
           for (int k = 0; k < N; ++k) {
-            const double xp = SSB_OUT(Pr, eR + (i + i0) + n * (k + i0));
+            const double xp = xpr[k];
             const double r = 0.5 * (xp + x[k]), t = 0.5 * (xp - x[k]);
             bad = bad || !(fabs(r) < 1.0e300) || !(fabs(t) < 1.0e300);
             SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = r;
@@ -627,10 +638,20 @@ SSB_HDI bool layer_lw_solve(const LayerCoef<NR, NS> &c, const double *brate, dou
     for (int sg = 0; sg < 2; ++sg) {
       layer_stage_factor<NREG, NS, NR, R0>(c, st, sg ? -1.0 : 1.0, lam, e, A, P, eT, sg ? nullptr : z, eIF);
       const double *Pr = opaque_ptr(P);
+      double xn[N], xpn[N];  // next row of B; next row of 2VZ (first stage) or of X+ (second stage)
+      layer_load_row<NREG, NS, NR, R0>(Pr, eT, 0, xn);
+      layer_load_row<NREG, NS, NR, R0>(Pr, sg ? eR : eIF, 0, xpn);
       SSB_ROLLED
       for (int i = 0; i < N; ++i) {
-        double x[N];
-        layer_solve_row<NREG, NS, NR, R0>(A, Pr, eT, i, x);
+        double x[N], xpr[N];
+        SSB_UNROLL
+        for (int k = 0; k < N; ++k) {
+          x[k] = xn[k];
+          xpr[k] = xpn[k];
+        }
+        layer_load_row<NREG, NS, NR, R0>(Pr, eT, i + 1, xn);
+        layer_load_row<NREG, NS, NR, R0>(Pr, sg ? eR : eIF, i + 1, xpn);
+        sm_lu_solve_right<1, N>(A, x);
         if (sg == 0) {
           const double yi = st(Stk::oX + i);
           double s = 0.0;
@@ -640,18 +661,18 @@ SSB_HDI bool layer_lw_solve(const LayerCoef<NR, NS> &c, const double *brate, dou
             SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = x[k];
           }
           SSB_OUT(P, eSrc + i + i0) = yi - s;
-          layer_solve_row<NREG, NS, NR, R0>(A, Pr, eIF, i, x);
+          sm_lu_solve_right<1, N>(A, xpr);
           double f = 0.0;
           SSB_UNROLL
           for (int k = 0; k < N; ++k) {
-            f = fma(x[k], y[k], f);
-            SSB_OUT(P, eIF + (i + i0) + n * (k + i0)) = x[k];
+            f = fma(xpr[k], y[k], f);
+            SSB_OUT(P, eIF + (i + i0) + n * (k + i0)) = xpr[k];
           }
           SSB_OUT(P, eIsrc + i + i0) = 2.0 * (yi * dz - f);
         } else {
           SSB_UNROLL
           for (int k = 0; k < N; ++k) {
-            const double xp = SSB_OUT(Pr, eR + (i + i0) + n * (k + i0));
+            const double xp = xpr[k];
             const double r = 0.5 * (xp + x[k]), t = 0.5 * (xp - x[k]);
             bad = bad || !(fabs(r) < 1.0e300) || !(fabs(t) < 1.0e300);
             SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = r;
