@@ -240,6 +240,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     if args.generic:
         lib.ssb200_set_option(b"fast_kernels", 0)

@@ -5,6 +5,7 @@ Kernels are assigned to families in launch order: k_partition_layers and the k_f
 that follow it form the layer family of the pass (SW first, then LW); k_fast_sweeps_* the sweep family."""
 import csv
 import json
+import re
 import subprocess
 import sys
 
@@ -27,12 +28,10 @@ def main(path, columns, streams, out=None):
         if "k_partition_layers" in name:
             pending = b
             continue
-        if "_sw" in name:
-            kind = "sw"
-        elif "_lw" in name:
-            kind = "lw"
-        else:
+        m = re.search(r"k_fast_(?:layer|sweeps)_(sw|lw)", name)
+        if not m:
             continue
+        kind = m.group(1)
         key = f"{kind}_{'sweep' if 'sweeps' in name else 'layer'}_s{streams}"
         e = fam.setdefault(key, {"dram_bytes": 0.0, "kernels": []})
         if pending is not None and "layer" in key:
