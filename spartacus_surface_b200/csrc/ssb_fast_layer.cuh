@@ -2,7 +2,7 @@
 // (column, interval, layer) with compile-time (NREG regions, NS streams).
 // Same inputs, outputs and scratch layout as layer_problem_sw/_lw of
 // ssb_solver.cuh (radsurf_urban_sw.F90:335-585, radsurf_urban_lw.F90:296-546
-// and the forest equivalents); the layer matrices come from ssb_fast_math.cuh.
+// and the forest equivalents); the layer matrices come from ssb_layer_math.cuh.
 #pragma once
 #include "ssb_layer_math.cuh"
 #include "ssb_solver.cuh"

@@ -3,7 +3,7 @@
 // index is static, so a matrix lives in registers of the one thread that owns
 // the problem.  No dynamic control flow except a fixed number of Jacobi sweeps.
 //
-// These routines back ssb_fast_math.cuh, which evaluates the same layer
+// These routines back ssb_layer_math.cuh, which evaluates the same layer
 // quantities as radtool_calc_matrices_{sw,lw}_eig.F90 through an algebraically
 // equivalent but cheaper and better conditioned route.
 #pragma once

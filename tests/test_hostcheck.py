@@ -73,7 +73,7 @@ def test_column_range_leaves_other_columns_untouched():
 @pytest.mark.parametrize("case", golden_io.list_cases())
 def test_fast_layer_math_within_sensitivity(case):
     """The register-resident layer formulation (symmetrised Jacobi eigenproblem, sum/difference
-    two-point solve; csrc/ssb_fast_math.cuh) against the oracle, tolerance of tests/parity.py."""
+    two-point solve; csrc/ssb_layer_math.cuh) against the oracle, tolerance of tests/parity.py."""
     import parity
     _, got = _run(case, hostcheck_lib.make_solver(fast=True))
     _, ora = _run(case, oracle_lib.make_solver())
