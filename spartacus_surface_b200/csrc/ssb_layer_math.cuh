@@ -124,8 +124,13 @@ struct LayerCoef {
 };
 
 // Cyclic Jacobi on a symmetric matrix held as its lower triangle (Y[i + N*j], i >= j);
-// eigenvalues return on the diagonal, eigenvectors in the columns of U.  Same rotations
-// and convergence rule as sm_jacobi.
+// eigenvalues return on the diagonal, eigenvectors in the columns of U.  The rotation
+// parameters come from two reciprocal square roots (no division): with alpha = (aqq-app)/2,
+// beta = apq, h = sqrt(alpha^2+beta^2): cos^2 = (1 + |alpha|/h)/2, sin = sign(alpha) beta /
+// (2 h cos).  A problem is converged when its off-diagonal mass is below eps^2 of the
+// diagonal mass; from then on it applies identity rotations only, so its result does not
+// depend on how many more sweeps its warp neighbours need (the sweeps stop when all lanes
+// have converged or after `max_sweeps`).
 template <int N>
 SSB_HDI void sm_jacobi_sym(double *Y, double *U, int max_sweeps) {
 #define SSB_YS(a, b) Y[((a) >= (b)) ? ((a) + N * (b)) : ((b) + N * (a))]
