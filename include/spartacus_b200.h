@@ -226,9 +226,9 @@ int ssb200_last_kernel_counts(int64_t out[5]);
  * one-thread-per-problem kernels everywhere; results agree to rounding),
  * "partition_layers" (1 = group layer problems by solved sub-block so that the
  * register-resident layer kernels run; 0 = generic layer kernels),
- * "pipeline" (1 = ssb200_radsurf overlaps H2D, kernels and D2H over blocks of
- * columns; effective with pinned host memory), "fast_minblocks[_sweeps]"
- * (launch-bounds variant of the register-resident kernels). */
+ * "pipeline" (1 = ssb200_radsurf uploads, solves and downloads blocks of columns as
+ * three overlapping stages; effective with pinned host memory), "pipeline_max_blocks"
+ * (default 16), "fast_minblocks_sweeps" (launch-bounds variant of the sweeps). */
 int ssb200_set_option(const char *name, int64_t value);
 
 /* Release cached plans, scratch and pinned staging buffers. */

@@ -144,10 +144,12 @@ struct Context {
   bool plan_uploaded = false;
   long uploaded_generation = -1;
   DevBuf d_nlay, d_istart, d_irep, d_cols, d_status, d_lay2col;
-  static constexpr int kLanes = 3;  // lane 0: device entry / bulk path; lanes 0-2: pipelined host entry
+  static constexpr int kLanes = 3;  // host entry: upload / kernel / download streams; scratch: lane 0 device entry, lane 1 host entry
   DevBuf d_scratch[kLanes], d_perm[kLanes];
   cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> blk_events;  // per pipeline block: upload done, kernels done
   int pipeline = 1;
+  int pipeline_max_blocks = 16;
   std::vector<DevBuf> stage;  // staging mirrors of host arrays for ssb200_radsurf
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -679,9 +681,8 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   ssb::CallArgs ca{config, &dcp, config->do_sw ? &dsw : nullptr, config->do_lw ? &dlw : nullptr, &dbc,
                    config->do_sw ? &d1 : nullptr, config->do_sw ? &d2 : nullptr,
                    config->do_lw ? &d3 : nullptr, config->do_lw ? &d4 : nullptr};
-  // Pipeline: the column range is cut into blocks; block b uploads its input slices,
-  // runs its kernels and downloads its output slices on lane b % 3, so transfers of
-  // neighbouring blocks overlap the kernels (pinned host memory needed for true
+  // Pipeline: the column range is cut into blocks whose input slices are uploaded, solved
+  // and downloaded as three overlapping stages (pinned host memory needed for true
   // overlap).  Requires a contiguous packed-layer range; profiling serialises.
   int range[2];
   rc = radsurf_device_locked(cx, ca, c1, c2, st, nullptr, range);
@@ -691,12 +692,21 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   int nblk = 1;
   if (cx.pipeline && contiguous && !cx.profiling && total_work >= ((size_t)1 << 17)) {
     nblk = (int)(total_work >> 16);
-    if (nblk > 12) nblk = 12;
+    if (nblk > cx.pipeline_max_blocks) nblk = cx.pipeline_max_blocks;
   }
-  const int nlanes = nblk > 1 ? Context::kLanes : 1;
-  for (int l = 0; l < nlanes; ++l)
+  // three stages on three streams, chained per block by events: uploads in block order on
+  // lane 0, kernels on lane 1 (one scratch area with the full budget, reused block after
+  // block), downloads on lane 2 - both copy engines stay busy once the pipeline has filled
+  for (int l = 0; l < Context::kLanes; ++l)
     if (!cx.lane_stream[l]) SSB_CUDA(cudaStreamCreateWithFlags(&cx.lane_stream[l], cudaStreamNonBlocking));
-  const size_t lane_budget = cx.budget_doubles / (size_t)nlanes;
+  cudaStream_t s_up = cx.lane_stream[0], s_run = cx.lane_stream[1], s_down = cx.lane_stream[2];
+  if (nblk == 1) s_up = s_down = s_run;
+  if ((int)cx.blk_events.size() < 2 * nblk) {
+    const size_t old_n = cx.blk_events.size();
+    cx.blk_events.resize((size_t)2 * nblk, nullptr);
+    for (size_t i = old_n; i < cx.blk_events.size(); ++i)
+      SSB_CUDA(cudaEventCreateWithFlags(&cx.blk_events[i], cudaEventDisableTiming));
+  }
   // first packed layer of every column >= j (Flat tiles own no layers): block boundaries
   auto layer_begin = [&](int j) -> size_t {
     for (; j < c2; ++j)
@@ -704,19 +714,25 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
     return l2;
   };
   for (int b = 0; b < nblk; ++b) {
-    const int lane = b % nlanes;
     const int cb0 = (c1 - 1) + (int)(((long long)cN * b) / nblk), cb1 = (c1 - 1) + (int)(((long long)cN * (b + 1)) / nblk);
     if (cb1 <= cb0) continue;
     const size_t lb0 = (b == 0) ? l1 : layer_begin(cb0), lb1 = (b == nblk - 1) ? l2 : layer_begin(cb1);
-    cudaStream_t ls = cx.lane_stream[lane];
-    rc = sg.copy_window(true, (size_t)cb0, (size_t)cb1, lb0, lb1, ls);
+    rc = sg.copy_window(true, (size_t)cb0, (size_t)cb1, lb0, lb1, s_up);
     if (rc) return rc;
-    rc = run_window(cx, ca, lane, lane_budget, cb0, cb1);
+    if (nblk > 1) {
+      SSB_CUDA(cudaEventRecord(cx.blk_events[2 * b], s_up));
+      SSB_CUDA(cudaStreamWaitEvent(s_run, cx.blk_events[2 * b], 0));
+    }
+    rc = run_window(cx, ca, 1, cx.budget_doubles, cb0, cb1);
     if (rc) return rc;
-    rc = sg.copy_window(false, (size_t)cb0, (size_t)cb1, lb0, lb1, ls);
+    if (nblk > 1) {
+      SSB_CUDA(cudaEventRecord(cx.blk_events[2 * b + 1], s_run));
+      SSB_CUDA(cudaStreamWaitEvent(s_down, cx.blk_events[2 * b + 1], 0));
+    }
+    rc = sg.copy_window(false, (size_t)cb0, (size_t)cb1, lb0, lb1, s_down);
     if (rc) return rc;
   }
-  for (int l = 0; l < nlanes; ++l) SSB_CUDA(cudaStreamSynchronize(cx.lane_stream[l]));
+  for (int l = 0; l < Context::kLanes; ++l) SSB_CUDA(cudaStreamSynchronize(cx.lane_stream[l]));
   int status = 0;
   SSB_CUDA(cudaMemcpy(&status, cx.d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
   return status;
@@ -755,6 +771,10 @@ int ssb200_set_option(const char *name, int64_t value) {
   }
   if (n == "pipeline") {
     g_ctx.pipeline = value != 0;
+    return 0;
+  }
+  if (n == "pipeline_max_blocks") {
+    g_ctx.pipeline_max_blocks = value < 1 ? 1 : (int)value;
     return 0;
   }
   if (n == "partition_layers") {
