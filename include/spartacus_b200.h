@@ -222,7 +222,7 @@ int ssb200_last_kernel_counts(int64_t out[5]);
 
 /* Tuning knobs: "scratch_budget_bytes" (device scratch per launch chunk;
  * 0 = automatic: half of the free memory, at most 24 GiB) and "fast_kernels"
- * (1 = use the sub-warp kernels where a configuration has one, 0 = generic
+ * (1 = use the register-resident kernels where a configuration has them, 0 = generic
  * one-thread-per-problem kernels everywhere; results agree to rounding),
  * "partition_layers" (1 = group layer problems by solved sub-block so that the
  * register-resident layer kernels run; 0 = generic layer kernels),

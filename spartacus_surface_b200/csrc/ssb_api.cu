@@ -431,7 +431,7 @@ struct Stager {
 // ===========================================================================
 extern "C" {
 
-const char *ssb200_version(void) { return "spartacus_surface_b200 0.1 (sm_100a, generic + sub-warp kernels)"; }
+const char *ssb200_version(void) { return "spartacus_surface_b200 0.1 (sm_100a, generic + register-resident kernels)"; }
 
 const char *ssb200_last_error(void) { return g_last_error.c_str(); }
 
