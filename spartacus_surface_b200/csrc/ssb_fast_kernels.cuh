@@ -25,13 +25,11 @@ constexpr int kLayerMinB = SSB_LAYER_THREADS / SSB_LAYER_BLOCK;
 // that every warp of the layer kernels runs one code path.  Warp-aggregated
 // append: the order inside a segment is not deterministic, the results are
 // (every problem is independent).
-// The same pass writes the geometry block of every layer and the overlap matrices of every
-// interface (fast_prepare_level), so one thread per (problem, level 0..lmax): `nt` layer
-// problems, `nti` >= nt threads.
-static __global__ void k_partition_layers(ClassArgs a, long nt, long nti) {
+// The same pass writes the geometry block of every layer (fast_prepare_level).
+static __global__ void k_partition_layers(ClassArgs a, long nt) {
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   int seg = -1;
-  if (t < nti) {
+  if (t < nt) {
     const long width = (long)a.ncols * a.cfg.nspec;
     seg = fast_prepare_level(a, (int)(t % width), (int)(t / width));
   }
@@ -70,8 +68,7 @@ template <int NREG, int NS>
 static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kLayerBlock - 1) / kLayerBlock);
   cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
-  const long nti = nt + (long)a.ncols * a.cfg.nspec;
-  k_partition_layers<<<(unsigned)((nti + 255) / 256), 256, 0, st>>>(a, nt, nti);
+  k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt);
   launch_fast_layer_sw_seg<NREG, NS, 0>(a, nt, grid, st);
   if (NREG > 1) launch_fast_layer_sw_seg<NREG, NS, 1>(a, nt, grid, st);
   if (NREG > 1) launch_fast_layer_sw_seg<NREG, NS, 2>(a, nt, grid, st);
@@ -146,8 +143,7 @@ template <int NREG, int NS>
 static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kLayerBlock - 1) / kLayerBlock);
   cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
-  const long nti = nt + (long)a.ncols * a.cfg.nspec;
-  k_partition_layers<<<(unsigned)((nti + 255) / 256), 256, 0, st>>>(a, nt, nti);
+  k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt);
   launch_fast_layer_lw_seg<NREG, NS, 0>(a, nt, grid, st);
   if (NREG > 1) launch_fast_layer_lw_seg<NREG, NS, 1>(a, nt, grid, st);
   if (NREG > 1) launch_fast_layer_lw_seg<NREG, NS, 2>(a, nt, grid, st);

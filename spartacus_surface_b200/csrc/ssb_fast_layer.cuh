@@ -247,43 +247,27 @@ SSB_HD inline void fast_layer_problem_lw(const ClassArgs &a, int q, int lev, con
   fast_layer_problem_lw_impl<NREG, NS, -1>(a, q, lev, st);
 }
 
-// Per (problem q, level k) preparation for the register-resident kernels, k = 0..nlay:
-//  * layer k (k < nlay): geometry block of the layer scratch; returns the segment of the
-//    layer problem (which sub-block of regions it solves), -1 when there is none;
-//  * interface k (k >= 1): overlap matrices U (nreg x nrb) and V (nrb x nreg) at the end of
-//    the interface scratch (radsurf_overlap.F90 via overlap_at).
+// Per layer problem (q, level k) preparation for the register-resident kernels: writes the
+// geometry block of the layer scratch and returns the segment of the problem (which
+// sub-block of regions it solves), -1 when there is none.
 SSB_HDI int fast_prepare_level(const ClassArgs &a, int q, int k) {
   const SolveCfg &c = a.cfg;
   const int col = a.cols[q / c.nspec];
-  const int nlay = a.nlay[col];
-  if (k > nlay) return -1;
+  if (k >= a.nlay[col]) return -1;
   if (!c.lw && !(a.cp.cos_sza[col] > 0.0)) return -1;
-  const int il1 = a.istartlay[col] - 1;
-  int seg = -1;
-  if (k < nlay) {
-    double bf, bs, vf, vs, ve, vcf, vfsd;
-    load_geometry_inputs(a, il1 + k, bf, bs, vf, vs, ve, vcf, vfsd);
-    LayerGeom gm;
-    layer_geometry(c, bf, bs, vf, vs, vcf, vfsd, c.lw ? a.lg.vadjustment2 : 1.0, gm);
-    seg = branch_segment(gm, c.nreg);
-    double *P = a.layer + sidx(a.ne_layer - kGeoElems, k, a.lmax, a.ne_layer, q);
-    for (int r = 0; r < 3; ++r) {
-      P[(size_t)r * kScratchTile] = gm.f_wall[r];
-      P[(size_t)(3 + r) * kScratchTile] = gm.od_scaling[r];
-    }
-    P[(size_t)6 * kScratchTile] = gm.f_wall_dir_clear;
-    P[(size_t)7 * kScratchTile] = (double)seg;
+  const int il = a.istartlay[col] - 1 + k;
+  double bf, bs, vf, vs, ve, vcf, vfsd;
+  load_geometry_inputs(a, il, bf, bs, vf, vs, ve, vcf, vfsd);
+  LayerGeom gm;
+  layer_geometry(c, bf, bs, vf, vs, vcf, vfsd, c.lw ? a.lg.vadjustment2 : 1.0, gm);
+  const int seg = branch_segment(gm, c.nreg);
+  double *P = a.layer + sidx(a.ne_layer - kGeoElems, k, a.lmax, a.ne_layer, q);
+  for (int r = 0; r < 3; ++r) {
+    P[(size_t)r * kScratchTile] = gm.f_wall[r];
+    P[(size_t)(3 + r) * kScratchTile] = gm.od_scaling[r];
   }
-  if (k >= 1) {
-    double U[12], V[12];
-    overlap_at(a, il1, nlay, k, U, V);
-    const int cnt = c.nreg * (c.urban ? c.nreg + 1 : c.nreg);
-    double *W = a.sweep + sidx(a.ne_sweep - 2 * cnt, k, a.lmax + 1, a.ne_sweep, q);
-    for (int i = 0; i < cnt; ++i) {
-      W[(size_t)i * kScratchTile] = U[i];
-      W[(size_t)(cnt + i) * kScratchTile] = V[i];
-    }
-  }
+  P[(size_t)6 * kScratchTile] = gm.f_wall_dir_clear;
+  P[(size_t)7 * kScratchTile] = (double)seg;
   return seg;
 }
 

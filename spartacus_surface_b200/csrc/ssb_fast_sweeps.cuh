@@ -154,14 +154,24 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
   sm_lu_solve_left<n, NW>(LU, rhs_extra);
 }
 
-// overlap matrices of interface k from the interface scratch (written by fast_prepare_level)
-template <int NREG, int NRB>
-SSB_HDI void load_overlap(const Scr &W, int oU, int k, double *U, double *V) {
-  SSB_UNROLL
-  for (int i = 0; i < NREG * NRB; ++i) {
-    U[i] = W.ld(oU + i, k);
-    V[i] = W.ld(oU + NREG * NRB + i, k);
+// overlap matrices of the interface above layer jl of the column starting at packed layer il1
+// (radsurf_overlap.F90), from the region fractions of the two adjacent layers
+template <int NREG, bool URBAN, bool LW>
+SSB_HDI void overlap_above(const ClassArgs &a, int il1, int nlay, int jl, double *U, double *V) {
+  const bool veg = NREG > 1 || !URBAN;
+  double fb[3] = {0.0, 0.0, 0.0}, fa[3] = {0.0, 0.0, 0.0};
+  {
+    const int il = il1 + jl;
+    region_fractions_t<NREG, URBAN, LW>(URBAN ? a.cp.building_fraction[il] : 0.0,
+                                        (veg && a.cp.veg_fraction) ? a.cp.veg_fraction[il] : 0.0, fb);
   }
+  const bool top = jl + 1 >= nlay;
+  if (!top) {
+    const int il = il1 + jl + 1;
+    region_fractions_t<NREG, URBAN, LW>(URBAN ? a.cp.building_fraction[il] : 0.0,
+                                        (veg && a.cp.veg_fraction) ? a.cp.veg_fraction[il] : 0.0, fa);
+  }
+  overlap_fast<NREG, URBAN>(fb, fa, top, a.cfg.min_veg, U, V);
 }
 
 // a_above(next)[(u,jt),(up,js)] = sum_{lo,lo'} U[u,lo] V[lo',up] Ab[(lo,jt),(lo',js)] + roof term,
@@ -287,7 +297,6 @@ struct SwSweepLayout {
   static constexpr int oGeo = oIdir + d * d;                      // geometry block (fast_prepare_level)
   static constexpr int oAa = 0, oDa = n * n, oLU = oDa + n * d;  // interface scratch of the fast path
   static constexpr int NRB = URBAN ? NREG + 1 : NREG, m = NRB * NS;
-  static constexpr int oU = 2 * n * n + n * d + m * m + m * NRB, oV = oU + NREG * NRB;  // overlap matrices
   static constexpr int state_doubles = n * n + n * d;
 };
 
@@ -407,7 +416,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
       }
     }
     double U[12], V[12];
-    load_overlap<NREG, NRB>(W, Lay::oU, jl + 1, U, V);
+    overlap_above<NREG, URBAN, false>(a, il1, nlay, jl, U, V);
     overlap_matrix<NREG, NRB, NS>(Ab, rb, U, V, st, Lay::oAa);
     // d_above(next)[(u,jt), up] = sum U[u,lo] (Db V)[(lo,jt), up] + roof
     SSB_UNROLL
@@ -489,7 +498,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
     double xb_d[m], xb_f[m], dir_below[NRB];
     {
       double U[12], V[12];
-      load_overlap<NREG, NRB>(W, Lay::oU, jl + 1, U, V);
+      overlap_above<NREG, URBAN, false>(a, il1, nlay, jl, U, V);
       expand_down<NREG, NRB, NS>(V, xa_d, xb_d);
       expand_down<NREG, NRB, NS>(V, xa_f, xb_f);
       SSB_UNROLL
@@ -748,7 +757,6 @@ struct LwSweepLayout {
   static constexpr int oGeo = oBook + 3 * d + 1;  // geometry block (fast_prepare_level)
   static constexpr int oAa = 0, oSa = n * n, oLU = oSa + n;
   static constexpr int NRB = URBAN ? NREG + 1 : NREG, m = NRB * NS;
-  static constexpr int oU = 2 * n * n + n + m * m + m, oV = oU + NREG * NRB;  // overlap matrices
   static constexpr int state_doubles = n * n + n;
 };
 
@@ -841,7 +849,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       }
     }
     double U[12], V[12];
-    load_overlap<NREG, NRB>(W, Lay::oU, jl + 1, U, V);
+    overlap_above<NREG, URBAN, true>(a, il1, nlay, jl, U, V);
     overlap_matrix<NREG, NRB, NS>(Ab, rb, U, V, st, Lay::oAa);
     SSB_UNROLL
     for (int u = 0; u < NREG; ++u) {
@@ -897,7 +905,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
     double xb_i[m], xb_f[m];
     {
       double U[12], V[12];
-      load_overlap<NREG, NRB>(W, Lay::oU, jl + 1, U, V);
+      overlap_above<NREG, URBAN, true>(a, il1, nlay, jl, U, V);
       expand_down<NREG, NRB, NS>(V, xa_i, xb_i);
       expand_down<NREG, NRB, NS>(V, xa_f, xb_f);
     }

@@ -293,6 +293,136 @@ SSB_HD inline void interface_fractions(const SolveCfg &c, int k, int nlay, const
   }
 }
 
+// Compile-time variant of region_fractions + interface_fractions + overlap_interface for the
+// register-resident sweeps (interfaces k = 1..nlay): same case analysis, orders known at
+// compile time, the divisions by the interface fractions replaced by 7 reciprocals.
+// `fb`, `fa`: region fractions of the layers below and above the interface (fa unused at the
+// canopy top).  U is (NREG x NRB) at [up + NREG*lo], V is (NRB x NREG) at [lo + NRB*up].
+template <int NREG, bool URBAN, bool LW>
+SSB_HDI void region_fractions_t(double bf, double vf, double *frac) {
+  if (URBAN) {
+    frac[0] = 1.0 - bf;
+    if (NREG > 1) {
+      frac[0] = dmax(0.0, frac[0] - vf);
+      const double fv = dmax(0.0, 1.0 - bf - frac[0]) * (NREG == 3 ? 0.5 : 1.0);
+      SSB_UNROLL
+      for (int r = 1; r < NREG; ++r) frac[r] = fv;
+    }
+  } else {
+    frac[0] = 1.0 - vf;
+    SSB_UNROLL
+    for (int r = 1; r < NREG; ++r) frac[r] = (LW ? (1.0 - frac[0]) : vf) * (NREG == 3 ? 0.5 : 1.0);
+  }
+}
+
+template <int NREG, bool URBAN>
+SSB_HDI void overlap_fast(const double *fb, const double *fa, bool top, double min_veg, double *U, double *V) {
+  constexpr int NRB = URBAN ? NREG + 1 : NREG;
+  double fu[NREG], fl[NRB], O[NREG * NRB];
+  SSB_UNROLL
+  for (int r = 0; r < NREG; ++r) {
+    fu[r] = top ? (r == 0 ? 1.0 : 0.0) : fa[r];
+    fl[r] = fb[r];
+  }
+  if (URBAN) {
+    double sa = 0.0, sb = 0.0;
+    SSB_UNROLL
+    for (int r = 0; r < NREG; ++r) {
+      sa += fa[r];
+      sb += fb[r];
+    }
+    if (top) {
+      fl[NREG] = 1.0 - sb;
+    } else {
+      fl[NREG] = sa - sb;
+      if (fl[NREG] < 0.0) {  // overhanging building (radsurf_overlap.F90:376-388)
+        const double sc = sa / sb;
+        SSB_UNROLL
+        for (int r = 0; r < NREG; ++r) fl[r] = fl[r] * sc;
+        fl[NREG] = 0.0;
+      }
+    }
+  }
+  SSB_UNROLL
+  for (int i = 0; i < NREG * NRB; ++i) O[i] = 0.0;
+#define OV(up, lo) O[(up) + NREG * (lo)]
+  if (!URBAN) {
+    const double f_upper = 1.0 - fu[0], f_lower = 1.0 - fl[0];
+    const double pair_cover = dmax(f_upper, f_lower);
+    OV(0, 0) = 1.0 - pair_cover;
+    if (NREG == 2) {
+      OV(0, 1) = pair_cover - f_upper;
+      OV(1, 0) = pair_cover - f_lower;
+      OV(1, 1) = f_upper + f_lower - pair_cover;
+    } else if (NREG == 3) {
+      OV(0, 1) = 0.5 * (pair_cover - f_upper);
+      OV(0, 2) = OV(0, 1);
+      OV(1, 0) = 0.5 * (pair_cover - f_lower);
+      OV(2, 0) = OV(1, 0);
+      OV(1, 1) = 0.5 * (f_upper + f_lower - pair_cover);
+      OV(2, 2) = OV(1, 1);
+    }
+  } else if (NREG == 1) {
+    OV(0, 0) = fl[0];
+    OV(0, 1) = fl[1];
+  } else if (NREG == 2) {
+    const double pair_cover = dmax(fu[1], fl[1]);
+    if (pair_cover <= fl[0] + fl[1]) {
+      OV(0, 2) = fl[2];
+      OV(0, 0) = fl[0] + fl[1] - pair_cover;
+      OV(0, 1) = pair_cover - fu[1];
+      OV(1, 0) = pair_cover - fl[1];
+      OV(1, 1) = fu[1] + fl[1] - pair_cover;
+    } else {
+      OV(1, 0) = fl[0];
+      OV(1, 1) = fl[1];
+      OV(1, 2) = fu[1] - fl[0] - fl[1];
+      OV(0, 2) = fu[0];
+    }
+  } else {
+    constexpr int r1 = NREG > 1 ? 1 : 0, r2 = NREG > 2 ? 2 : 0, rr = NRB - 1;  // (valid indices for every NREG)
+    const double pair_cover = dmax(fu[r1] + fu[r2], fl[r1] + fl[r2]);
+    if (pair_cover <= fl[0] + fl[r1] + fl[r2]) {
+      OV(0, rr) = fl[rr];
+      OV(0, 0) = fl[0] + fl[r1] + fl[r2] - pair_cover;
+      if (pair_cover > fu[r1] + fu[r2]) {
+        OV(r1, r1) = fu[r1];
+        OV(r2, r2) = fu[r2];
+        OV(0, r1) = fl[r1] - fu[r1];
+        OV(0, r2) = fl[r2] - fu[r2];
+      } else {
+        OV(r1, r1) = fl[r1];
+        OV(r2, r2) = fl[r2];
+        OV(r1, 0) = fu[r1] - fl[r1];
+        OV(r2, 0) = fu[r2] - fl[r2];
+      }
+    } else {
+      // overhang: vegetation above extends over the roof below
+      OV(r1, r1) = fl[r1];
+      OV(r2, r2) = fl[r2];
+      OV(r1, 0) = fl[0] * 0.5;
+      OV(r2, 0) = OV(0, r1);  // the reference assigns O(3,1) = O(1,2), zero here (radsurf_overlap.F90:268)
+      OV(r1, rr) = (fl[rr] - fu[0]) * 0.5;
+      OV(r2, rr) = OV(r1, rr);
+      OV(0, rr) = fu[0];
+    }
+  }
+  double rfl[NRB], rfu[NREG];
+  SSB_UNROLL
+  for (int lo = 0; lo < NRB; ++lo) rfl[lo] = (fl[lo] >= min_veg) ? 1.0 / fl[lo] : 0.0;
+  SSB_UNROLL
+  for (int up = 0; up < NREG; ++up) rfu[up] = (fu[up] >= min_veg) ? 1.0 / fu[up] : 0.0;
+  SSB_UNROLL
+  for (int up = 0; up < NREG; ++up) {
+    SSB_UNROLL
+    for (int lo = 0; lo < NRB; ++lo) {
+      U[up + NREG * lo] = OV(up, lo) * rfl[lo];
+      V[lo + NRB * up] = OV(up, lo) * rfu[up];
+    }
+  }
+#undef OV
+}
+
 // View factors of the single-layer urban models (radsurf_view_factor.F90).
 SSB_HD inline void view_factors(bool infinite_street, double h, bool with_sun, double cos_sza,
                                 double &view_ground_sky, double &view_wall_wall, double &view_dir_ground) {

@@ -18,6 +18,14 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
+#define SSB_UNROLL _Pragma("unroll")
+#define SSB_ROLLED _Pragma("unroll 1")  // keep a loop rolled: the code must fit the instruction cache
+#else
+#define SSB_UNROLL
+#define SSB_ROLLED
+#endif
+
+#if defined(__CUDACC__)
 #define SSB_HD __host__ __device__
 #define SSB_HDI __host__ __device__ __forceinline__
 #else

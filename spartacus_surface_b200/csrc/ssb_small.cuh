@@ -9,13 +9,6 @@
 #pragma once
 #include "ssb_math.cuh"
 
-#if defined(__CUDACC__)
-#define SSB_UNROLL _Pragma("unroll")
-#define SSB_ROLLED _Pragma("unroll 1")  // keep a loop rolled: the code must fit the instruction cache
-#else
-#define SSB_UNROLL
-#define SSB_ROLLED
-#endif
 
 namespace ssb {
 

@@ -70,8 +70,7 @@ SSB_HDI size_t scratch_doubles(size_t nelem, size_t nlev, size_t width) {
 // written before the layer kernels run (register-resident path): f_wall[3], od_scaling[3],
 // f_wall_dir_clear and the solved sub-block ("segment": 0 all regions, 1 clear region only,
 // 2 vegetated regions only), so that the sweeps evaluate no geometry and skip the
-// structural zeros of partially solved layers.  The interface area ends with the overlap
-// matrices U, V of the interface.
+// structural zeros of partially solved layers.
 constexpr int kGeoElems = 8;
 SSB_HDI int sw_layer_elems(int n, int d) { return 3 * n * n + 3 * n * d + 2 * d * d + kGeoElems; }
 SSB_HDI int lw_layer_elems(int n, int nreg) { return 3 * n * n + 2 * n + 3 * nreg + 1 + kGeoElems; }

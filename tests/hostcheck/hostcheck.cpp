@@ -36,8 +36,8 @@ struct HostBackend {
     const bool f = fast && a.cfg.ns == NS && NS <= 2;
     double stack[128];
     const ssb::StateMem st{stack, 1};
-    if (f)  // what k_partition_layers does on the device: geometry blocks and overlap matrices
-      for (long t = 0; t < nt + width; ++t) ssb::fast_prepare_level(a, (int)(t % width), (int)(t / width));
+    if (f)  // what k_partition_layers does on the device: geometry block of every layer
+      for (long t = 0; t < nt; ++t) ssb::fast_prepare_level(a, (int)(t % width), (int)(t / width));
     for (long t = 0; t < nt; ++t) {
       const int q = (int)(t % width), lev = (int)(t / width);
       if (f && a.cfg.nreg == 1)
@@ -56,8 +56,8 @@ struct HostBackend {
     const bool f = fast && a.cfg.ns == NS && NS <= 2;
     double stack[128];
     const ssb::StateMem st{stack, 1};
-    if (f)  // what k_partition_layers does on the device: geometry blocks and overlap matrices
-      for (long t = 0; t < nt + width; ++t) ssb::fast_prepare_level(a, (int)(t % width), (int)(t / width));
+    if (f)  // what k_partition_layers does on the device: geometry block of every layer
+      for (long t = 0; t < nt; ++t) ssb::fast_prepare_level(a, (int)(t % width), (int)(t / width));
     for (long t = 0; t < nt; ++t) {
       const int q = (int)(t % width), lev = (int)(t / width);
       if (f && a.cfg.nreg == 1)
