@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--generic", action="store_true", help="force the generic kernels")
     ap.add_argument("--minblocks", type=int, default=0, help="launch-bounds variant of the fast layer kernels")
     ap.add_argument("--minblocks-sweeps", type=int, default=0)
+    ap.add_argument("--sort-group", type=int, default=None, help="tuning: column ordering group (0 = whole chunk)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -247,6 +248,9 @@ def main():
         lib.ssb200_set_option(b"fast_kernels", 0)
     if args.minblocks:
         lib.ssb200_set_option(b"fast_minblocks", args.minblocks)
+    if args.sort_group is not None:
+        lib.ssb200_set_option(b"sort_columns", 0 if args.sort_group < 0 else 1)
+        lib.ssb200_set_option(b"sort_group", max(args.sort_group, 0))
     if args.minblocks_sweeps:
         lib.ssb200_set_option(b"fast_minblocks_sweeps", args.minblocks_sweeps)
 

@@ -34,6 +34,7 @@ struct Plan {
   std::vector<int> all_cols;  // concatenation uploaded to the device
   bool valid = false;
   long generation = 0;  // bumped on every rebuild (device copies are refreshed when it changes)
+  const int *host_cols(size_t offset) const { return all_cols.data() + offset; }
 };
 
 inline int stream_capacity(int ns) {
@@ -148,6 +149,7 @@ struct CallArgs {
 
 // Backend concept:
 //   const int *dev_cols(const Plan&, size_t offset)  device copy of plan.all_cols (+offset)
+//   const int *order_chunk(const ClassArgs&, const int *host_cols)   a.cols, possibly reordered
 //   const int *dev_nlay(), *dev_istartlay(), *dev_irep()
 //   double *scratch(size_t doubles)                  grow-only scratch
 //   size_t scratch_budget_doubles()
@@ -189,6 +191,9 @@ struct Dispatcher {
       a.ncols = (int)cnt;
       a.lmax = lmax;
       a.cols = be.dev_cols(plan, col_offset + pos);
+      // the backend may reorder the columns of the chunk (every problem is independent; scratch
+      // positions follow the order of a.cols, global arrays are addressed through it)
+      a.cols = be.order_chunk(a, plan.host_cols(col_offset + pos));
       const size_t width = cnt * (size_t)c.nspec;
       double *s = be.scratch(scratch_doubles(el, (size_t)lmax, width) + scratch_doubles(es, (size_t)lmax + 1, width));
       a.layer = s;

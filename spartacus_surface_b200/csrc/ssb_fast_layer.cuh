@@ -247,6 +247,29 @@ SSB_HD inline void fast_layer_problem_lw(const ClassArgs &a, int q, int lev, con
   fast_layer_problem_lw_impl<NREG, NS, -1>(a, q, lev, st);
 }
 
+// Sort key of a column for the register-resident kernels: bit l is set when layer l solves
+// only a sub-block of its regions (same rule as layer_geometry: radsurf_urban_sw.F90:512-583).
+// Columns with equal keys take the same code path layer by layer, so ordering the columns of
+// a launch by this key makes warps uniform: the segment kernels write, and the sweeps skip,
+// whole 32-byte sectors.  Night-time columns (shortwave) go last.
+SSB_HDI unsigned column_segment_key(const ClassArgs &a, int col) {
+  const SolveCfg &c = a.cfg;
+  if (!c.lw && !(a.cp.cos_sza[col] > 0.0)) return 0xffffffffu;
+  const bool veg_branching = c.urban ? (c.nreg > 1) : true;
+  if (!veg_branching) return 0u;
+  const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
+  const bool veg = c.nreg > 1 || !c.urban;
+  unsigned key = 0u;
+  for (int l = 0; l < nlay && l < 31; ++l) {
+    const double bf = c.urban ? a.cp.building_fraction[il1 + l] : 0.0;
+    const double vf = (veg && a.cp.veg_fraction) ? a.cp.veg_fraction[il1 + l] : 0.0;
+    double frac[3];
+    region_fractions(c, bf, vf, frac);
+    if (vf <= c.min_veg || frac[0] <= c.min_veg) key |= 1u << l;
+  }
+  return key;
+}
+
 // Per layer problem (q, level k) preparation for the register-resident kernels: writes the
 // geometry block of the layer scratch and returns the segment of the problem (which
 // sub-block of regions it solves), -1 when there is none.

@@ -19,6 +19,13 @@ struct HostBackend {
   bool fast = false;  // use the register-resident layer bodies where they exist (ns <= 2)
   size_t budget = (size_t)1 << 22;  // small on purpose: exercises the chunk loop
   const int *dev_cols(const ssb::Plan &p, size_t off) { return p.all_cols.data() + off; }
+  // reversed column order inside every chunk: results must not depend on it
+  std::vector<int> ordered;
+  const int *order_chunk(const ssb::ClassArgs &a, const int *host_cols) {
+    ordered.assign(host_cols, host_cols + a.ncols);
+    std::reverse(ordered.begin(), ordered.end());
+    return ordered.data();
+  }
   const int *dev_nlay() { return plan->nlay.data(); }
   const int *dev_istartlay() { return plan->istartlay.data(); }
   const int *dev_irep() { return plan->irep.data(); }

@@ -105,6 +105,11 @@ def test_pipeline_and_chunking_do_not_change_results():
         _same(base, _solve_host(cfg, cp, sw, lw))
     finally:
         lib.ssb200_set_option(b"pipeline", 1)
+    lib.ssb200_set_option(b"sort_columns", 1)  # columns in segment order instead of input order
+    try:
+        _same(base, _solve_host(cfg, cp, sw, lw))
+    finally:
+        lib.ssb200_set_option(b"sort_columns", 0)
     lib.ssb200_set_option(b"scratch_budget_bytes", 64 << 20)  # forces many chunks
     try:
         _same(base, _solve_host(cfg, cp, sw, lw))
