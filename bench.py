@@ -214,8 +214,6 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--generic", action="store_true", help="force the generic kernels")
-    ap.add_argument("--minblocks", type=int, default=0, help="launch-bounds variant of the fast layer kernels")
-    ap.add_argument("--minblocks-sweeps", type=int, default=0)
     ap.add_argument("--sort-group", type=int, default=None, help="tuning: column ordering group (0 = whole chunk)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -246,13 +244,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     if args.generic:
         lib.ssb200_set_option(b"fast_kernels", 0)
-    if args.minblocks:
-        lib.ssb200_set_option(b"fast_minblocks", args.minblocks)
     if args.sort_group is not None:
         lib.ssb200_set_option(b"sort_columns", 0 if args.sort_group < 0 else 1)
         lib.ssb200_set_option(b"sort_group", max(args.sort_group, 0))
-    if args.minblocks_sweeps:
-        lib.ssb200_set_option(b"fast_minblocks_sweeps", args.minblocks_sweeps)
 
     cfg = make_config(args.streams).consolidate()
     ncol = args.columns

@@ -230,7 +230,7 @@ int ssb200_last_kernel_counts(int64_t out[5]);
  * three overlapping stages; effective with pinned host memory), "pipeline_max_blocks"
  * (default 16), "sort_columns" (default 0; 1 = the register-resident kernels process the columns
  * of a launch ordered by their segment pattern inside groups of "sort_group" neighbours, so
- * that warps are uniform; results do not depend on it), "fast_minblocks_sweeps" (launch-bounds variant of the sweeps). */
+ * that warps are uniform; results do not depend on it). */
 int ssb200_set_option(const char *name, int64_t value);
 
 /* Release cached plans, scratch and pinned staging buffers. */

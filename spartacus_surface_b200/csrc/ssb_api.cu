@@ -177,7 +177,6 @@ struct Context {
   int sort_columns = 0;
   int sort_group = 512;  // ... inside groups of this many neighbouring columns
   int partition = 1;  // group layer problems by solved sub-block before the fast layer kernels
-  int fast_minblocks = 3, fast_minblocks_sweeps = 2;  // __launch_bounds__ min blocks of the fast kernels
 };
 Context g_ctx;
 
@@ -259,7 +258,7 @@ struct CudaBackend {
         b.perm_count = (int *)cx.d_perm[lane].p;
         b.perm = b.perm_count + 4;
       }
-      const bool done = ssb::fast_layer_sw<NS>(b, nt, cx.stream, cx.fast_minblocks);
+      const bool done = ssb::fast_layer_sw<NS>(b, nt, cx.stream);
       layer_was_fast = done;
       if (done && b.perm) g_launches += 4;
       if (done) check_launch();
@@ -277,7 +276,7 @@ struct CudaBackend {
         b.perm_count = (int *)cx.d_perm[lane].p;
         b.perm = b.perm_count + 4;
       }
-      const bool done = ssb::fast_layer_lw<NS>(b, nt, cx.stream, cx.fast_minblocks);
+      const bool done = ssb::fast_layer_lw<NS>(b, nt, cx.stream);
       layer_was_fast = done;
       if (done && b.perm) g_launches += 4;
       if (done) check_launch();
@@ -291,7 +290,7 @@ struct CudaBackend {
     // the register-resident sweeps read what the partition pass of the layer kernels prepared
     if (cx.fast_mode && (layer_was_fast || a.lmax == 0) && nt > 0 && cx.first_error == cudaSuccess) {
       tick(1, true);
-      const bool done = ssb::fast_sweeps_sw<NS>(a, nt, cx.stream, cx.fast_minblocks_sweeps);
+      const bool done = ssb::fast_sweeps_sw<NS>(a, nt, cx.stream);
       if (done) check_launch();
       tick(1, false);
       if (done) return;
@@ -302,7 +301,7 @@ struct CudaBackend {
   void sweeps_lw(const ssb::ClassArgs &a, long nt) {
     if (cx.fast_mode && (layer_was_fast || a.lmax == 0) && nt > 0 && cx.first_error == cudaSuccess) {
       tick(3, true);
-      const bool done = ssb::fast_sweeps_lw<NS>(a, nt, cx.stream, cx.fast_minblocks_sweeps);
+      const bool done = ssb::fast_sweeps_lw<NS>(a, nt, cx.stream);
       if (done) check_launch();
       tick(3, false);
       if (done) return;
@@ -828,14 +827,6 @@ int ssb200_set_option(const char *name, int64_t value) {
   }
   if (n == "partition_layers") {
     g_ctx.partition = value != 0;
-    return 0;
-  }
-  if (n == "fast_minblocks") {
-    g_ctx.fast_minblocks = (int)value;
-    return 0;
-  }
-  if (n == "fast_minblocks_sweeps") {
-    g_ctx.fast_minblocks_sweeps = (int)value;
     return 0;
   }
   return fail(SSB200_ERR_ARG, "unknown option " + n);

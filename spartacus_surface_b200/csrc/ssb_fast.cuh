@@ -9,27 +9,27 @@
 
 namespace ssb {
 template <int NS>
-inline bool fast_layer_sw(const ClassArgs &, long, cudaStream_t, int) {
+inline bool fast_layer_sw(const ClassArgs &, long, cudaStream_t) {
   return false;
 }
 template <int NS>
-inline bool fast_layer_lw(const ClassArgs &, long, cudaStream_t, int) {
+inline bool fast_layer_lw(const ClassArgs &, long, cudaStream_t) {
   return false;
 }
 template <int NS>
-inline bool fast_sweeps_sw(const ClassArgs &, long, cudaStream_t, int) {
+inline bool fast_sweeps_sw(const ClassArgs &, long, cudaStream_t) {
   return false;
 }
 template <int NS>
-inline bool fast_sweeps_lw(const ClassArgs &, long, cudaStream_t, int) {
+inline bool fast_sweeps_lw(const ClassArgs &, long, cudaStream_t) {
   return false;
 }
-template <> bool fast_sweeps_sw<1>(const ClassArgs &, long, cudaStream_t, int);
-template <> bool fast_sweeps_sw<2>(const ClassArgs &, long, cudaStream_t, int);
-template <> bool fast_sweeps_lw<1>(const ClassArgs &, long, cudaStream_t, int);
-template <> bool fast_sweeps_lw<2>(const ClassArgs &, long, cudaStream_t, int);
-template <> bool fast_layer_sw<1>(const ClassArgs &, long, cudaStream_t, int);
-template <> bool fast_layer_sw<2>(const ClassArgs &, long, cudaStream_t, int);
-template <> bool fast_layer_lw<1>(const ClassArgs &, long, cudaStream_t, int);
-template <> bool fast_layer_lw<2>(const ClassArgs &, long, cudaStream_t, int);
+template <> bool fast_sweeps_sw<1>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_sweeps_sw<2>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_sweeps_lw<1>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_sweeps_lw<2>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_layer_sw<1>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_layer_sw<2>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_layer_lw<1>(const ClassArgs &, long, cudaStream_t);
+template <> bool fast_layer_lw<2>(const ClassArgs &, long, cudaStream_t);
 }  // namespace ssb

@@ -74,7 +74,7 @@ static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st) {
   if (NREG > 1) launch_fast_layer_sw_seg<NREG, NS, 2>(a, nt, grid, st);
 }
 template <>
-bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int) {
+bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
   if (a.cfg.ns != SSB_NS || a.perm == nullptr) return false;
   switch (a.cfg.nreg) {
     case 1: launch_fast_layer_sw<1, SSB_NS>(a, nt, st); return true;
@@ -83,39 +83,33 @@ bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int) {
     default: return false;
   }
 }
-template <int NREG, int NS, bool URBAN, int MINB>
-__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_sweeps_sw(ClassArgs a, long nt) {
+template <int NREG, int NS, bool URBAN>
+__global__ void __launch_bounds__(kFastBlock, 2) k_fast_sweeps_sw(ClassArgs a, long nt) {
   extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
   const StateMem st{ssb_state + threadIdx.x, kFastBlock};
   fast_column_sweeps_sw<NREG, NS, URBAN>(a, (int)t, st);
 }
+// (3 or 4 blocks per SM at 168 / 128 registers were measured: the spills cost more than the
+// extra warps hide)
 template <int NREG, int NS, bool URBAN>
-static void launch_fast_sweeps_sw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
+static void launch_fast_sweeps_sw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
   const size_t smem = sizeof(double) * SwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
-  if (minb >= 4) {
-    cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fast_sweeps_sw<NREG, NS, URBAN, 4><<<grid, kFastBlock, smem, st>>>(a, nt);
-  } else if (minb == 3) {
-    cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fast_sweeps_sw<NREG, NS, URBAN, 3><<<grid, kFastBlock, smem, st>>>(a, nt);
-  } else {
-    cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fast_sweeps_sw<NREG, NS, URBAN, 2><<<grid, kFastBlock, smem, st>>>(a, nt);
-  }
+  cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fast_sweeps_sw<NREG, NS, URBAN><<<grid, kFastBlock, smem, st>>>(a, nt);
 }
 template <>
-bool fast_sweeps_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
+bool fast_sweeps_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
   if (a.cfg.ns != SSB_NS) return false;
   switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
-    case 2: launch_fast_sweeps_sw<1, SSB_NS, false>(a, nt, st, minb); return true;
-    case 3: launch_fast_sweeps_sw<1, SSB_NS, true>(a, nt, st, minb); return true;
-    case 4: launch_fast_sweeps_sw<2, SSB_NS, false>(a, nt, st, minb); return true;
-    case 5: launch_fast_sweeps_sw<2, SSB_NS, true>(a, nt, st, minb); return true;
-    case 6: launch_fast_sweeps_sw<3, SSB_NS, false>(a, nt, st, minb); return true;
-    case 7: launch_fast_sweeps_sw<3, SSB_NS, true>(a, nt, st, minb); return true;
+    case 2: launch_fast_sweeps_sw<1, SSB_NS, false>(a, nt, st); return true;
+    case 3: launch_fast_sweeps_sw<1, SSB_NS, true>(a, nt, st); return true;
+    case 4: launch_fast_sweeps_sw<2, SSB_NS, false>(a, nt, st); return true;
+    case 5: launch_fast_sweeps_sw<2, SSB_NS, true>(a, nt, st); return true;
+    case 6: launch_fast_sweeps_sw<3, SSB_NS, false>(a, nt, st); return true;
+    case 7: launch_fast_sweeps_sw<3, SSB_NS, true>(a, nt, st); return true;
     default: return false;
   }
 }
@@ -149,7 +143,7 @@ static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st) {
   if (NREG > 1) launch_fast_layer_lw_seg<NREG, NS, 2>(a, nt, grid, st);
 }
 template <>
-bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int) {
+bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
   if (a.cfg.ns != SSB_NS || a.perm == nullptr) return false;
   switch (a.cfg.nreg) {
     case 1: launch_fast_layer_lw<1, SSB_NS>(a, nt, st); return true;
@@ -158,39 +152,33 @@ bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int) {
     default: return false;
   }
 }
-template <int NREG, int NS, bool URBAN, int MINB>
-__global__ void __launch_bounds__(kFastBlock, MINB) k_fast_sweeps_lw(ClassArgs a, long nt) {
+template <int NREG, int NS, bool URBAN>
+__global__ void __launch_bounds__(kFastBlock, 2) k_fast_sweeps_lw(ClassArgs a, long nt) {
   extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
   const StateMem st{ssb_state + threadIdx.x, kFastBlock};
   fast_column_sweeps_lw<NREG, NS, URBAN>(a, (int)t, st);
 }
+// (3 or 4 blocks per SM at 168 / 128 registers were measured: the spills cost more than the
+// extra warps hide)
 template <int NREG, int NS, bool URBAN>
-static void launch_fast_sweeps_lw(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
+static void launch_fast_sweeps_lw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
   const size_t smem = sizeof(double) * LwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
-  if (minb >= 4) {
-    cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fast_sweeps_lw<NREG, NS, URBAN, 4><<<grid, kFastBlock, smem, st>>>(a, nt);
-  } else if (minb == 3) {
-    cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fast_sweeps_lw<NREG, NS, URBAN, 3><<<grid, kFastBlock, smem, st>>>(a, nt);
-  } else {
-    cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fast_sweeps_lw<NREG, NS, URBAN, 2><<<grid, kFastBlock, smem, st>>>(a, nt);
-  }
+  cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fast_sweeps_lw<NREG, NS, URBAN><<<grid, kFastBlock, smem, st>>>(a, nt);
 }
 template <>
-bool fast_sweeps_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st, int minb) {
+bool fast_sweeps_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
   if (a.cfg.ns != SSB_NS) return false;
   switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
-    case 2: launch_fast_sweeps_lw<1, SSB_NS, false>(a, nt, st, minb); return true;
-    case 3: launch_fast_sweeps_lw<1, SSB_NS, true>(a, nt, st, minb); return true;
-    case 4: launch_fast_sweeps_lw<2, SSB_NS, false>(a, nt, st, minb); return true;
-    case 5: launch_fast_sweeps_lw<2, SSB_NS, true>(a, nt, st, minb); return true;
-    case 6: launch_fast_sweeps_lw<3, SSB_NS, false>(a, nt, st, minb); return true;
-    case 7: launch_fast_sweeps_lw<3, SSB_NS, true>(a, nt, st, minb); return true;
+    case 2: launch_fast_sweeps_lw<1, SSB_NS, false>(a, nt, st); return true;
+    case 3: launch_fast_sweeps_lw<1, SSB_NS, true>(a, nt, st); return true;
+    case 4: launch_fast_sweeps_lw<2, SSB_NS, false>(a, nt, st); return true;
+    case 5: launch_fast_sweeps_lw<2, SSB_NS, true>(a, nt, st); return true;
+    case 6: launch_fast_sweeps_lw<3, SSB_NS, false>(a, nt, st); return true;
+    case 7: launch_fast_sweeps_lw<3, SSB_NS, true>(a, nt, st); return true;
     default: return false;
   }
 }
