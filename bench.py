@@ -62,8 +62,8 @@ ALGO_BYTES_PER_COL_LAYER = 540.0
 def sweep_bytes(ns, f_full, f_clear, f_veg):
     """Bytes a sweep kernel must move per (column, layer) given the layer / sweep kernel split (nreg = 3,
     urban): the layer matrices of the solved sub-block once in the upward and once in the fused downward
-    sweep, interface state (a_above, d_above / source_above, LU factors) written and read once, overlap
-    matrices and geometry block read in both sweeps, flux outputs."""
+    sweep, interface state (a_above, d_above / source_above, LU factors) written and read once, geometry
+    block, flux outputs and per-layer inputs."""
     def one(nr):
         n, d = nr * ns, nr
         sw_up = 2 * n * n + 2 * n * d + d * d                # R, T, S_dn, S_up, E
@@ -73,7 +73,7 @@ def sweep_bytes(ns, f_full, f_clear, f_veg):
         return sw_up + sw_dn, lw_up + lw_dn
     n, d = 3 * ns, 3
     sw_if, lw_if = 2 * n * n + n * d, 2 * n * n + n         # per interface, written once and read once
-    uvg = 2 * (24 + 8)                                       # U, V and the geometry block, both sweeps
+    uvg = 1 + 8                                              # segment (upward), geometry block (downward)
     sw = lw = 0.0
     for f, nr in ((f_full, 3), (f_clear, 1), (f_veg, 2)):
         a, b = one(nr)
@@ -372,8 +372,8 @@ def main():
             roofline = {"bound": "hbm", "kernel": dom, "achieved": e["gbs"], "peak": hbm_peak, "unit": "GB/s",
                         "frac": e["hbm_frac"], "traffic": e["traffic"],
                         "bytes_note": "algorithmic bytes: layer matrices of the solved sub-block read in the upward and "
-                                      "in the fused downward sweep, interface state written and read once, overlap "
-                                      "matrices and geometry block, flux outputs (DESIGN.md section 4.3)"}
+                                      "in the fused downward sweep, interface state written and read once, "
+                                      "geometry block, flux outputs (DESIGN.md section 4.3)"}
         roofline.update({"avg_launch_ms": e["avg_launch_ms"], "launches_per_step": e["launches_per_step"],
                          "segment_mix": {"all_regions": f_full, "clear_only": f_clear, "vegetated_only": f_veg},
                          "fp64_peak_source": "measured in this run: register-resident independent DFMA chains on "
