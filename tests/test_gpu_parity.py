@@ -51,3 +51,45 @@ def test_golden_case(case, fast):
     ok2, _, lines2 = parity.check(masked, stored, {n: {k: stored[n][k] + (orb[n][k] - ora[n][k]) for k in f}
                                                     for n, f in stored.items()})
     assert ok2, "\n".join(lines2)
+
+
+@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("streams", [1, 2])
+def test_mixed_edge_case(streams, fast):
+    """Ragged layers, flat / forest / urban / vegetated-urban tiles in one call, night-time
+    columns, several spectral intervals, direct ground albedo (tests/mixed_case.py)."""
+    from mixed_case import mixed_config, make_mixed
+    from spartacus_surface_b200 import canopy_flux_type, boundary_conds_out_type
+    from spartacus_surface_b200.radsurf_canopy_flux import ALL_FIELDS
+    lib = load()
+    lib.ssb200_set_option(b"fast_kernels", fast)
+    cfg = mixed_config(streams).consolidate()
+    cp, sw, lw = make_mixed(cfg, ncol=1500)
+
+    def run(solver):
+        bc = boundary_conds_out_type().allocate(cp.ncol, cfg.nsw, cfg.nlw)
+        fl = [canopy_flux_type().allocate(cfg, cp.ncol, cp.ntotlay, n, use_direct=d)
+              for n, d in ((cfg.nsw, True), (cfg.nsw, True), (cfg.nlw, False), (cfg.nlw, False))]
+        for f in fl:
+            f.fill(POISON)
+        assert solver(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+        out = {n: {k: getattr(f, k) for k in ALL_FIELDS if getattr(f, k) is not None}
+               for n, f in zip(("sw_norm_dir", "sw_norm_diff", "lw_internal", "lw_norm"), fl)}
+        out["bc"] = {k: getattr(bc, k) for k in golden_io.BC_FIELDS}
+        return out
+
+    try:
+        got = run(radsurf)
+    finally:
+        lib.ssb200_set_option(b"fast_kernels", 1)
+    ora, orb = run(oracle_lib.make_solver()), run(oracle_lib.make_solver(nofma=True))
+    ok, worst, lines = parity.check(got, ora, orb)
+    print(f"mixed case, {streams} streams, fast={fast}: max err/bound = {worst:.3e}")
+    assert ok, "\n".join(lines)
+    # night-time canopy columns: every shortwave member is zero (radsurf_interface.F90:193-196);
+    # nothing the oracle writes is left at the poison value and vice versa
+    night = ~(cp.cos_sza > 0.0) & (cp.i_representation != 0)
+    assert night.any() and np.all(got["sw_norm_dir"]["top_net"][night] == 0.0)
+    for n in ("sw_norm_dir", "sw_norm_diff", "lw_internal", "lw_norm"):
+        for k, v in got[n].items():
+            assert np.array_equal(v == POISON, ora[n][k] == POISON), (n, k)

@@ -80,3 +80,32 @@ def test_fast_layer_math_within_sensitivity(case):
     _, orb = _run(case, oracle_lib.make_solver(nofma=True))
     ok, worst, lines = parity.check(got, ora, orb)
     assert ok, "\n".join(lines)
+
+
+@pytest.mark.parametrize("streams", [1, 2])
+def test_mixed_edge_case_fast_path(streams):
+    """Ragged layers, all tile types, night columns, several spectral intervals through the
+    register-resident bodies (host build) against the oracle."""
+    import parity
+    from mixed_case import mixed_config, make_mixed
+    from spartacus_surface_b200 import canopy_flux_type, boundary_conds_out_type
+    from spartacus_surface_b200.radsurf_canopy_flux import ALL_FIELDS
+    cfg = mixed_config(streams).consolidate(LG)
+    cp, sw, lw = make_mixed(cfg)
+
+    def run(solver):
+        bc = boundary_conds_out_type().allocate(cp.ncol, cfg.nsw, cfg.nlw)
+        fl = [canopy_flux_type().allocate(cfg, cp.ncol, cp.ntotlay, n, use_direct=d)
+              for n, d in ((cfg.nsw, True), (cfg.nsw, True), (cfg.nlw, False), (cfg.nlw, False))]
+        for f in fl:
+            f.fill(7.0)
+        assert solver(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+        out = {n: {k: getattr(f, k) for k in ALL_FIELDS if getattr(f, k) is not None}
+               for n, f in zip(("sw_norm_dir", "sw_norm_diff", "lw_internal", "lw_norm"), fl)}
+        out["bc"] = {k: getattr(bc, k) for k in golden_io.BC_FIELDS}
+        return out
+
+    ora, orb = run(oracle_lib.make_solver()), run(oracle_lib.make_solver(nofma=True))
+    _identical(run(hostcheck_lib.make_solver()), orb)
+    ok, worst, lines = parity.check(run(hostcheck_lib.make_solver(fast=True)), ora, orb)
+    assert ok, "\n".join(lines)
