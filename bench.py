@@ -141,6 +141,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """Host cores this process may use (torchrun sets OMP_NUM_THREADS=1: ask the scheduler instead)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle (C++ restatement of the Fortran solver; the Fortran itself cannot be
     built: no Fortran compiler in the image) on all host threads, bounded sample per step."""
@@ -153,8 +161,8 @@ def run_reference(args, rank, world):
     ncol = args.cpu_columns
     cp, sw, lw = make_synthetic(cfg, ncol, NLAY)
     bc, fl = allocate_outputs(cfg, ncol, cp.ntotlay)
-    solver = oracle_lib.make_solver(nthreads=0, nblocksize=16)
-    threads = oracle_lib.load().oracle_num_threads()
+    threads = host_threads()
+    solver = oracle_lib.make_solver(nthreads=threads, nblocksize=16)
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -443,13 +451,14 @@ def main():
             # the CPU sample uses the very arrays the GPU solved (first nc columns, copied from HBM)
             ccp, csw, clw = head_to_host(cp, nc, ncol), head_to_host(sw, nc, ncol), head_to_host(lw, nc, ncol)
             cbc, cfl = allocate_outputs(cfg, nc, ccp.ntotlay)
-            solver = oracle_lib.make_solver()
+            cpu_threads = host_threads()
+            solver = oracle_lib.make_solver(nthreads=cpu_threads)
             solver(cfg, ccp, csw, clw, cbc, None, 256, *cfl)  # touch pages / warm caches
             t0 = time.perf_counter()
             rc = solver(cfg, ccp, csw, clw, cbc, None, None, *cfl)
             dt = time.perf_counter() - t0
             assert rc == 0
-            cpu = {"value": nc * NLAY * 2 / dt, "unit": UNIT, "cores": oracle_lib.load().oracle_num_threads(),
+            cpu = {"value": nc * NLAY * 2 / dt, "unit": UNIT, "cores": cpu_threads,
                    "kind": "port",
                    "sample": f"first {nc} of the {ncol} columns, one pass, OpenMP dynamic blocks of 16 columns "
                              f"({dt:.1f} s); C++ restatement of the reference (no Fortran compiler in the image)"}
@@ -465,7 +474,7 @@ def main():
             outs = []
             for nofma in (False, True):
                 sbc, sfl = allocate_outputs(cfg, ns_, scp.ntotlay)
-                oracle_lib.make_solver(nofma=nofma)(cfg, scp, ssw, slw, sbc, None, None, *sfl)
+                oracle_lib.make_solver(nthreads=cpu_threads, nofma=nofma)(cfg, scp, ssw, slw, sbc, None, None, *sfl)
                 outs.append({n: {k: getattr(f, k) for k in ALL_FIELDS if getattr(f, k) is not None}
                              for n, f in zip(names, sfl)})
             gsub = {n: {k: v[:ns_ * (NLAY if v.shape[0] != nc else 1)] for k, v in f.items()} for n, f in got.items()}
