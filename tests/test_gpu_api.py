@@ -198,3 +198,43 @@ def test_error_codes():
     with pytest.raises(RadsurfError, match="spectral resolution"):
         radsurf(bad, cp, sw, lw, bc, None, None, *fl)
     assert lib.ssb200_measure_fp64_peak_tflops(1 << 12) > 1.0
+
+
+def test_full_size_properties():
+    """BASELINE size (1,048,576 columns x 16 layers, device-resident): shortwave energy is
+    conserved column by column, nothing is non-finite, and a column's result does not depend
+    on the columns solved with it (a window of the full solve equals the same columns solved
+    alone, bit for bit)."""
+    import torch
+    lib = load()
+    cfg = _cfg()
+    ncol, nlay = 1 << 20, 16
+    cp, sw, lw = make_synthetic(cfg, ncol, nlay, device="cuda:0")
+    bc, fl = _outputs(cfg, ncol, cp.ntotlay, device="cuda:0", profile=False)
+    assert radsurf(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+    torch.cuda.synchronize()
+    for name, f in zip(("sw_norm_dir", "sw_norm_diff", "lw_internal", "lw_norm"), fl):
+        for k in ALL_FIELDS:
+            a = getattr(f, k)
+            if a is not None:
+                assert bool(torch.isfinite(a).all()), (name, k)
+    for f in fl[:2]:
+        res = torch.zeros(ncol, dtype=torch.float64, device="cuda:0")
+        s, c = f.as_struct(), cp.as_struct()
+        assert lib.ssb200_canopy_flux_check_device(C.byref(s), C.byref(c), C.c_void_p(res.data_ptr()), None) == 0
+        torch.cuda.synchronize()
+        assert float((res.abs() / f.top_dn[:, 0].abs().clamp_min(1e-30)).max()) < 1e-12
+    # the same columns alone: generated with their global column offset, solved as a 4096-column call
+    off, n = 777_216, 4096
+    cp2, sw2, lw2 = make_synthetic(cfg, n, nlay, col_offset=off, device="cuda:0")
+    bc2, fl2 = _outputs(cfg, n, cp2.ntotlay, device="cuda:0", profile=False)
+    assert radsurf(cfg, cp2, sw2, lw2, bc2, None, None, *fl2) == 0
+    torch.cuda.synchronize()
+    for f, g in zip(fl, fl2):
+        for k in ALL_FIELDS:
+            a, b = getattr(f, k), getattr(g, k)
+            if a is None:
+                continue
+            rows = slice(off, off + n) if a.shape[0] == ncol else slice(off * nlay, (off + n) * nlay)
+            assert torch.equal(a[rows], b), k
+    lib.ssb200_release()
