@@ -251,6 +251,21 @@ int ssb200_canopy_flux_check_device(const ssb200_canopy_flux *flux,
                                     const ssb200_canopy_properties *canopy_props,
                                     double *residual, void *stream);
 
+/* "Next" row f2: the input stage in front of the path on device -
+ * calc_simple_spectrum_lw (radsurf/radsurf_simple_spectrum.F90:41-66) and, with the
+ * air / vegetation temperatures NULL, lw_spectral_properties_type%calc_monochromatic_emission
+ * (radsurf/radsurf_lw_spectral_properties.F90:161-199): broadband sigma T^4 emission and
+ * Planck arrays from temperatures and emissivities (interval 1 of (nspec, .) arrays), so that
+ * only the temperatures have to cross PCIe.  Device pointers; a NULL temperature skips the
+ * members it feeds.  Columns istartcol..iendcol (1-based, 0 = all) and the packed layers
+ * ilay1..ilay2 (1-based, as computed by the reference from istartlay/nlay; ilay2 < ilay1 = none). */
+int ssb200_calc_simple_spectrum_lw_device(ssb200_lw_spectral_properties *lw, int32_t ncol, int32_t ntotlay,
+                                          int32_t istartcol, int32_t iendcol, int32_t ilay1, int32_t ilay2,
+                                          const double *ground_temperature, const double *roof_temperature,
+                                          const double *wall_temperature, const double *clear_air_temperature,
+                                          const double *veg_temperature, const double *veg_air_temperature,
+                                          void *stream);
+
 /* FP64 FMA peak micro-benchmark used as roofline denominator by bench.py:
  * returns measured TFLOP/s (2 flop per DFMA) on the current device, <0 on
  * error. */

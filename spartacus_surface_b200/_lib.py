@@ -47,6 +47,8 @@ def _declare(lib):
                                                   P(_abi.CanopyFlux), C.c_void_p]
     lib.ssb200_canopy_flux_check_device.argtypes = [P(_abi.CanopyFlux), P(_abi.CanopyProperties),
                                                     C.c_void_p, C.c_void_p]
+    lib.ssb200_calc_simple_spectrum_lw_device.argtypes = ([P(_abi.LwSpectralProperties)] + [C.c_int32] * 6
+                                                          + [C.c_void_p] * 7)
     lib.ssb200_measure_fp64_peak_tflops.argtypes = [C.c_int]
     lib.ssb200_measure_fp64_peak_tflops.restype = C.c_double
     return lib

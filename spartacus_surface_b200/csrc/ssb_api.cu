@@ -110,6 +110,16 @@ __global__ void k_check(ssb200_canopy_flux f, const int *nlay, const int *istart
   residual[col] = ground_net + clear + wall + roof + veg + vegair - top_net;
 }
 
+// sigma * emissivity * T^4 (emissivity NULL: 1) for elements [i0, i1) of (nspec, .) arrays, interval 1
+__global__ void k_sigma_t4(double *out, const double *emissivity, const double *temperature, int nspec, long i0,
+                           long i1) {
+  const long i = i0 + blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= i1) return;
+  const double t = temperature[i], t2 = t * t;
+  const double sb = 5.67037321e-8;  // radtool/radiation_constants.F90:26
+  out[(size_t)nspec * i] = emissivity ? (sb * emissivity[(size_t)nspec * i]) * (t2 * t2) : sb * (t2 * t2);
+}
+
 // register-resident independent DFMA chains: FP64 roofline denominator
 __global__ void k_fp64_peak(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
@@ -968,6 +978,39 @@ int ssb200_canopy_flux_check_device(const ssb200_canopy_flux *flux, const ssb200
     ++g_launches;
     SSB_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+int ssb200_calc_simple_spectrum_lw_device(ssb200_lw_spectral_properties *lw, int32_t ncol, int32_t ntotlay,
+                                          int32_t istartcol, int32_t iendcol, int32_t ilay1, int32_t ilay2,
+                                          const double *ground_temperature, const double *roof_temperature,
+                                          const double *wall_temperature, const double *clear_air_temperature,
+                                          const double *veg_temperature, const double *veg_air_temperature,
+                                          void *stream) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  if (!lw) return fail(SSB200_ERR_ARG, "NULL argument");
+  if (lw->nspec > 1 && (clear_air_temperature || veg_temperature || veg_air_temperature))
+    return fail(SSB200_ERR_ARG, "Simple longwave spectrum only possible with one input spectral interval");
+  const long c0 = (istartcol > 0 ? istartcol : 1) - 1, c1 = iendcol > 0 ? (iendcol < ncol ? iendcol : ncol) : ncol;
+  const long l0 = (ilay1 > 0 ? ilay1 : 1) - 1, l1 = ilay2 < ntotlay ? ilay2 : ntotlay;
+  cudaStream_t st = (cudaStream_t)stream;
+  // (the members are inputs of radsurf, hence const in the struct; this stage fills them)
+  auto run = [&](const double *out_c, const double *emis, const double *temp, long i0, long i1, bool need_emis) -> int {
+    double *out = const_cast<double *>(out_c);
+    if (!temp || i1 <= i0) return 0;
+    if (!out || (need_emis && !emis)) return fail(SSB200_ERR_ARG, "temperature given but emission / emissivity array missing");
+    k_sigma_t4<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, st>>>(out, emis, temp, lw->nspec, i0, i1);
+    ++g_launches;
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+  };
+  if ((rc = run(lw->ground_emission, lw->ground_emissivity, ground_temperature, c0, c1, true))) return rc;
+  if ((rc = run(lw->roof_emission, lw->roof_emissivity, roof_temperature, l0, l1, true))) return rc;
+  if ((rc = run(lw->wall_emission, lw->wall_emissivity, wall_temperature, l0, l1, true))) return rc;
+  if ((rc = run(lw->clear_air_planck, nullptr, clear_air_temperature, l0, l1, false))) return rc;
+  if ((rc = run(lw->veg_planck, nullptr, veg_temperature, l0, l1, false))) return rc;
+  if ((rc = run(lw->veg_air_planck, nullptr, veg_air_temperature, l0, l1, false))) return rc;
   return 0;
 }
 

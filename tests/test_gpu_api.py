@@ -238,3 +238,29 @@ def test_full_size_properties():
             rows = slice(off, off + n) if a.shape[0] == ncol else slice(off * nlay, (off + n) * nlay)
             assert torch.equal(a[rows], b), k
     lib.ssb200_release()
+
+
+def test_simple_spectrum_lw_on_device():
+    """calc_simple_spectrum_lw through the device entry equals the host (numpy) version."""
+    import copy
+    import torch
+    from spartacus_surface_b200.radsurf_simple_spectrum import calc_simple_spectrum_lw
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, 500, NLAY)
+    rng = np.random.default_rng(3)
+    cp.ground_temperature = rng.uniform(260, 310, cp.ncol)
+    for k in ("roof_temperature", "wall_temperature", "clear_air_temperature", "veg_temperature",
+              "veg_air_temperature"):
+        setattr(cp, k, rng.uniform(260, 310, cp.ntotlay))
+    fields = ("ground_emission", "roof_emission", "wall_emission", "clear_air_planck", "veg_planck", "veg_air_planck")
+    dcp, dlw = _to_device(cp), _to_device(lw)
+    for k in fields:
+        getattr(lw, k)[...] = -1.0
+        getattr(dlw, k).fill_(-1.0)
+    calc_simple_spectrum_lw(cfg, cp, lw, 11, 420)
+    calc_simple_spectrum_lw(cfg, dcp, dlw, 11, 420)
+    torch.cuda.synchronize()
+    for k in fields:
+        h, d = getattr(lw, k), getattr(dlw, k).cpu().numpy()
+        assert np.array_equal(h == -1.0, d == -1.0), k          # same range written
+        assert np.allclose(h, d, rtol=1e-15, atol=0), k         # ** 4 (pow) against (t*t)*(t*t)
