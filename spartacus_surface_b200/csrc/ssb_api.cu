@@ -270,7 +270,7 @@ struct CudaBackend {
       }
       const bool done = ssb::fast_layer_sw<NS>(b, nt, cx.stream);
       layer_was_fast = done;
-      if (done && b.perm) g_launches += 4;
+      if (done && b.perm) g_launches += 3;
       if (done) check_launch();
       tick(0, false);
       if (done) return;
@@ -288,7 +288,7 @@ struct CudaBackend {
       }
       const bool done = ssb::fast_layer_lw<NS>(b, nt, cx.stream);
       layer_was_fast = done;
-      if (done && b.perm) g_launches += 4;
+      if (done && b.perm) g_launches += 3;
       if (done) check_launch();
       tick(2, false);
       if (done) return;

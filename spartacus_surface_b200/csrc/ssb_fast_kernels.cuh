@@ -21,21 +21,35 @@ constexpr int kFastBlock = 128;  // sweeps: one thread per (column, interval)
 constexpr int kLayerBlock = SSB_LAYER_BLOCK;
 constexpr int kLayerMinB = SSB_LAYER_THREADS / SSB_LAYER_BLOCK;
 
-// Groups the layer problems of a launch by the sub-block of regions they solve, so
-// that every warp of the layer kernels runs one code path.  Warp-aggregated
-// append: the order inside a segment is not deterministic, the results are
-// (every problem is independent).
-// The same pass writes the geometry block of every layer (fast_prepare_level).
-static __global__ void k_partition_layers(ClassArgs a, long nt) {
+// First pass over the layer problems of a launch (one thread each): evaluates the layer
+// geometry once and writes the geometry block (fast_prepare_level); solves the problems of
+// layers without vegetation on the spot (clear region only: order NS, a few hundred flops,
+// not worth a launch and a second pass over their inputs); groups the other problems by the
+// sub-block of regions they solve, so that every warp of the layer kernels runs one code
+// path.  Warp-aggregated append: the order inside a segment is not deterministic, the results
+// are (every problem is independent).
+constexpr int kPartitionBlock = 256;
+template <int NREG, int NS, bool LW>
+static __global__ void __launch_bounds__(kPartitionBlock) k_partition_layers(ClassArgs a, long nt) {
+  extern __shared__ double ssb_stack[];
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   int seg = -1;
   if (t < nt) {
     const long width = (long)a.ncols * a.cfg.nspec;
-    seg = fast_prepare_level(a, (int)(t % width), (int)(t / width));
+    const int q = (int)(t % width), lev = (int)(t / width);
+    seg = fast_prepare_level(a, q, lev);
+    if (NREG > 1 && seg == 1) {
+      const StateMem st{ssb_stack + threadIdx.x, kPartitionBlock};
+      if (LW)
+        fast_layer_problem_lw_impl<NREG, NS, 1>(a, q, lev, st);
+      else
+        fast_layer_problem_sw_seg<NREG, NS, 1>(a, q, lev, st);
+      seg = -1;
+    }
   }
   const unsigned lane = threadIdx.x & 31u;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 3; k += 2) {
     const unsigned mask = __ballot_sync(0xffffffffu, seg == k);
     if (mask == 0u) continue;
     int base = 0;
@@ -44,6 +58,13 @@ static __global__ void k_partition_layers(ClassArgs a, long nt) {
     base = __shfl_sync(0xffffffffu, base, leader);
     if (seg == k) a.perm[(size_t)k * (size_t)nt + base + __popc(mask & ((1u << lane) - 1u))] = (int)t;
   }
+}
+template <int NREG, int NS, bool LW>
+static void launch_partition_layers(const ClassArgs &a, long nt, cudaStream_t st) {
+  const size_t smem = sizeof(double) * kPartitionBlock *
+                      (LW ? LayerStack<1, NS>::lw_doubles : LayerStack<1, NS>::sw_doubles);
+  cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
+  k_partition_layers<NREG, NS, LW><<<(unsigned)((nt + kPartitionBlock - 1) / kPartitionBlock), kPartitionBlock, smem, st>>>(a, nt);
 }
 
 #ifdef SSB_KIND_SW
@@ -67,10 +88,8 @@ static void launch_fast_layer_sw_seg(const ClassArgs &a, long nt, unsigned grid,
 template <int NREG, int NS>
 static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kLayerBlock - 1) / kLayerBlock);
-  cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
-  k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt);
+  launch_partition_layers<NREG, NS, false>(a, nt, st);
   launch_fast_layer_sw_seg<NREG, NS, 0>(a, nt, grid, st);
-  if (NREG > 1) launch_fast_layer_sw_seg<NREG, NS, 1>(a, nt, grid, st);
   if (NREG > 1) launch_fast_layer_sw_seg<NREG, NS, 2>(a, nt, grid, st);
 }
 template <>
@@ -136,10 +155,8 @@ static void launch_fast_layer_lw_seg(const ClassArgs &a, long nt, unsigned grid,
 template <int NREG, int NS>
 static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kLayerBlock - 1) / kLayerBlock);
-  cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
-  k_partition_layers<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a, nt);
+  launch_partition_layers<NREG, NS, true>(a, nt, st);
   launch_fast_layer_lw_seg<NREG, NS, 0>(a, nt, grid, st);
-  if (NREG > 1) launch_fast_layer_lw_seg<NREG, NS, 1>(a, nt, grid, st);
   if (NREG > 1) launch_fast_layer_lw_seg<NREG, NS, 2>(a, nt, grid, st);
 }
 template <>

@@ -68,6 +68,30 @@ SSB_HDI void load_geometry_inputs(const ClassArgs &a, int il, double &bf, double
   vfsd = (c.nreg == 3) ? a.cp.veg_fsd[il] : 0.0;
 }
 
+// layer geometry from the geometry block of the layer scratch (written by fast_prepare_level)
+template <int NREG>
+SSB_HDI void load_layer_geom(const ClassArgs &a, int q, int lev, LayerGeom &gm) {
+  const double *P = a.layer + sidx(a.ne_layer - kGeoElems, lev, a.lmax, a.ne_layer, q);
+  SSB_UNROLL
+  for (int i = 0; i < 9; ++i) gm.f_exchange[i] = 0.0;
+  SSB_UNROLL
+  for (int r = 0; r < 3; ++r) {
+    gm.f_wall[r] = P[(size_t)r * kScratchTile];
+    gm.od_scaling[r] = P[(size_t)(3 + r) * kScratchTile];
+    gm.frac[r] = P[(size_t)(8 + r) * kScratchTile];
+    gm.norm_perim_wall[r] = P[(size_t)(17 + r) * kScratchTile];
+    gm.norm_perim[r] = 0.0;  // (only used to derive the exchange rates)
+  }
+  if (NREG > 1) {
+    SSB_UNROLL
+    for (int i = 0; i < 6; ++i) gm.f_exchange[geo_exchange_index(i)] = P[(size_t)(11 + i) * kScratchTile];
+  }
+  gm.f_wall_dir_clear = P[(size_t)6 * kScratchTile];
+  const int seg = (int)P[(size_t)7 * kScratchTile];
+  gm.r0 = (seg == 2) ? 1 : 0;
+  gm.nr = (seg == 0) ? NREG : (seg == 1 ? 1 : NREG - 1);
+}
+
 // which sub-block of regions a layer solves: 0 = all regions, 1 = clear region only,
 // 2 = vegetated regions only (radsurf_urban_sw.F90:512-583)
 SSB_HDI int branch_segment(const LayerGeom &gm, int nreg) {
@@ -95,9 +119,8 @@ SSB_HDI bool fast_sw_prepare(const ClassArgs &a, int q, int lev, LayerGeom &gm, 
     op.tan0 = sqrt(1.0 - op.cos_sza * op.cos_sza) / dmax(op.cos_sza, 1.0e-6);
   }
   op.dz = a.cp.dz[il];
-  double bf, bs, vf, vs, ve, vcf, vfsd;
-  load_geometry_inputs(a, il, bf, bs, vf, vs, ve, vcf, vfsd);
-  layer_geometry(c, bf, bs, vf, vs, vcf, vfsd, 1.0, gm);
+  load_layer_geom<NREG>(a, q, lev, gm);
+  const double ve = ((NREG > 1 || !c.urban) && a.cp.veg_ext) ? a.cp.veg_ext[il] : 0.0;
   op.ext[0] = SSB_LAY(a.sw.air_ext, g, il);
   op.ssa[0] = SSB_LAY(a.sw.air_ssa, g, il);
   SSB_UNROLL
@@ -176,10 +199,9 @@ SSB_HDI void fast_layer_problem_lw_impl(const ClassArgs &a, int q, int lev, cons
   const int il = a.istartlay[col] - 1 + lev;
   LayerOptics op;
   op.dz = a.cp.dz[il];
-  double bf, bs, vf, vs, ve, vcf, vfsd;
-  load_geometry_inputs(a, il, bf, bs, vf, vs, ve, vcf, vfsd);
   LayerGeom gm;
-  layer_geometry(c, bf, bs, vf, vs, vcf, vfsd, a.lg.vadjustment2, gm);
+  load_layer_geom<NREG>(a, q, lev, gm);
+  const double ve = ((NREG > 1 || !c.urban) && a.cp.veg_ext) ? a.cp.veg_ext[il] : 0.0;
   op.ext[0] = SSB_LAY(a.lw.air_ext, g, il);
   op.ssa[0] = SSB_LAY(a.lw.air_ssa, g, il);
   op.planck[0] = SSB_LAY(a.lw.clear_air_planck, g, il);
@@ -288,7 +310,10 @@ SSB_HDI int fast_prepare_level(const ClassArgs &a, int q, int k) {
   for (int r = 0; r < 3; ++r) {
     P[(size_t)r * kScratchTile] = gm.f_wall[r];
     P[(size_t)(3 + r) * kScratchTile] = gm.od_scaling[r];
+    P[(size_t)(8 + r) * kScratchTile] = gm.frac[r];
+    P[(size_t)(17 + r) * kScratchTile] = gm.norm_perim_wall[r];
   }
+  for (int i = 0; i < 6; ++i) P[(size_t)(11 + i) * kScratchTile] = gm.f_exchange[geo_exchange_index(i)];
   P[(size_t)6 * kScratchTile] = gm.f_wall_dir_clear;
   P[(size_t)7 * kScratchTile] = (double)seg;
   return seg;

@@ -68,10 +68,13 @@ SSB_HDI size_t scratch_doubles(size_t nelem, size_t nlev, size_t width) {
 
 // element counts of the two scratch areas.  The layer area ends with a geometry block
 // written before the layer kernels run (register-resident path): f_wall[3], od_scaling[3],
-// f_wall_dir_clear and the solved sub-block ("segment": 0 all regions, 1 clear region only,
-// 2 vegetated regions only), so that the sweeps evaluate no geometry and skip the
-// structural zeros of partially solved layers.
-constexpr int kGeoElems = 8;
+// f_wall_dir_clear, the solved sub-block ("segment": 0 all regions, 1 clear region only,
+// 2 vegetated regions only), frac[3], the six exchange rates and norm_perim_wall[3]: the
+// layer geometry is evaluated once per layer, the layer kernels and the sweeps read it, and
+// the sweeps skip the structural zeros of partially solved layers.
+constexpr int kGeoElems = 20;
+// entries [to + 3*from] of f_exchange that can be non-zero: 1, 2, 3, 5, 6, 7
+SSB_HDI int geo_exchange_index(int i) { return i < 3 ? i + 1 : i + 2; }
 SSB_HDI int sw_layer_elems(int n, int d) { return 3 * n * n + 3 * n * d + 2 * d * d + kGeoElems; }
 SSB_HDI int lw_layer_elems(int n, int nreg) { return 3 * n * n + 2 * n + 3 * nreg + 1 + kGeoElems; }
 SSB_HDI int sw_sweep_elems(int n, int d, int m, int db, int nreg, int nrb) {
