@@ -119,16 +119,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock and throttle reasons of the samples that arrived in [t_begin, t_end]
+        (the timed region); if the region was too short to catch one, of the samples since the
+        sampler started (it starts before the warm-up steps, so those are under the same load)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if t_begin is None or t_begin <= t <= (t_end or t) + 0.15]
+        window = "timed region" if inside else "warm-up and timed region"
+        for r in (inside or [r for _, r in self.rows]):
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -138,7 +143,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def host_threads():
@@ -245,10 +250,13 @@ def main():
     torch.cuda.set_device(local_rank)
     lib.ssb200_set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: whatever libraries print there (the NCCL version
+    # banner under torchrun) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     if args.generic:
         lib.ssb200_set_option(b"fast_kernels", 0)
@@ -272,20 +280,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     launches0 = lib.ssb200_kernel_launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     launches = lib.ssb200_kernel_launch_count() - launches0
     barrier()
     t = torch.tensor([ms], dtype=torch.float64, device=device)
@@ -309,6 +319,49 @@ def main():
         res[name] = float((r.abs() / denom).max().item())
     nonfinite = int(sum((~torch.isfinite(getattr(f, k))).sum().item() for f in fl
                         for k in ("ground_net", "top_net", "clear_air_abs", "veg_abs", "wall_net", "roof_net")))
+
+    # ---- end to end through the host-pointer C ABI entry (pinned host buffers), every rank at once ----
+    e2e = None
+    if args.e2e_steps > 0:
+        hcp, hsw, hlw = to_host(cp), to_host(sw), to_host(lw)
+        pin = []
+        for obj in (hcp, hsw, hlw):
+            for k, v in list(vars(obj).items()):
+                if isinstance(v, np.ndarray) and v.dtype == np.float64:
+                    tt = torch.from_numpy(v).pin_memory()
+                    pin.append(tt)
+                    setattr(obj, k, tt.numpy())
+        hbc, hfl = allocate_outputs(cfg, ncol, hcp.ntotlay)
+        for obj in [hbc] + hfl:
+            for k, v in list(vars(obj).items()):
+                if isinstance(v, np.ndarray) and v.dtype == np.float64:
+                    tt = torch.from_numpy(v).pin_memory()
+                    pin.append(tt)
+                    setattr(obj, k, tt.numpy())
+        h2d = sum(v.nbytes for obj in (hcp, hsw, hlw) for v in vars(obj).values()
+                  if isinstance(v, np.ndarray) and v.dtype == np.float64)
+        d2h = sum(v.nbytes for obj in [hbc] + hfl for v in vars(obj).values()
+                  if isinstance(v, np.ndarray) and v.dtype == np.float64)
+        radsurf(cfg, hcp, hsw, hlw, hbc, None, None, *hfl)  # warm-up (allocates the device mirrors)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            rc = radsurf(cfg, hcp, hsw, hlw, hbc, None, None, *hfl)  # returns when the outputs are on the host
+            assert rc == 0
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * units_per_rank * args.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+               "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "note": "ssb200_radsurf with pinned host arrays on every rank at once: H2D of every input, kernels, "
+                       "D2H of every output; host wall clock, max over ranks; bytes summed over ranks"}
+        # the device-resident result equals the host-path result (same kernels)
+        dev_top = fl[0].top_net[:4096, 0].cpu().numpy()
+        assert np.array_equal(dev_top, hfl[0].top_net[:4096, 0]), "device and host entry disagree"
+        del pin, hcp, hsw, hlw, hbc, hfl
 
     out = None
     if rank == 0:
@@ -402,43 +455,6 @@ def main():
         roofline_hbm = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                         "note": "compulsory input+output bytes of the whole path only (540 B per column-layer)"}
 
-        # ---- end to end through the host-pointer C ABI entry (pinned host buffers) --------------
-        e2e = None
-        if args.e2e_steps > 0:
-            hcp, hsw, hlw = to_host(cp), to_host(sw), to_host(lw)
-            pin = []
-            for obj in (hcp, hsw, hlw):
-                for k, v in list(vars(obj).items()):
-                    if isinstance(v, np.ndarray) and v.dtype == np.float64:
-                        tt = torch.from_numpy(v).pin_memory()
-                        pin.append(tt)
-                        setattr(obj, k, tt.numpy())
-            hbc, hfl = allocate_outputs(cfg, ncol, hcp.ntotlay)
-            for obj in [hbc] + hfl:
-                for k, v in list(vars(obj).items()):
-                    if isinstance(v, np.ndarray) and v.dtype == np.float64:
-                        tt = torch.from_numpy(v).pin_memory()
-                        pin.append(tt)
-                        setattr(obj, k, tt.numpy())
-            h2d = sum(v.nbytes for obj in (hcp, hsw, hlw) for v in vars(obj).values()
-                      if isinstance(v, np.ndarray) and v.dtype == np.float64)
-            d2h = sum(v.nbytes for obj in [hbc] + hfl for v in vars(obj).values()
-                      if isinstance(v, np.ndarray) and v.dtype == np.float64)
-            radsurf(cfg, hcp, hsw, hlw, hbc, None, None, *hfl)  # warm-up (allocates the device mirrors)
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                rc = radsurf(cfg, hcp, hsw, hlw, hbc, None, None, *hfl)
-                assert rc == 0
-            dt = time.perf_counter() - t0
-            e2e = {"value": world * units_per_rank * args.e2e_steps / dt, "unit": UNIT,
-                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": 1e3 * dt / args.e2e_steps,
-                   "note": "ssb200_radsurf with pinned host arrays: H2D of every input, kernels, D2H of every "
-                           "output, host wall clock; measured on rank 0 and scaled by the number of ranks"}
-            # parity of the device-resident result against the host-path result (same kernels)
-            dev_top = fl[0].top_net[:4096, 0].cpu().numpy()
-            assert np.array_equal(dev_top, hfl[0].top_net[:4096, 0]), "device and host entry disagree"
-
         # ---- CPU baseline beside it (oracle on the host cores, bounded sample) -------------------
         cpu = None
         parity_err = None
@@ -500,7 +516,8 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":
