@@ -32,13 +32,28 @@ struct Scr {
   size_t lev_stride;
   SSB_HDI Scr(double *area, int nlev, int nelem, int q)
       : base(area + sidx(0, 0, nlev, nelem, q)), lev_stride((size_t)nelem * kScratchTile) {}
-  SSB_HDI double ld(int e, int lev) const { return base[(size_t)lev * lev_stride + (size_t)e * kScratchTile]; }
+  // The scratch is streamed (every element is used once or twice, hundreds of megabytes apart):
+  // evict-first loads and stores keep it from flushing the partially written sectors of the
+  // per-column output arrays out of L2.
+  SSB_HDI double ld(int e, int lev) const {
+#if defined(__CUDA_ARCH__)
+    return __ldcs(base + (size_t)lev * lev_stride + (size_t)e * kScratchTile);
+#else
+    return base[(size_t)lev * lev_stride + (size_t)e * kScratchTile];
+#endif
+  }
   SSB_HDI double ldp(int e, int lev, bool keep) const {  // structural zeros are not loaded
     double v = 0.0;
-    if (keep) v = base[(size_t)lev * lev_stride + (size_t)e * kScratchTile];
+    if (keep) v = ld(e, lev);
     return v;
   }
-  SSB_HDI void st(int e, int lev, double v) const { base[(size_t)lev * lev_stride + (size_t)e * kScratchTile] = v; }
+  SSB_HDI void st(int e, int lev, double v) const {
+#if defined(__CUDA_ARCH__)
+    __stcs(base + (size_t)lev * lev_stride + (size_t)e * kScratchTile, v);
+#else
+    base[(size_t)lev * lev_stride + (size_t)e * kScratchTile] = v;
+#endif
+  }
 };
 
 // A layer that solves only a sub-block of its regions ("segment" 1: clear region, 2: vegetated

@@ -309,6 +309,13 @@ SSB_HDI void layer_vm_row(const LayerCoef<NR, NS> &c, const StateMem &st, int i,
 
 // addressing of the layer scratch of one problem: element e at P[e * kScratchTile]
 #define SSB_OUT(P, e) (P)[(size_t)(e) * kScratchTile]
+// final value of an element: not read again in this kernel, consumed by the sweeps hundreds of
+// megabytes later - a streaming (evict-first) store keeps it from displacing the parked rows
+#if defined(__CUDA_ARCH__)
+#define SSB_FINAL(P, e, v) __stcs((P) + (size_t)(e) * kScratchTile, (v))
+#else
+#define SSB_FINAL(P, e, v) ((P)[(size_t)(e) * kScratchTile] = (v))
+#endif
 
 // One stage of the two-point solve, X = B A^-1 with A = V(1+s e) + M(1-s e),
 // B = V(1+s e) - M(1-s e): builds both row by row, parks the rows of B in the scratch
@@ -394,8 +401,8 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
           se = fma(gk, e0[k], se);
           si = fma(gk, reps[k], si);
         }
-        SSB_OUT(P, eE + (i + r0) + d * (j + r0)) = se;
-        SSB_OUT(P, eIdir + (i + r0) + d * (j + r0)) = -si;
+        SSB_FINAL(P, eE + (i + r0) + d * (j + r0), se);
+        SSB_FINAL(P, eIdir + (i + r0) + d * (j + r0), -si);
         g0inv[i + D * j] = si;
       }
     }
@@ -418,7 +425,7 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
       for (int i = 0; i < N; ++i) x[i] = (i == j) ? -1.0 : 0.0;
       sm_lu_solve_left<N, 1>(LUs, x);
       SSB_UNROLL
-      for (int i = 0; i < N; ++i) SSB_OUT(P, eIdiff + (i + i0) + n * (j + i0)) = x[i];
+      for (int i = 0; i < N; ++i) SSB_FINAL(P, eIdiff + (i + i0) + n * (j + i0), x[i]);
       const double gj = -2.0 * c.g3(j);
       SSB_UNROLL
       for (int jd = 0; jd < D; ++jd) {
@@ -430,7 +437,7 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
     SSB_UNROLL
     for (int jd = 0; jd < D; ++jd) {
       SSB_UNROLL
-      for (int i = 0; i < N; ++i) SSB_OUT(P, eIdd + (i + i0) + n * (jd + r0)) = Idd[i + N * jd];
+      for (int i = 0; i < N; ++i) SSB_FINAL(P, eIdd + (i + i0) + n * (jd + r0), Idd[i + N * jd]);
     }
   }
   // ---- diffuse eigen-system and the two-point solve ---------------------------------------
@@ -599,8 +606,8 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
           sum = fma(xp[k], rp[k + N * j], sum);
           dif = fma(xm[k], rm[k + N * j], dif);
         }
-        SSB_OUT(P, eSup + (i + i0) + n * (j + r0)) = 0.5 * (sum + dif);
-        SSB_OUT(P, eSdn + (i + i0) + n * (j + r0)) = 0.5 * (sum - dif);
+        SSB_FINAL(P, eSup + (i + i0) + n * (j + r0), 0.5 * (sum + dif));
+        SSB_FINAL(P, eSdn + (i + i0) + n * (j + r0), 0.5 * (sum - dif));
       }
     }
   }
@@ -669,23 +676,23 @@ SSB_HDI bool layer_lw_solve(const LayerCoef<NR, NS> &c, const double *brate, dou
             s = fma(x[k], y[k], s);
             SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = x[k];
           }
-          SSB_OUT(P, eSrc + i + i0) = yi - s;
+          SSB_FINAL(P, eSrc + i + i0, yi - s);
           sm_lu_solve_right<1, N>(A, xpr);
           double f = 0.0;
           SSB_UNROLL
           for (int k = 0; k < N; ++k) {
             f = fma(xpr[k], y[k], f);
-            SSB_OUT(P, eIF + (i + i0) + n * (k + i0)) = xpr[k];
+            SSB_FINAL(P, eIF + (i + i0) + n * (k + i0), xpr[k]);
           }
-          SSB_OUT(P, eIsrc + i + i0) = 2.0 * (yi * dz - f);
+          SSB_FINAL(P, eIsrc + i + i0, 2.0 * (yi * dz - f));
         } else {
           SSB_UNROLL
           for (int k = 0; k < N; ++k) {
             const double xp = xpr[k];
             const double r = 0.5 * (xp + x[k]), t = 0.5 * (xp - x[k]);
             bad = bad || !(fabs(r) < 1.0e300) || !(fabs(t) < 1.0e300);
-            SSB_OUT(P, eR + (i + i0) + n * (k + i0)) = r;
-            SSB_OUT(P, eT + (i + i0) + n * (k + i0)) = t;
+            SSB_FINAL(P, eR + (i + i0) + n * (k + i0), r);
+            SSB_FINAL(P, eT + (i + i0) + n * (k + i0), t);
           }
         }
       }
