@@ -264,3 +264,36 @@ def test_simple_spectrum_lw_on_device():
         h, d = getattr(lw, k), getattr(dlw, k).cpu().numpy()
         assert np.array_equal(h == -1.0, d == -1.0), k          # same range written
         assert np.allclose(h, d, rtol=1e-15, atol=0), k         # ** 4 (pow) against (t*t)*(t*t)
+
+
+def test_empty_and_flat_only_inputs():
+    """No columns at all, and columns that own no layers (Flat tiles only, ntotlay = 0)."""
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, 16, 2)
+    # empty column range
+    bc, fl = _outputs(cfg, cp.ncol, cp.ntotlay)
+    for f in fl:
+        f.fill(7.0)
+    assert radsurf(cfg, cp, sw, lw, bc, 5, 4, *fl) == 0
+    assert all(np.all(getattr(f, k) == 7.0) for f in fl for k in ALL_FIELDS if getattr(f, k) is not None)
+    # Flat tiles only: per-layer arrays are empty
+    ncol = 5
+    fcp, fsw, flw = make_synthetic(cfg, ncol, 1)
+    fcp.set_layers(np.zeros(ncol, dtype=np.int32))
+    fcp.i_representation = np.zeros(ncol, dtype=np.int32)
+    for obj in (fcp, fsw, flw):
+        for k, v in list(vars(obj).items()):
+            if isinstance(v, np.ndarray) and v.dtype == np.float64 and v.shape[0] == ncol * 1 and k not in (
+                    "cos_sza", "ground_albedo", "ground_albedo_dir", "ground_emissivity", "ground_emission"):
+                setattr(obj, k, np.ascontiguousarray(v[:0]))
+    fbc, ffl = _outputs(cfg, ncol, 0)
+    assert radsurf(cfg, fcp, fsw, flw, fbc, None, None, *ffl) == 0
+    obc, ofl = _outputs(cfg, ncol, 0)
+    oracle_lib.make_solver()(cfg, fcp, fsw, flw, obc, None, None, *ofl)
+    for f, g in zip(ffl, ofl):
+        for k in ALL_FIELDS:
+            a = getattr(f, k)
+            if a is not None:
+                assert np.allclose(a, getattr(g, k), rtol=1e-14, atol=1e-300), k
+    for k in golden_io.BC_FIELDS:
+        assert np.allclose(getattr(fbc, k), getattr(obc, k), rtol=1e-14), k
