@@ -11,6 +11,10 @@
 #include "ssb_fast_layer.cuh"
 #include "ssb_launch.hpp"
 
+namespace ssb {
+cudaError_t g_fast_error = cudaSuccess;
+}
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -249,6 +253,8 @@ struct CudaBackend {
   void check_launch() {
     ++g_launches;
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = ssb::g_fast_error;
+    ssb::g_fast_error = cudaSuccess;
     if (e != cudaSuccess && cx.first_error == cudaSuccess) cx.first_error = e;
   }
   template <class F>

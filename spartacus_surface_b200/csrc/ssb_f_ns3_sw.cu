@@ -1,0 +1,4 @@
+// register-resident sw layer kernels, 3 stream(s) per hemisphere
+#define SSB_NS 3
+#define SSB_KIND_SW
+#include "ssb_fast_kernels.cuh"

@@ -3,6 +3,8 @@
 // SSB_KIND_SW / SSB_KIND_LW defined.
 #pragma once
 #include "ssb_fast.cuh"
+#define SSB_CAT2(a, b) a##b
+#define SSB_CAT(a, b) SSB_CAT2(a, b)
 #include "ssb_fast_layer.cuh"
 #include "ssb_fast_sweeps.cuh"
 
@@ -63,8 +65,11 @@ template <int NREG, int NS, bool LW>
 static void launch_partition_layers(const ClassArgs &a, long nt, cudaStream_t st) {
   const size_t smem = sizeof(double) * kPartitionBlock *
                       (LW ? LayerStack<1, NS>::lw_doubles : LayerStack<1, NS>::sw_doubles);
-  cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st);
+  if (smem > 48 * 1024)
+    fast_note(cudaFuncSetAttribute(k_partition_layers<NREG, NS, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fast_note(cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st));
   k_partition_layers<NREG, NS, LW><<<(unsigned)((nt + kPartitionBlock - 1) / kPartitionBlock), kPartitionBlock, smem, st>>>(a, nt);
+  fast_note(cudaGetLastError());
 }
 
 #ifdef SSB_KIND_SW
@@ -82,8 +87,9 @@ template <int NREG, int NS, int SEG>
 static void launch_fast_layer_sw_seg(const ClassArgs &a, long nt, unsigned grid, cudaStream_t st) {
   constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
   const size_t smem = sizeof(double) * LayerStack<NR, NS>::sw_doubles * kLayerBlock;
-  cudaFuncSetAttribute(k_fast_layer_sw_seg<NREG, NS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fast_note(cudaFuncSetAttribute(k_fast_layer_sw_seg<NREG, NS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_fast_layer_sw_seg<NREG, NS, SEG><<<grid, kLayerBlock, smem, st>>>(a, nt);
+  fast_note(cudaGetLastError());
 }
 template <int NREG, int NS>
 static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st) {
@@ -92,8 +98,7 @@ static void launch_fast_layer_sw(const ClassArgs &a, long nt, cudaStream_t st) {
   launch_fast_layer_sw_seg<NREG, NS, 0>(a, nt, grid, st);
   if (NREG > 1) launch_fast_layer_sw_seg<NREG, NS, 2>(a, nt, grid, st);
 }
-template <>
-bool fast_layer_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
+bool SSB_CAT(fast_layer_sw_ns, SSB_NS)(const ClassArgs &a, long nt, cudaStream_t st) {
   if (a.cfg.ns != SSB_NS || a.perm == nullptr) return false;
   switch (a.cfg.nreg) {
     case 1: launch_fast_layer_sw<1, SSB_NS>(a, nt, st); return true;
@@ -116,11 +121,11 @@ template <int NREG, int NS, bool URBAN>
 static void launch_fast_sweeps_sw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
   const size_t smem = sizeof(double) * SwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
-  cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fast_note(cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_fast_sweeps_sw<NREG, NS, URBAN><<<grid, kFastBlock, smem, st>>>(a, nt);
+  fast_note(cudaGetLastError());
 }
-template <>
-bool fast_sweeps_sw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
+bool SSB_CAT(fast_sweeps_sw_ns, SSB_NS)(const ClassArgs &a, long nt, cudaStream_t st) {
   if (a.cfg.ns != SSB_NS) return false;
   switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
     case 2: launch_fast_sweeps_sw<1, SSB_NS, false>(a, nt, st); return true;
@@ -149,8 +154,9 @@ template <int NREG, int NS, int SEG>
 static void launch_fast_layer_lw_seg(const ClassArgs &a, long nt, unsigned grid, cudaStream_t st) {
   constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
   const size_t smem = sizeof(double) * LayerStack<NR, NS>::lw_doubles * kLayerBlock;
-  cudaFuncSetAttribute(k_fast_layer_lw_seg<NREG, NS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fast_note(cudaFuncSetAttribute(k_fast_layer_lw_seg<NREG, NS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_fast_layer_lw_seg<NREG, NS, SEG><<<grid, kLayerBlock, smem, st>>>(a, nt);
+  fast_note(cudaGetLastError());
 }
 template <int NREG, int NS>
 static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st) {
@@ -159,8 +165,7 @@ static void launch_fast_layer_lw(const ClassArgs &a, long nt, cudaStream_t st) {
   launch_fast_layer_lw_seg<NREG, NS, 0>(a, nt, grid, st);
   if (NREG > 1) launch_fast_layer_lw_seg<NREG, NS, 2>(a, nt, grid, st);
 }
-template <>
-bool fast_layer_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
+bool SSB_CAT(fast_layer_lw_ns, SSB_NS)(const ClassArgs &a, long nt, cudaStream_t st) {
   if (a.cfg.ns != SSB_NS || a.perm == nullptr) return false;
   switch (a.cfg.nreg) {
     case 1: launch_fast_layer_lw<1, SSB_NS>(a, nt, st); return true;
@@ -183,11 +188,11 @@ template <int NREG, int NS, bool URBAN>
 static void launch_fast_sweeps_lw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
   const size_t smem = sizeof(double) * LwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
-  cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fast_note(cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_fast_sweeps_lw<NREG, NS, URBAN><<<grid, kFastBlock, smem, st>>>(a, nt);
+  fast_note(cudaGetLastError());
 }
-template <>
-bool fast_sweeps_lw<SSB_NS>(const ClassArgs &a, long nt, cudaStream_t st) {
+bool SSB_CAT(fast_sweeps_lw_ns, SSB_NS)(const ClassArgs &a, long nt, cudaStream_t st) {
   if (a.cfg.ns != SSB_NS) return false;
   switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
     case 2: launch_fast_sweeps_lw<1, SSB_NS, false>(a, nt, st); return true;

@@ -16,7 +16,7 @@ struct HostBackend {
   const ssb::Plan *plan = nullptr;
   std::vector<double> buf;
   int status = 0;
-  bool fast = false;  // use the register-resident layer bodies where they exist (ns <= 2)
+  bool fast = false;  // use the register-resident bodies where they exist (ns <= 4)
   size_t budget = (size_t)1 << 22;  // small on purpose: exercises the chunk loop
   const int *dev_cols(const ssb::Plan &p, size_t off) { return p.all_cols.data() + off; }
   // reversed column order inside every chunk: results must not depend on it
@@ -37,78 +37,92 @@ struct HostBackend {
   }
   size_t scratch_budget_doubles() { return budget; }
   int *dev_status() { return &status; }
-  template <int NS>
-  void layer_sw(const ssb::ClassArgs &a, long nt) {
+  // register-resident bodies for the actual stream count NSA (1..4), as the device runs them:
+  // prepare pass (k_partition_layers), then every layer problem
+  template <int NSA, bool LW>
+  void fast_layers(const ssb::ClassArgs &a, long nt) {
     const long width = (long)a.ncols * a.cfg.nspec;
-    const bool f = fast && a.cfg.ns == NS && NS <= 2;
-    double stack[128];
+    double stack[256];
     const ssb::StateMem st{stack, 1};
-    if (f)  // what k_partition_layers does on the device: geometry block of every layer
-      for (long t = 0; t < nt; ++t) ssb::fast_prepare_level(a, (int)(t % width), (int)(t / width));
+    for (long t = 0; t < nt; ++t) ssb::fast_prepare_level(a, (int)(t % width), (int)(t / width));
     for (long t = 0; t < nt; ++t) {
       const int q = (int)(t % width), lev = (int)(t / width);
-      if (f && a.cfg.nreg == 1)
-        ssb::fast_layer_problem_sw<1, (NS <= 2 ? NS : 1)>(a, q, lev, st);
-      else if (f && a.cfg.nreg == 2)
-        ssb::fast_layer_problem_sw<2, (NS <= 2 ? NS : 1)>(a, q, lev, st);
-      else if (f && a.cfg.nreg == 3)
-        ssb::fast_layer_problem_sw<3, (NS <= 2 ? NS : 1)>(a, q, lev, st);
-      else
-        ssb::layer_problem_sw<NS>(a, q, lev);
+      if (LW) {
+        if (a.cfg.nreg == 1) ssb::fast_layer_problem_lw<1, NSA>(a, q, lev, st);
+        else if (a.cfg.nreg == 2) ssb::fast_layer_problem_lw<2, NSA>(a, q, lev, st);
+        else ssb::fast_layer_problem_lw<3, NSA>(a, q, lev, st);
+      } else {
+        if (a.cfg.nreg == 1) ssb::fast_layer_problem_sw<1, NSA>(a, q, lev, st);
+        else if (a.cfg.nreg == 2) ssb::fast_layer_problem_sw<2, NSA>(a, q, lev, st);
+        else ssb::fast_layer_problem_sw<3, NSA>(a, q, lev, st);
+      }
     }
+  }
+  template <bool LW>
+  bool try_fast_layers(const ssb::ClassArgs &a, long nt) {
+    if (!fast) return false;
+    switch (a.cfg.ns) {
+      case 1: fast_layers<1, LW>(a, nt); return true;
+      case 2: fast_layers<2, LW>(a, nt); return true;
+      case 3: fast_layers<3, LW>(a, nt); return true;
+      case 4: fast_layers<4, LW>(a, nt); return true;
+      default: return false;
+    }
+  }
+  template <int NS>
+  void layer_sw(const ssb::ClassArgs &a, long nt) {
+    if (try_fast_layers<false>(a, nt)) return;
+    const long width = (long)a.ncols * a.cfg.nspec;
+    for (long t = 0; t < nt; ++t) ssb::layer_problem_sw<NS>(a, (int)(t % width), (int)(t / width));
   }
   template <int NS>
   void layer_lw(const ssb::ClassArgs &a, long nt) {
+    if (try_fast_layers<true>(a, nt)) return;
     const long width = (long)a.ncols * a.cfg.nspec;
-    const bool f = fast && a.cfg.ns == NS && NS <= 2;
-    double stack[128];
-    const ssb::StateMem st{stack, 1};
-    if (f)  // what k_partition_layers does on the device: geometry block of every layer
-      for (long t = 0; t < nt; ++t) ssb::fast_prepare_level(a, (int)(t % width), (int)(t / width));
-    for (long t = 0; t < nt; ++t) {
-      const int q = (int)(t % width), lev = (int)(t / width);
-      if (f && a.cfg.nreg == 1)
-        ssb::fast_layer_problem_lw<1, (NS <= 2 ? NS : 1)>(a, q, lev, st);
-      else if (f && a.cfg.nreg == 2)
-        ssb::fast_layer_problem_lw<2, (NS <= 2 ? NS : 1)>(a, q, lev, st);
-      else if (f && a.cfg.nreg == 3)
-        ssb::fast_layer_problem_lw<3, (NS <= 2 ? NS : 1)>(a, q, lev, st);
-      else
-        ssb::layer_problem_lw<NS>(a, q, lev);
-    }
+    for (long t = 0; t < nt; ++t) ssb::layer_problem_lw<NS>(a, (int)(t % width), (int)(t / width));
   }
-  template <int NS, bool LW, int NREG, bool URBAN>
+  template <int NSA, bool LW, int NREG, bool URBAN>
   void fast_sweeps(const ssb::ClassArgs &a, long nt) {
-    double state[64];
+    double state[256];
     const ssb::StateMem st{state, 1};
     for (long t = 0; t < nt; ++t) {
       if (LW)
-        ssb::fast_column_sweeps_lw<NREG, (NS <= 2 ? NS : 1), URBAN>(a, (int)t, st);
+        ssb::fast_column_sweeps_lw<NREG, NSA, URBAN>(a, (int)t, st);
       else
-        ssb::fast_column_sweeps_sw<NREG, (NS <= 2 ? NS : 1), URBAN>(a, (int)t, st);
+        ssb::fast_column_sweeps_sw<NREG, NSA, URBAN>(a, (int)t, st);
     }
   }
-  template <int NS, bool LW>
-  bool try_fast_sweeps(const ssb::ClassArgs &a, long nt) {
-    if (!(fast && a.cfg.ns == NS && NS <= 2)) return false;
+  template <int NSA, bool LW>
+  bool fast_sweeps_ns(const ssb::ClassArgs &a, long nt) {
     switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
-      case 2: fast_sweeps<NS, LW, 1, false>(a, nt); return true;
-      case 3: fast_sweeps<NS, LW, 1, true>(a, nt); return true;
-      case 4: fast_sweeps<NS, LW, 2, false>(a, nt); return true;
-      case 5: fast_sweeps<NS, LW, 2, true>(a, nt); return true;
-      case 6: fast_sweeps<NS, LW, 3, false>(a, nt); return true;
-      case 7: fast_sweeps<NS, LW, 3, true>(a, nt); return true;
+      case 2: fast_sweeps<NSA, LW, 1, false>(a, nt); return true;
+      case 3: fast_sweeps<NSA, LW, 1, true>(a, nt); return true;
+      case 4: fast_sweeps<NSA, LW, 2, false>(a, nt); return true;
+      case 5: fast_sweeps<NSA, LW, 2, true>(a, nt); return true;
+      case 6: fast_sweeps<NSA, LW, 3, false>(a, nt); return true;
+      case 7: fast_sweeps<NSA, LW, 3, true>(a, nt); return true;
+      default: return false;
+    }
+  }
+  template <bool LW>
+  bool try_fast_sweeps(const ssb::ClassArgs &a, long nt) {
+    if (!fast) return false;
+    switch (a.cfg.ns) {
+      case 1: return fast_sweeps_ns<1, LW>(a, nt);
+      case 2: return fast_sweeps_ns<2, LW>(a, nt);
+      case 3: return fast_sweeps_ns<3, LW>(a, nt);
+      case 4: return fast_sweeps_ns<4, LW>(a, nt);
       default: return false;
     }
   }
   template <int NS>
   void sweeps_sw(const ssb::ClassArgs &a, long nt) {
-    if (try_fast_sweeps<NS, false>(a, nt)) return;
+    if (try_fast_sweeps<false>(a, nt)) return;
     for (long t = 0; t < nt; ++t) ssb::column_sweeps_sw<NS>(a, (int)t);
   }
   template <int NS>
   void sweeps_lw(const ssb::ClassArgs &a, long nt) {
-    if (try_fast_sweeps<NS, true>(a, nt)) return;
+    if (try_fast_sweeps<true>(a, nt)) return;
     for (long t = 0; t < nt; ++t) ssb::column_sweeps_lw<NS>(a, (int)t);
   }
   void surface(const ssb::SurfaceArgs &s, int nsw_threads, int nlw_threads) {

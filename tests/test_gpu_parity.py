@@ -54,7 +54,7 @@ def test_golden_case(case, fast):
 
 
 @pytest.mark.parametrize("fast", [0, 1])
-@pytest.mark.parametrize("streams", [1, 2])
+@pytest.mark.parametrize("streams", [1, 2, 3, 4])
 def test_mixed_edge_case(streams, fast):
     """Ragged layers, flat / forest / urban / vegetated-urban tiles in one call, night-time
     columns, several spectral intervals, direct ground albedo (tests/mixed_case.py)."""

@@ -82,7 +82,7 @@ def test_fast_layer_math_within_sensitivity(case):
     assert ok, "\n".join(lines)
 
 
-@pytest.mark.parametrize("streams", [1, 2])
+@pytest.mark.parametrize("streams", [1, 2, 3, 4])
 def test_mixed_edge_case_fast_path(streams):
     """Ragged layers, all tile types, night columns, several spectral intervals through the
     register-resident bodies (host build) against the oracle."""
