@@ -204,7 +204,7 @@ struct CudaBackend {
   const int *dev_cols(const ssb::Plan &, size_t off) { return (const int *)cx.d_cols.p + off; }
   // columns of the chunk ordered by their segment pattern (device radix sort, stable)
   const int *order_chunk(const ssb::ClassArgs &a, const int *) {
-    if (!cx.fast_mode || !cx.sort_columns || !cx.partition || a.ncols < 64 || a.cfg.ns > 2 ||
+    if (!cx.fast_mode || !cx.sort_columns || !cx.partition || a.ncols < 64 || a.cfg.ns > 4 ||
         cx.first_error != cudaSuccess)
       return a.cols;
     const size_t n = (size_t)a.ncols, pad = (n + 63) & ~(size_t)63;
