@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 4, 8])
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 3, 4, 8])
     ap.add_argument("--columns", type=int, default=FULL_COLUMNS, help="columns per GPU")
     ap.add_argument("--cpu-columns", type=int, default=131072, help="columns of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
