@@ -11,8 +11,8 @@
 
 namespace orc {
 
-static const double kPi = 3.14159265358979323846; // radiation_constants.F90:24
-static const double kEps = std::numeric_limits<double>::epsilon();
+static const real kPi = 3.14159265358979323846; // radiation_constants.F90:24
+static const real kEps = std::numeric_limits<double>::epsilon(); // epsilon(1.0_jprb): an algorithm constant, FP64 in every build
 
 static LegendreGauss lg_from_c(const ssb200_legendre_gauss &c) {
   LegendreGauss lg;
@@ -34,9 +34,9 @@ static LegendreGauss lg_from_c(const ssb200_legendre_gauss &c) {
 // ---------------------------------------------------------------------------
 
 // calc_overlap_matrix_max_ran: radsurf_overlap.F90:28-73 (nreg 2 or 3).
-static Mat overlap_max_ran(int nreg, double f_upper, double f_lower) {
+static Mat overlap_max_ran(int nreg, real f_upper, real f_lower) {
   Mat O(nreg, nreg);
-  const double pair_cover = std::max(f_upper, f_lower);
+  const real pair_cover = rmax(f_upper, f_lower);
   O(0, 0) = 1.0 - pair_cover;
   if (nreg == 2) {
     O(0, 1) = pair_cover - f_upper;
@@ -58,7 +58,7 @@ static Mat overlap_max_ran(int nreg, double f_upper, double f_lower) {
 // calc_overlap_matrices: radsurf_overlap.F90:85-171.  frac is (nreg, nlay+1);
 // outputs are per interface jlay = 0..nlay (0 = ground).
 static void calc_overlap_matrices(int nlay, int nreg, const Mat &frac, std::vector<Mat> &u,
-                                  std::vector<Mat> &v, double frac_threshold) {
+                                  std::vector<Mat> &v, real frac_threshold) {
   u.assign(nlay + 1, Mat(nreg, nreg));
   v.assign(nlay + 1, Mat(nreg, nreg));
   Vec frac_upper(nreg, 0.0), frac_lower(nreg, 0.0);
@@ -93,7 +93,7 @@ static Mat overlap_max_ran_urban(int nreg, const Vec &fu, const Vec &fl) {
     O(0, 0) = fl[0];
     O(0, 1) = fl[1];
   } else if (nreg == 2) {
-    const double pair_cover = std::max(fu[1], fl[1]);
+    const real pair_cover = rmax(fu[1], fl[1]);
     if (pair_cover <= fl[0] + fl[1]) {
       O(1, 2) = 0.0;
       O(0, 2) = fl[2];
@@ -112,7 +112,7 @@ static Mat overlap_max_ran_urban(int nreg, const Vec &fu, const Vec &fl) {
   } else {
     O(1, 2) = 0.0;
     O(2, 1) = 0.0;
-    const double pair_cover = std::max(fu[1] + fu[2], fl[1] + fl[2]);
+    const real pair_cover = rmax(fu[1] + fu[2], fl[1] + fl[2]);
     if (pair_cover <= fl[0] + fl[1] + fl[2]) {
       O(1, 3) = 0.0;
       O(2, 3) = 0.0;
@@ -154,12 +154,12 @@ static Mat overlap_max_ran_urban(int nreg, const Vec &fu, const Vec &fl) {
 // argument region_fracs(1:nreg,nlay).
 static void calc_overlap_matrices_urban(int nlay, int nreg, const Mat &frac,
                                         std::vector<Mat> &u, std::vector<Mat> &v,
-                                        double frac_threshold) {
+                                        real frac_threshold) {
   u.assign(nlay + 1, Mat(nreg, nreg + 1));
   v.assign(nlay + 1, Mat(nreg + 1, nreg));
   Vec frac_upper(nreg, 0.0), frac_lower(nreg + 1, 0.0);
   auto sumfrac = [&](int jl) {
-    double s = 0.0;
+    real s = 0.0;
     for (int r = 0; r < nreg; ++r) s += frac(r, jl);
     return s;
   };
@@ -188,7 +188,7 @@ static void calc_overlap_matrices_urban(int nlay, int nreg, const Mat &frac,
     if (fj < nlay) {
       frac_lower[nreg] = sumfrac(fj) - sumfrac(fj - 1);
       if (frac_lower[nreg] < 0.0) {
-        const double sc_num = sumfrac(fj), sc_den = sumfrac(fj - 1);
+        const real sc_num = sumfrac(fj), sc_den = sumfrac(fj - 1);
         for (int r = 0; r < nreg; ++r) frac_lower[r] = frac_lower[r] * sc_num / sc_den;
         frac_lower[nreg] = 0.0;
       }
@@ -207,13 +207,13 @@ static void calc_norm_perim_forest(const ssb200_config &cfg, int nlay, int nreg,
                                    const double *veg_fraction, const double *veg_scale,
                                    Mat &norm_perim) {
   norm_perim = Mat(nreg, nlay);
-  const double fiso = cfg.vegetation_isolation_factor_forest;
+  const real fiso = cfg.vegetation_isolation_factor_forest;
   for (int jlay = 0; jlay < nlay; ++jlay) {
     if (nreg > 1) {
       if (veg_fraction[jlay] > cfg.min_vegetation_fraction) {
         if (cfg.use_symmetric_vegetation_scale_forest)
           norm_perim(0, jlay) = 4.0 * veg_fraction[jlay] *
-                                std::max(0.0, 1.0 - veg_fraction[jlay]) / veg_scale[jlay];
+                                rmax(0.0, 1.0 - veg_fraction[jlay]) / veg_scale[jlay];
         else
           norm_perim(0, jlay) = 4.0 * veg_fraction[jlay] / veg_scale[jlay];
         if (nreg > 2) {
@@ -241,15 +241,15 @@ static void calc_norm_perim_urban(const ssb200_config &cfg, int nlay, int nreg,
                                   Mat &norm_perim, Mat &norm_perim_wall) {
   norm_perim = Mat(nreg, nlay);
   norm_perim_wall = Mat(nreg, nlay);
-  const double fiso = cfg.vegetation_isolation_factor_urban;
+  const real fiso = cfg.vegetation_isolation_factor_urban;
   for (int jlay = 0; jlay < nlay; ++jlay) {
     if (nreg > 1) {
       if (veg_fraction[jlay] > cfg.min_vegetation_fraction) {
         if (cfg.use_symmetric_vegetation_scale_urban)
           norm_perim(0, jlay) =
               4.0 * veg_fraction[jlay] *
-              std::max(0.0, 1.0 - veg_fraction[jlay] - building_fraction[jlay]) /
-              (std::max(cfg.min_building_fraction, 1.0 - building_fraction[jlay]) *
+              rmax(0.0, 1.0 - veg_fraction[jlay] - building_fraction[jlay]) /
+              (rmax(cfg.min_building_fraction, 1.0 - building_fraction[jlay]) *
                veg_scale[jlay]);
         else
           norm_perim(0, jlay) = 4.0 * veg_fraction[jlay] / veg_scale[jlay];
@@ -260,7 +260,7 @@ static void calc_norm_perim_urban(const ssb200_config &cfg, int nlay, int nreg,
             norm_perim(1, jlay) =
                 (1.0 - fiso) * 4.0 * (0.5 * veg_fraction[jlay]) *
                 (1.0 - (0.5 * veg_fraction[jlay]) - building_fraction[jlay]) /
-                (std::max(cfg.min_building_fraction, 1.0 - building_fraction[jlay]) *
+                (rmax(cfg.min_building_fraction, 1.0 - building_fraction[jlay]) *
                  veg_scale[jlay]);
           else
             norm_perim(1, jlay) =
@@ -305,14 +305,14 @@ static void calc_norm_perim_urban(const ssb200_config &cfg, int nlay, int nreg,
 // ---------------------------------------------------------------------------
 
 // calc_view_factors_inf: radsurf_view_factor.F90:28-70.
-static void calc_view_factors_inf(double hw, double &view_ground_sky, double &view_wall_wall,
-                                  const double *cos_sza, double *view_dir_ground) {
+static void calc_view_factors_inf(real hw, real &view_ground_sky, real &view_wall_wall,
+                                  const real *cos_sza, real *view_dir_ground) {
   view_ground_sky = std::sqrt(hw * hw + 1.0) - hw;
   view_wall_wall = std::sqrt(1.0 / (hw * hw) + 1.0) - 1.0 / hw;
   if (cos_sza && view_dir_ground) {
-    const double c = *cos_sza;
-    const double norm_x0 = (kPi * 0.5) * hw * std::sqrt(1.0 / (c * c) - 1.0);
-    const double y_over_w = std::sqrt(std::max(norm_x0 * norm_x0 - 1.0, 0.0));
+    const real c = *cos_sza;
+    const real norm_x0 = (kPi * 0.5) * hw * std::sqrt(1.0 / (c * c) - 1.0);
+    const real y_over_w = std::sqrt(rmax(norm_x0 * norm_x0 - 1.0, 0.0));
     if (y_over_w > 0.0)
       *view_dir_ground = (2.0 / kPi) * (y_over_w - norm_x0 + std::atan(1.0 / y_over_w));
     else
@@ -321,17 +321,17 @@ static void calc_view_factors_inf(double hw, double &view_ground_sky, double &vi
 }
 
 // calc_view_factors_exp: radsurf_view_factor.F90:76-138.
-static void calc_view_factors_exp(double hx, double &view_ground_sky, double &view_wall_wall,
-                                  const double *cos_sza, double *view_dir_ground) {
+static void calc_view_factors_exp(real hx, real &view_ground_sky, real &view_wall_wall,
+                                  const real *cos_sza, real *view_dir_ground) {
   static const int nw = 8;
-  static const double weights[nw] = {0.0506142681451884, 0.111190517226687, 0.156853322938944,
+  static const real weights[nw] = {0.0506142681451884, 0.111190517226687, 0.156853322938944,
                                      0.181341891689181,  0.181341891689181, 0.156853322938944,
                                      0.111190517226687,  0.0506142681451884};
-  static const double nodes[nw] = {0.0198550717512319, 0.101666761293187, 0.237233795041836,
+  static const real nodes[nw] = {0.0198550717512319, 0.101666761293187, 0.237233795041836,
                                    0.408282678752175,  0.591717321247825, 0.762766204958164,
                                    0.898333238706813,  0.980144928248768};
-  double hweight[nw], vweight[nw], tk[nw], exp_tk[nw];
-  double sh = 0.0, sv = 0.0;
+  real hweight[nw], vweight[nw], tk[nw], exp_tk[nw];
+  real sh = 0.0, sv = 0.0;
   for (int i = 0; i < nw; ++i) sh += weights[i] * nodes[i];
   for (int i = 0; i < nw; ++i) hweight[i] = weights[i] * nodes[i] / sh;
   for (int i = 0; i < nw; ++i) vweight[i] = weights[i] * std::sqrt(1.0 - nodes[i] * nodes[i]);
@@ -341,14 +341,14 @@ static void calc_view_factors_exp(double hx, double &view_ground_sky, double &vi
     tk[i] = hx * std::sqrt(1.0 / (nodes[i] * nodes[i]) - 1.0);
     exp_tk[i] = std::exp(-tk[i]);
   }
-  double s1 = 0.0, s2 = 0.0;
+  real s1 = 0.0, s2 = 0.0;
   for (int i = 0; i < nw; ++i) s1 += hweight[i] * exp_tk[i];
   for (int i = 0; i < nw; ++i) s2 += vweight[i] * (1.0 - exp_tk[i]) / tk[i];
   view_ground_sky = s1;
   view_wall_wall = 1.0 - s2;
   if (cos_sza && view_dir_ground) {
-    const double c = *cos_sza;
-    const double norm_x0 = hx * std::sqrt(1.0 / (c * c) - 1.0);
+    const real c = *cos_sza;
+    const real norm_x0 = hx * std::sqrt(1.0 / (c * c) - 1.0);
     *view_dir_ground = std::exp(-norm_x0);
   }
 }
@@ -418,8 +418,8 @@ static void flux_zero(ssb200_canopy_flux *f, int icol, int ilay1, int ilay2) {
   }
 }
 
-static inline double vsum(const Vec &v, int i0, int n) {
-  double s = 0.0;
+static inline real vsum(const Vec &v, int i0, int n) {
+  real s = 0.0;
   for (int i = i0; i < i0 + n; ++i) s += v[i];
   return s;
 }
@@ -437,7 +437,7 @@ struct Ctx {
 // icol and ilay1 are 0-based.
 // ---------------------------------------------------------------------------
 static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, int nreg,
-                         int nlay, int icol, int ilay1, const LegendreGauss &lg, double cos_sza,
+                         int nlay, int icol, int ilay1, const LegendreGauss &lg, real cos_sza,
                          const ssb200_canopy_properties &cp,
                          const ssb200_sw_spectral_properties &sw, const double *ground_albedo_diff,
                          const double *ground_albedo_dir, double *top_albedo_diff,
@@ -454,14 +454,14 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
   const double *veg_fsd = cp.veg_fsd ? cp.veg_fsd + ilay1 : nullptr;
 #define SP(arr, g, jlay) (sw.arr[(g) + (size_t)nsw * (ilay1 + (jlay))])
   // urban_sw:268 clamps; forest_sw uses the raw value except inside tan0 (App. B7)
-  const double zcos_sza = urban ? std::max(cos_sza, 1.0e-6) : cos_sza;
+  const real zcos_sza = urban ? rmax(cos_sza, 1.0e-6) : cos_sza;
   const bool do_vegetation = (nreg > 1);
-  double sin0 = 0.0, tan0;
+  real sin0 = 0.0, tan0;
   if (urban) {
     sin0 = std::sqrt(1.0 - zcos_sza * zcos_sza);
     tan0 = sin0 / zcos_sza;
   } else {
-    tan0 = std::sqrt(1.0 - cos_sza * cos_sza) / std::max(cos_sza, 1.0e-6);
+    tan0 = std::sqrt(1.0 - cos_sza * cos_sza) / rmax(cos_sza, 1.0e-6);
   }
 
   // Region fractions (urban_sw:284-291, forest_sw:244-248)
@@ -471,8 +471,8 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
     frac(0, nlay) = 1.0;
     if (do_vegetation) {
       for (int j = 0; j < nlay; ++j) {
-        frac(0, j) = std::max(0.0, frac(0, j) - veg_fraction[j]);
-        const double fv = std::max(0.0, 1.0 - building_fraction[j] - frac(0, j)) / (double)(nreg - 1);
+        frac(0, j) = rmax(0.0, frac(0, j) - veg_fraction[j]);
+        const real fv = rmax(0.0, 1.0 - building_fraction[j] - frac(0, j)) / (real)(nreg - 1);
         for (int r = 1; r < nreg; ++r) frac(r, j) = fv;
       }
       for (int r = 1; r < nreg; ++r) frac(r, nlay) = 0.0;
@@ -480,7 +480,7 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
   } else {
     for (int j = 0; j < nlay; ++j) {
       frac(0, j) = 1.0 - veg_fraction[j];
-      for (int r = 1; r < nreg; ++r) frac(r, j) = veg_fraction[j] / (double)(nreg - 1);
+      for (int r = 1; r < nreg; ++r) frac(r, j) = veg_fraction[j] / (real)(nreg - 1);
     }
     frac(0, nlay) = 1.0;
     for (int r = 1; r < nreg; ++r) frac(r, nlay) = 0.0;
@@ -490,7 +490,7 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
     roof_fraction[nlay] = 0.0;
     roof_fraction[nlay - 1] = building_fraction[nlay - 1];
     for (int j = 0; j < nlay - 1; ++j)
-      roof_fraction[j] = std::max(0.0, building_fraction[j] - building_fraction[j + 1]);
+      roof_fraction[j] = rmax(0.0, building_fraction[j] - building_fraction[j + 1]);
     non_building_fraction[nlay] = 1.0;
     for (int j = 0; j < nlay; ++j) non_building_fraction[j] = 1.0 - building_fraction[j];
   }
@@ -498,9 +498,9 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
   // Most transparent interval (urban_sw:310): first minimum of column OD
   int itransp = 0;
   {
-    double best = 0.0;
+    real best = 0.0;
     for (int g = 0; g < nsw; ++g) {
-      double od = 0.0;
+      real od = 0.0;
       for (int j = 0; j < nlay; ++j) od += SP(air_ext, g, j) * dz[j];
       if (g == 0 || od < best) {
         best = od;
@@ -572,7 +572,7 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
       if (non_building_fraction[jlay] <= cfg.min_building_fraction) {
         f_wall_dir_clear[jlay] = 0.0;
       } else {
-        double s = 0.0;
+        real s = 0.0;
         for (jreg = 0; jreg < nreg; ++jreg) s += norm_perim_wall(jreg, jlay);
         f_wall_dir_clear[jlay] = s / (kPi * non_building_fraction[jlay]);
       }
@@ -593,18 +593,18 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
       if (nreg == 2) {
         ext_reg[1] = SP(air_ext, g, jlay) + veg_ext[jlay];
         ssa_reg[1] = (ext_reg[0] * ssa_reg[0] + veg_ext[jlay] * SP(veg_ssa, g, jlay)) /
-                     std::max(ext_reg[1], 1.0e-8);
+                     rmax(ext_reg[1], 1.0e-8);
       } else if (nreg == 3) {
         ext_reg[1] = SP(air_ext, g, jlay) + od_scaling(1, jlay) * veg_ext[jlay];
         ext_reg[2] = SP(air_ext, g, jlay) + od_scaling(2, jlay) * veg_ext[jlay];
         ssa_reg[1] = (ext_reg[0] * ssa_reg[0] +
                       od_scaling(1, jlay) * veg_ext[jlay] * SP(veg_ssa, g, jlay)) /
-                     std::max(ext_reg[1], 1.0e-8);
+                     rmax(ext_reg[1], 1.0e-8);
         ssa_reg[2] = (ext_reg[0] * ssa_reg[0] +
                       od_scaling(2, jlay) * veg_ext[jlay] * SP(veg_ssa, g, jlay)) /
-                     std::max(ext_reg[2], 1.0e-8);
+                     rmax(ext_reg[2], 1.0e-8);
       }
-      double wall_ext = 0.0, wall_factor = 0.0;
+      real wall_ext = 0.0, wall_factor = 0.0;
       if (urban) { // urban_sw:414-418
         wall_ext = 1.0 - SP(wall_albedo, g, jlay) * SP(wall_specular_frac, g, jlay);
         wall_factor = SP(wall_albedo, g, jlay) * (1.0 - SP(wall_specular_frac, g, jlay));
@@ -740,7 +740,7 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
   for (int g = 0; g < nsw; ++g) {
     Vec y = matvec(sub(a_above[L(g, nlay)], 0, ns, 0, ns), lg.hweight);
     talb_diff[g] = vsum(y, 0, ns);
-    double s = 0.0;
+    real s = 0.0;
     for (int js = 0; js < ns; ++js) s += d_above[L(g, nlay)](js, 0);
     talb_dir[g] = s / zcos_sza;
     top_albedo_diff[g] = talb_diff[g];
@@ -761,7 +761,7 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
     FC(ndir, top_net, g) = FC(ndir, top_dn_dir, g) * (1.0 - talb_dir[g]);
   }
   if (urban && ndir->roof_sunlit_frac) ndir->roof_sunlit_frac[ilay2] = 1.0;
-  double flux_dn_dir_clear = 1.0 / zcos_sza;
+  real flux_dn_dir_clear = 1.0 / zcos_sza;
 
   for (int jlay = nlay - 1; jlay >= 0; --jlay) {
     const int ilay = ilay1 + jlay;
@@ -801,21 +801,21 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
       Vec int_flux_diff = matvec(int_diff[k], conv) + matvec(int_dir_diff[k], dir_b - dn_dir_above[g]);
 
       auto sum_over_mu = [&](int jreg) {
-        double s = 0.0;
+        real s = 0.0;
         for (int js = 0; js < ns; ++js) s += int_flux_diff[jreg * ns + js] * (1.0 / lg.mu[js]);
         return s;
       };
       auto sum_tan = [&](int jreg) {
-        double s = 0.0;
+        real s = 0.0;
         for (int js = 0; js < ns; ++js) s += int_flux_diff[jreg * ns + js] * lg.tan_ang[js];
         return s;
       };
-      const double air_abs = SP(air_ext, g, jlay) * (1.0 - SP(air_ssa, g, jlay));
+      const real air_abs = SP(air_ext, g, jlay) * (1.0 - SP(air_ssa, g, jlay));
       FL(ndir, clear_air_abs, g, ilay) =
           FL(ndir, clear_air_abs, g, ilay) + air_abs * (int_flux_dir[0] + sum_over_mu(0));
       if (do_vegetation) {
         for (int jreg = 1; jreg < nreg; ++jreg) {
-          const double vabs = veg_ext[jlay] * (1.0 - SP(veg_ssa, g, jlay));
+          const real vabs = veg_ext[jlay] * (1.0 - SP(veg_ssa, g, jlay));
           FL(ndir, veg_air_abs, g, ilay) =
               FL(ndir, veg_air_abs, g, ilay) + air_abs * (int_flux_dir[jreg] + sum_over_mu(jreg));
           FL(ndir, veg_abs_dir, g, ilay) =
@@ -839,12 +839,12 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
     if (urban) {
       ndir->roof_sunlit_frac[ilay] =
           FL(ndir, roof_in_dir, itransp, ilay) * non_building_fraction[jlay + 1] /
-          (zcos_sza * flux_dn_dir_clear * std::max(cfg.min_building_fraction, roof_fraction[jlay]));
+          (zcos_sza * flux_dn_dir_clear * rmax(cfg.min_building_fraction, roof_fraction[jlay]));
       flux_dn_dir_clear =
           flux_dn_dir_clear * non_building_fraction[jlay] / non_building_fraction[jlay + 1];
     }
-    const double trans_dir_clear = std::exp(-SP(air_ext, itransp, jlay) * dz[jlay] / zcos_sza);
-    double int_flux_dir_clear;
+    const real trans_dir_clear = std::exp(-SP(air_ext, itransp, jlay) * dz[jlay] / zcos_sza);
+    real int_flux_dir_clear;
     if (SP(air_ext, itransp, jlay) > 0.0)
       int_flux_dir_clear =
           flux_dn_dir_clear * (1.0 - trans_dir_clear) * zcos_sza / SP(air_ext, itransp, jlay);
@@ -853,16 +853,16 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
     if (urban ? do_vegetation : true) {
       // forest computes this unconditionally (forest_sw: veg_sunlit_frac)
       if (veg_ext && veg_fraction && sw.veg_ssa && ndir->veg_sunlit_frac) {
-        const double veg_abs_dir_clear = int_flux_dir_clear * veg_ext[jlay] *
+        const real veg_abs_dir_clear = int_flux_dir_clear * veg_ext[jlay] *
                                          (1.0 - SP(veg_ssa, itransp, jlay)) * veg_fraction[jlay];
         ndir->veg_sunlit_frac[ilay] =
-            FL(ndir, veg_abs_dir, itransp, ilay) / std::max(kEps, veg_abs_dir_clear);
+            FL(ndir, veg_abs_dir, itransp, ilay) / rmax(kEps, veg_abs_dir_clear);
       }
     }
     if (urban)
       ndir->wall_sunlit_frac[ilay] =
           0.5 * FL(ndir, wall_in_dir, itransp, ilay) /
-          std::max(kEps, (f_wall_dir_clear[jlay] * sin0 * int_flux_dir_clear));
+          rmax(kEps, (f_wall_dir_clear[jlay] * sin0 * int_flux_dir_clear));
     flux_dn_dir_clear = flux_dn_dir_clear * trans_dir_clear;
   }
   for (int g = 0; g < nsw; ++g) {
@@ -912,20 +912,20 @@ static void spartacus_sw(bool urban, const ssb200_config &cfg, int nsw, int ns, 
       for (int i = 0; i < n; ++i) conv[i] = diff_b[i] - dn_diff_above[g][i] - up_b[i] + up_above[g][i];
       Vec int_flux_diff = matvec(int_diff[k], conv);
       auto sum_over_mu = [&](int jreg) {
-        double s = 0.0;
+        real s = 0.0;
         for (int js = 0; js < ns; ++js) s += int_flux_diff[jreg * ns + js] * (1.0 / lg.mu[js]);
         return s;
       };
       auto sum_tan = [&](int jreg) {
-        double s = 0.0;
+        real s = 0.0;
         for (int js = 0; js < ns; ++js) s += int_flux_diff[jreg * ns + js] * lg.tan_ang[js];
         return s;
       };
-      const double air_abs = SP(air_ext, g, jlay) * (1.0 - SP(air_ssa, g, jlay));
+      const real air_abs = SP(air_ext, g, jlay) * (1.0 - SP(air_ssa, g, jlay));
       FL(ndiff, clear_air_abs, g, ilay) = FL(ndiff, clear_air_abs, g, ilay) + air_abs * sum_over_mu(0);
       if (do_vegetation) {
         for (int jreg = 1; jreg < nreg; ++jreg) {
-          const double vabs = veg_ext[jlay] * (1.0 - SP(veg_ssa, g, jlay));
+          const real vabs = veg_ext[jlay] * (1.0 - SP(veg_ssa, g, jlay));
           FL(ndiff, veg_air_abs, g, ilay) = FL(ndiff, veg_air_abs, g, ilay) + air_abs * sum_over_mu(jreg);
           FL(ndiff, veg_abs, g, ilay) =
               FL(ndiff, veg_abs, g, ilay) + vabs * sum_over_mu(jreg) * od_scaling(jreg, jlay);
@@ -982,8 +982,8 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
     frac(0, nlay) = 1.0;
     if (do_vegetation) {
       for (int j = 0; j < nlay; ++j) {
-        frac(0, j) = std::max(0.0, frac(0, j) - veg_fraction[j]);
-        const double fv = std::max(0.0, 1.0 - building_fraction[j] - frac(0, j)) / (double)(nreg - 1);
+        frac(0, j) = rmax(0.0, frac(0, j) - veg_fraction[j]);
+        const real fv = rmax(0.0, 1.0 - building_fraction[j] - frac(0, j)) / (real)(nreg - 1);
         for (int r = 1; r < nreg; ++r) frac(r, j) = fv;
       }
       for (int r = 1; r < nreg; ++r) frac(r, nlay) = 0.0;
@@ -992,7 +992,7 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
     frac(0, nlay) = 1.0;
     for (int j = 0; j < nlay; ++j) {
       frac(0, j) = 1.0 - veg_fraction[j];
-      for (int r = 1; r < nreg; ++r) frac(r, j) = (1.0 - frac(0, j)) / (double)(nreg - 1);
+      for (int r = 1; r < nreg; ++r) frac(r, j) = (1.0 - frac(0, j)) / (real)(nreg - 1);
     }
     for (int r = 1; r < nreg; ++r) frac(r, nlay) = 0.0;
   }
@@ -1062,7 +1062,7 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
           std::exp(-veg_fsd[jlay] * (1.0 + 0.5 * veg_fsd[jlay] * (1.0 + 0.5 * veg_fsd[jlay])));
       od_scaling(2, jlay) = 2.0 - od_scaling(1, jlay);
     }
-    double emiss_factor = 0.0; // urban_lw:447
+    real emiss_factor = 0.0; // urban_lw:447
     for (int js = 0; js < ns; ++js) emiss_factor += lg.hweight[js] / lg.mu[js];
     emiss_factor = 2.0 * emiss_factor;
 
@@ -1074,26 +1074,26 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
       if (nreg == 2) {
         ext_reg[1] = LP(air_ext, g, jlay) + veg_ext[jlay];
         ssa_reg[1] = (ext_reg[0] * ssa_reg[0] + veg_ext[jlay] * LP(veg_ssa, g, jlay)) /
-                     std::max(ext_reg[1], 1.0e-8);
+                     rmax(ext_reg[1], 1.0e-8);
         planck_reg[1] = (ext_reg[0] * (1.0 - ssa_reg[0]) * LP(veg_air_planck, g, jlay) +
                          veg_ext[jlay] * (1.0 - LP(veg_ssa, g, jlay)) * LP(veg_planck, g, jlay)) /
-                        std::max(ext_reg[1] * (1.0 - ssa_reg[1]), 1.0e-8);
+                        rmax(ext_reg[1] * (1.0 - ssa_reg[1]), 1.0e-8);
       } else if (nreg == 3) {
         for (int r = 1; r < 3; ++r) {
           ext_reg[r] = LP(air_ext, g, jlay) + od_scaling(r, jlay) * veg_ext[jlay];
           ssa_reg[r] = (ext_reg[0] * ssa_reg[0] +
                         od_scaling(r, jlay) * veg_ext[jlay] * LP(veg_ssa, g, jlay)) /
-                       std::max(ext_reg[r], 1.0e-8);
+                       rmax(ext_reg[r], 1.0e-8);
         }
         for (int r = 1; r < 3; ++r)
           planck_reg[r] = (ext_reg[0] * (1.0 - ssa_reg[0]) * LP(veg_air_planck, g, jlay) +
                            od_scaling(r, jlay) * veg_ext[jlay] * (1.0 - LP(veg_ssa, g, jlay)) *
                                LP(veg_planck, g, jlay)) /
-                          std::max(ext_reg[r] * (1.0 - ssa_reg[r]), 1.0e-8);
+                          rmax(ext_reg[r] * (1.0 - ssa_reg[r]), 1.0e-8);
       }
-      const double wall_ext = 1.0;
+      const real wall_ext = 1.0;
       // sic: spectral index 1 for every interval (urban_lw:392, App. B2)
-      const double wall_factor = urban ? 1.0 - LP(wall_emissivity, 0, jlay) : 0.0;
+      const real wall_factor = urban ? 1.0 - LP(wall_emissivity, 0, jlay) : 0.0;
 
       Mat gamma1(n, n), gamma2(n, n);
       for (int jreg_fr = 0; jreg_fr < nreg; ++jreg_fr)
@@ -1130,9 +1130,9 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
       const size_t k = L(g, jlay);
       Vec emiss_rate(n, 0.0);
       for (jreg = 0; jreg < nreg; ++jreg) {
-        const double volume_emiss =
+        const real volume_emiss =
             frac(jreg, jlay) * (ext_reg[jreg] * (1.0 - ssa_reg[jreg]) * planck_reg[jreg]);
-        double wall_emiss = 0.0;
+        real wall_emiss = 0.0;
         if (urban) wall_emiss = norm_perim_wall(jreg, jlay) * lg.vadjustment * LP(wall_emission, g, jlay);
         for (int js = 0; js < ns; ++js) {
           const int ifr = js + jreg * ns;
@@ -1152,7 +1152,7 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
         }
       }
       if (urban) {
-        double s = 0.0;
+        real s = 0.0;
         for (jreg = 0; jreg < nreg; ++jreg) s += norm_perim_wall(jreg, jlay);
         emiss_wall[k] = (s * lg.vadjustment) * LP(wall_emission, g, jlay);
       }
@@ -1195,8 +1195,8 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
   std::vector<Vec> source_above(nlw * (nlay + 1), Vec(n, 0.0)), source_below(nlw * (nlay + 1), Vec(m, 0.0));
   std::vector<Mat> denominator(nlw * nlay, Mat(n, n));
   for (int g = 0; g < nlw; ++g) {
-    const double ground_emissivity = lw.ground_emissivity[g + (size_t)nlw * icol];
-    const double ground_emission = lw.ground_emission[g + (size_t)nlw * icol];
+    const real ground_emissivity = lw.ground_emissivity[g + (size_t)nlw * icol];
+    const real ground_emission = lw.ground_emission[g + (size_t)nlw * icol];
     for (int jreg = 0; jreg < nreg; ++jreg) {
       for (int js_to = 0; js_to < ns; ++js_to)
         for (int js_fr = 0; js_fr < ns; ++js_fr)
@@ -1216,9 +1216,9 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
       paste(a_below[k1], 0, 0, ab);
       for (int i = 0; i < n; ++i) source_below[k1][i] = sb[i];
       if (urban) {
-        double exposed_roof_frac;
+        real exposed_roof_frac;
         if (jlay < nlay - 1)
-          exposed_roof_frac = std::max(0.0, building_fraction[jlay] - building_fraction[jlay + 1]);
+          exposed_roof_frac = rmax(0.0, building_fraction[jlay] - building_fraction[jlay + 1]);
         else
           exposed_roof_frac = building_fraction[jlay];
         for (int js = 0; js < ns; ++js) {
@@ -1271,21 +1271,21 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
       }
       Vec int_flux = matvec(int_flux_mat[k], dn_b + up_above[g]) + int_source[k];
       auto sum_over_mu = [&](int jreg) {
-        double s = 0.0;
+        real s = 0.0;
         for (int js = 0; js < ns; ++js) s += int_flux[jreg * ns + js] * (1.0 / lg.mu[js]);
         return s;
       };
       auto sum_tan = [&](int jreg) {
-        double s = 0.0;
+        real s = 0.0;
         for (int js = 0; js < ns; ++js) s += int_flux[jreg * ns + js] * lg.tan_ang[js];
         return s;
       };
-      const double air_abs = LP(air_ext, g, jlay) * (1.0 - LP(air_ssa, g, jlay));
+      const real air_abs = LP(air_ext, g, jlay) * (1.0 - LP(air_ssa, g, jlay));
       FL(lint, clear_air_abs, g, ilay) =
           FL(lint, clear_air_abs, g, ilay) + air_abs * sum_over_mu(0) - emiss_reg[k][0] * dz[jlay];
       if (do_vegetation) {
         for (int jreg = 1; jreg < nreg; ++jreg) {
-          const double vabs = veg_ext[jlay] * (1.0 - LP(veg_ssa, g, jlay));
+          const real vabs = veg_ext[jlay] * (1.0 - LP(veg_ssa, g, jlay));
           FL(lint, veg_air_abs, g, ilay) =
               FL(lint, veg_air_abs, g, ilay) + air_abs * sum_over_mu(jreg) - emiss_air[k][jreg] * dz[jlay];
           FL(lint, veg_abs, g, ilay) = FL(lint, veg_abs, g, ilay) +
@@ -1340,20 +1340,20 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
       }
       Vec int_flux = matvec(int_flux_mat[k], dn_b + up_above[g]);
       auto sum_over_mu = [&](int jreg) {
-        double s = 0.0;
+        real s = 0.0;
         for (int js = 0; js < ns; ++js) s += int_flux[jreg * ns + js] * (1.0 / lg.mu[js]);
         return s;
       };
       auto sum_tan = [&](int jreg) {
-        double s = 0.0;
+        real s = 0.0;
         for (int js = 0; js < ns; ++js) s += int_flux[jreg * ns + js] * lg.tan_ang[js];
         return s;
       };
-      const double air_abs = LP(air_ext, g, jlay) * (1.0 - LP(air_ssa, g, jlay));
+      const real air_abs = LP(air_ext, g, jlay) * (1.0 - LP(air_ssa, g, jlay));
       FL(lnorm, clear_air_abs, g, ilay) = FL(lnorm, clear_air_abs, g, ilay) + air_abs * sum_over_mu(0);
       if (do_vegetation) {
         for (int jreg = 1; jreg < nreg; ++jreg) {
-          const double vabs = veg_ext[jlay] * (1.0 - LP(veg_ssa, g, jlay));
+          const real vabs = veg_ext[jlay] * (1.0 - LP(veg_ssa, g, jlay));
           FL(lnorm, veg_air_abs, g, ilay) = FL(lnorm, veg_air_abs, g, ilay) + air_abs * sum_over_mu(jreg);
           FL(lnorm, veg_abs, g, ilay) =
               FL(lnorm, veg_abs, g, ilay) + vabs * sum_over_mu(jreg) * od_scaling(jreg, jlay);
@@ -1387,37 +1387,37 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
 // is mirrored literally, guarded only against leaving the array.
 // ---------------------------------------------------------------------------
 static int simple_urban_sw(const ssb200_config &cfg, bool is_infinite_street, int nsw, int icol,
-                           int ilay, double cos_sza, const ssb200_canopy_properties &cp,
+                           int ilay, real cos_sza, const ssb200_canopy_properties &cp,
                            const ssb200_sw_spectral_properties &sw,
                            const double *ground_albedo_diff, const double *ground_albedo_dir,
                            ssb200_canopy_flux *ndir, ssb200_canopy_flux *ndiff) {
   if (ilay >= cp.ncol) return SSB200_ERR_ARG; // would index outside (nspec,ncol)
-  const double dz = cp.dz[ilay];
+  const real dz = cp.dz[ilay];
   const double building_fraction = cp.building_fraction[ilay];
   const double building_scale = cp.building_scale[ilay];
   double veg_fraction = 0.0, veg_scale = 1.0, veg_contact_fraction = 0.0;
   Mat norm_perim, norm_perim_wall;
   calc_norm_perim_urban(cfg, 1, 1, &building_fraction, &building_scale, &veg_fraction, &veg_scale,
                         &veg_contact_fraction, norm_perim, norm_perim_wall);
-  const double npw = norm_perim_wall(0, 0);
-  double view_ground_sky, view_wall_wall, view_dir_ground;
+  const real npw = norm_perim_wall(0, 0);
+  real view_ground_sky, view_wall_wall, view_dir_ground;
   if (is_infinite_street) {
-    const double street_width = 2.0 * (1.0 - building_fraction) / npw;
+    const real street_width = 2.0 * (1.0 - building_fraction) / npw;
     calc_view_factors_inf(dz / street_width, view_ground_sky, view_wall_wall, &cos_sza, &view_dir_ground);
   } else {
-    const double building_separation_scale = kPi * (1.0 - building_fraction) / npw;
+    const real building_separation_scale = kPi * (1.0 - building_fraction) / npw;
     calc_view_factors_exp(dz / building_separation_scale, view_ground_sky, view_wall_wall, &cos_sza,
                           &view_dir_ground);
   }
-  const double view_dir_wall = 1.0 - view_dir_ground;
-  const double view_wall_ground = 0.5 * (1.0 - view_wall_wall);
-  const double view_ground_wall = 1.0 - view_ground_sky;
+  const real view_dir_wall = 1.0 - view_dir_ground;
+  const real view_wall_ground = 0.5 * (1.0 - view_wall_wall);
+  const real view_ground_wall = 1.0 - view_ground_sky;
   flux_zero(ndiff, icol, ilay, ilay);
   flux_zero(ndir, icol, ilay, ilay);
 #define XC(f, member, g, c) (f->member[(g) + (size_t)nsw * (c)])
   for (int g = 0; g < nsw; ++g) {
-    const double roof_albedo = sw.roof_albedo[g + (size_t)nsw * ilay];
-    const double wall_albedo = sw.wall_albedo[g + (size_t)nsw * ilay];
+    const real roof_albedo = sw.roof_albedo[g + (size_t)nsw * ilay];
+    const real wall_albedo = sw.wall_albedo[g + (size_t)nsw * ilay];
     Mat im(2, 2);
     im(0, 0) = 1.0;
     im(0, 1) = -view_wall_ground * wall_albedo;
@@ -1440,10 +1440,10 @@ static int simple_urban_sw(const ssb200_config &cfg, bool is_infinite_street, in
     XC(ndir, wall_in_dir, g, ilay) = view_dir_wall * (1.0 - building_fraction);
     XC(ndir, wall_in, g, ilay) = sol[1];
     XC(ndir, wall_net, g, ilay) = XC(ndir, wall_in, g, ilay) * (1.0 - wall_albedo);
-    const double tan_sza = std::sqrt(1.0 / (cos_sza * cos_sza) - 1.0);
+    const real tan_sza = std::sqrt(1.0 / (cos_sza * cos_sza) - 1.0);
     ndir->wall_sunlit_frac[ilay] =
         0.5 * view_dir_wall /
-        (std::max(tan_sza, 1.0e-6) * npw * dz / (kPi * (1.0 - building_fraction)));
+        (rmax(tan_sza, 1.0e-6) * npw * dz / (kPi * (1.0 - building_fraction)));
     XC(ndir, top_dn_dir, g, icol) = 1.0;
     XC(ndir, top_dn, g, icol) = 1.0;
     XC(ndir, top_net, g, icol) =
@@ -1495,33 +1495,33 @@ static int simple_urban_lw(const ssb200_config &cfg, bool is_infinite_street, in
                            ssb200_canopy_flux *lnorm) {
   if (ilay >= cp.ncol) return SSB200_ERR_ARG;
   const int nsw = nlw;
-  const double dz = cp.dz[ilay];
+  const real dz = cp.dz[ilay];
   const double building_fraction = cp.building_fraction[ilay];
   const double building_scale = cp.building_scale[ilay];
   double veg_fraction = 0.0, veg_scale = 1.0, veg_contact_fraction = 0.0;
   Mat norm_perim, norm_perim_wall;
   calc_norm_perim_urban(cfg, 1, 1, &building_fraction, &building_scale, &veg_fraction, &veg_scale,
                         &veg_contact_fraction, norm_perim, norm_perim_wall);
-  const double npw = norm_perim_wall(0, 0);
-  double view_ground_sky, view_wall_wall;
+  const real npw = norm_perim_wall(0, 0);
+  real view_ground_sky, view_wall_wall;
   if (is_infinite_street) {
-    const double street_width = 2.0 * (1.0 - building_fraction) / npw;
+    const real street_width = 2.0 * (1.0 - building_fraction) / npw;
     calc_view_factors_inf(dz / street_width, view_ground_sky, view_wall_wall, nullptr, nullptr);
   } else {
-    const double building_separation_scale = kPi * (1.0 - building_fraction) / npw;
+    const real building_separation_scale = kPi * (1.0 - building_fraction) / npw;
     calc_view_factors_exp(dz / building_separation_scale, view_ground_sky, view_wall_wall, nullptr, nullptr);
   }
-  const double view_wall_ground = 0.5 * (1.0 - view_wall_wall);
-  const double view_ground_wall = 1.0 - view_ground_sky;
+  const real view_wall_ground = 0.5 * (1.0 - view_wall_wall);
+  const real view_ground_wall = 1.0 - view_ground_sky;
   flux_zero(lnorm, icol, ilay, ilay);
   flux_zero(lint, icol, ilay, ilay);
   for (int g = 0; g < nlw; ++g) {
-    const double ground_emissivity = lw.ground_emissivity[g + (size_t)nlw * icol];
-    const double ground_emission = lw.ground_emission[g + (size_t)nlw * icol];
-    const double roof_emissivity = lw.roof_emissivity[g + (size_t)nlw * ilay];
-    const double roof_emission = lw.roof_emission[g + (size_t)nlw * ilay];
-    const double wall_emissivity = lw.wall_emissivity[g + (size_t)nlw * ilay];
-    const double wall_emission = lw.wall_emission[g + (size_t)nlw * ilay];
+    const real ground_emissivity = lw.ground_emissivity[g + (size_t)nlw * icol];
+    const real ground_emission = lw.ground_emission[g + (size_t)nlw * icol];
+    const real roof_emissivity = lw.roof_emissivity[g + (size_t)nlw * ilay];
+    const real roof_emission = lw.roof_emission[g + (size_t)nlw * ilay];
+    const real wall_emissivity = lw.wall_emissivity[g + (size_t)nlw * ilay];
+    const real wall_emission = lw.wall_emission[g + (size_t)nlw * ilay];
     Mat im(2, 2);
     im(0, 0) = 1.0;
     im(0, 1) = -view_wall_ground * (1.0 - wall_emissivity);
@@ -1627,8 +1627,8 @@ static int radsurf_column(const ssb200_config &cfg, const ssb200_canopy_properti
     if (cfg.do_lw) {
       const int nspec_ = nlw;
       for (int g = 0; g < nlw; ++g) {
-        const double em = lw->ground_emissivity[g + (size_t)nlw * jcol];
-        const double es = lw->ground_emission[g + (size_t)nlw * jcol];
+        const real em = lw->ground_emissivity[g + (size_t)nlw * jcol];
+        const real es = lw->ground_emission[g + (size_t)nlw * jcol];
         bc->lw_emissivity[g + (size_t)nlw * jcol] = em;
         bc->lw_emission[g + (size_t)nlw * jcol] = es;
         CC(lint, ground_dn, g) = 0.0;
@@ -1723,6 +1723,14 @@ static int radsurf_column(const ssb200_config &cfg, const ssb200_canopy_properti
   return 0;
 }
 
+// FP64 <-> real at the C boundary (identity copies in the double builds)
+static void load_reals(real *dst, const double *src, size_t n) {
+  for (size_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+static void store_reals(double *dst, const real *src, size_t n) {
+  for (size_t i = 0; i < n; ++i) dst[i] = (double)src[i];
+}
+
 } // namespace orc
 
 // ---------------------------------------------------------------------------
@@ -1799,10 +1807,10 @@ int oracle_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
 int oracle_eigen_decomposition_real(int32_t n, const double *amat, double *eigenvalue, double *eigenvector) {
   orc::Mat A(n, n), V;
   orc::Vec w;
-  std::memcpy(A.a.data(), amat, sizeof(double) * n * n);
+  orc::load_reals(A.a.data(), amat, n * n);
   int nerr = orc::eigen_decomposition_real(n, A, w, V);
-  std::memcpy(eigenvalue, w.data(), sizeof(double) * n);
-  std::memcpy(eigenvector, V.a.data(), sizeof(double) * n * n);
+  orc::store_reals(eigenvalue, w.data(), n);
+  orc::store_reals(eigenvector, V.a.data(), n * n);
   return nerr;
 }
 
@@ -1811,20 +1819,20 @@ int oracle_calc_matrices_sw_eig(int32_t ndiff, int32_t ndir, double dz, double m
                                 double *reflectance, double *transmittance, double *s_up, double *s_dn,
                                 double *trans_dir, double *int_dir, double *int_diff, double *int_dir_diff) {
   orc::Mat g0(ndir, ndir), g1(ndiff, ndiff), g2(ndiff, ndiff), g3(ndiff, ndir);
-  std::memcpy(g0.a.data(), gamma0, sizeof(double) * ndir * ndir);
-  std::memcpy(g1.a.data(), gamma1, sizeof(double) * ndiff * ndiff);
-  std::memcpy(g2.a.data(), gamma2, sizeof(double) * ndiff * ndiff);
-  std::memcpy(g3.a.data(), gamma3, sizeof(double) * ndiff * ndir);
+  orc::load_reals(g0.a.data(), gamma0, ndir * ndir);
+  orc::load_reals(g1.a.data(), gamma1, ndiff * ndiff);
+  orc::load_reals(g2.a.data(), gamma2, ndiff * ndiff);
+  orc::load_reals(g3.a.data(), gamma3, ndiff * ndir);
   orc::Mat R, T, Su, Sd, E, Id, Idf, Idd;
   orc::calc_matrices_sw_eig(ndiff, ndir, dz, mu0, g0, g1, g2, g3, R, T, Su, Sd, E, Id, Idf, Idd);
-  std::memcpy(reflectance, R.a.data(), sizeof(double) * ndiff * ndiff);
-  std::memcpy(transmittance, T.a.data(), sizeof(double) * ndiff * ndiff);
-  std::memcpy(s_up, Su.a.data(), sizeof(double) * ndiff * ndir);
-  std::memcpy(s_dn, Sd.a.data(), sizeof(double) * ndiff * ndir);
-  std::memcpy(trans_dir, E.a.data(), sizeof(double) * ndir * ndir);
-  std::memcpy(int_dir, Id.a.data(), sizeof(double) * ndir * ndir);
-  std::memcpy(int_diff, Idf.a.data(), sizeof(double) * ndiff * ndiff);
-  std::memcpy(int_dir_diff, Idd.a.data(), sizeof(double) * ndiff * ndir);
+  orc::store_reals(reflectance, R.a.data(), ndiff * ndiff);
+  orc::store_reals(transmittance, T.a.data(), ndiff * ndiff);
+  orc::store_reals(s_up, Su.a.data(), ndiff * ndir);
+  orc::store_reals(s_dn, Sd.a.data(), ndiff * ndir);
+  orc::store_reals(trans_dir, E.a.data(), ndir * ndir);
+  orc::store_reals(int_dir, Id.a.data(), ndir * ndir);
+  orc::store_reals(int_diff, Idf.a.data(), ndiff * ndiff);
+  orc::store_reals(int_dir_diff, Idd.a.data(), ndiff * ndir);
   return 0;
 }
 
@@ -1832,31 +1840,31 @@ int oracle_calc_matrices_lw_eig(int32_t n, double dz, const double *gamma1, cons
                                 const double *emiss_rate, double *reflectance, double *transmittance,
                                 double *source, double *int_flux, double *int_flux_source) {
   orc::Mat g1(n, n), g2(n, n);
-  std::memcpy(g1.a.data(), gamma1, sizeof(double) * n * n);
-  std::memcpy(g2.a.data(), gamma2, sizeof(double) * n * n);
+  orc::load_reals(g1.a.data(), gamma1, n * n);
+  orc::load_reals(g2.a.data(), gamma2, n * n);
   orc::Vec b(emiss_rate, emiss_rate + n), src, isrc;
   orc::Mat R, T, IF;
   orc::calc_matrices_lw_eig(n, dz, g1, g2, b, R, T, src, IF, isrc);
-  std::memcpy(reflectance, R.a.data(), sizeof(double) * n * n);
-  std::memcpy(transmittance, T.a.data(), sizeof(double) * n * n);
-  std::memcpy(source, src.data(), sizeof(double) * n);
-  std::memcpy(int_flux, IF.a.data(), sizeof(double) * n * n);
-  std::memcpy(int_flux_source, isrc.data(), sizeof(double) * n);
+  orc::store_reals(reflectance, R.a.data(), n * n);
+  orc::store_reals(transmittance, T.a.data(), n * n);
+  orc::store_reals(source, src.data(), n);
+  orc::store_reals(int_flux, IF.a.data(), n * n);
+  orc::store_reals(int_flux_source, isrc.data(), n);
   return 0;
 }
 
 int oracle_schur_invert_sw(int32_t n0, int32_t n1, const double *g0, const double *g1, const double *g2,
                            const double *g3, double *g0i, double *g1i, double *g2i, double *g3i) {
   orc::Mat G0(n0, n0), G1(n1, n1), G2(n1, n1), G3(n1, n0), a, b, c, d;
-  std::memcpy(G0.a.data(), g0, sizeof(double) * n0 * n0);
-  std::memcpy(G1.a.data(), g1, sizeof(double) * n1 * n1);
-  std::memcpy(G2.a.data(), g2, sizeof(double) * n1 * n1);
-  std::memcpy(G3.a.data(), g3, sizeof(double) * n1 * n0);
+  orc::load_reals(G0.a.data(), g0, n0 * n0);
+  orc::load_reals(G1.a.data(), g1, n1 * n1);
+  orc::load_reals(G2.a.data(), g2, n1 * n1);
+  orc::load_reals(G3.a.data(), g3, n1 * n0);
   orc::schur_invert_sw(G0, G1, G2, G3, a, b, c, d);
-  std::memcpy(g0i, a.a.data(), sizeof(double) * n0 * n0);
-  std::memcpy(g1i, b.a.data(), sizeof(double) * n1 * n1);
-  std::memcpy(g2i, c.a.data(), sizeof(double) * n1 * n1);
-  std::memcpy(g3i, d.a.data(), sizeof(double) * n1 * n0);
+  orc::store_reals(g0i, a.a.data(), n0 * n0);
+  orc::store_reals(g1i, b.a.data(), n1 * n1);
+  orc::store_reals(g2i, c.a.data(), n1 * n1);
+  orc::store_reals(g3i, d.a.data(), n1 * n0);
   return 0;
 }
 

@@ -5,11 +5,16 @@
 namespace orc {
 
 thread_local double g_flops = 0.0;
+#if defined(ORACLE_QUAD)
+static const int kMaxQrIter = 90;
+#else
+static const int kMaxQrIter = 30;
+#endif
 
-static const double kPi = 3.14159265358979323846; // radiation_constants.F90:24
+static const real kPi = 3.14159265358979323846; // radiation_constants.F90:24
 
 // calc_legendre_gauss: radtool/radtool_legendre_gauss.F90:119-170.
-void calc_legendre_gauss(int nnode, double x1, double x2, Vec &xnode, Vec &weight) {
+void calc_legendre_gauss(int nnode, real x1, real x2, Vec &xnode, Vec &weight) {
   const int n = nnode;
   Vec ynode(n), ynode0(n), lgvm_deriv(n);
   std::vector<Vec> lgvm(n + 1, Vec(n)); // lgvm[k][node], k = 0..n
@@ -17,13 +22,13 @@ void calc_legendre_gauss(int nnode, double x1, double x2, Vec &xnode, Vec &weigh
     // "(0.27/nnode)" is a default-real (single precision) expression (:142)
     const float c027 = 0.27f / (float)n;
     ynode[jn - 1] = std::cos((2 * (jn - 1) + 1) * kPi / (2 * n)) +
-                    (double)c027 * std::sin(kPi * (-1.0 + 2.0 * jn) / (n + 1));
+                    (real)c027 * std::sin(kPi * (-1.0 + 2.0 * jn) / (n + 1));
     ynode0[jn - 1] = 2.0;
   }
-  const double eps = std::numeric_limits<double>::epsilon();
+  const real eps = std::numeric_limits<real>::epsilon();
   for (;;) {
-    double maxdiff = 0.0;
-    for (int i = 0; i < n; ++i) maxdiff = std::max(maxdiff, std::fabs(ynode[i] - ynode0[i]));
+    real maxdiff = 0.0;
+    for (int i = 0; i < n; ++i) maxdiff = rmax(maxdiff, std::fabs(ynode[i] - ynode0[i]));
     if (!(maxdiff > eps)) break;
     for (int i = 0; i < n; ++i) {
       lgvm[0][i] = 1.0;
@@ -44,7 +49,7 @@ void calc_legendre_gauss(int nnode, double x1, double x2, Vec &xnode, Vec &weigh
   for (int i = 0; i < n; ++i) {
     // sic: both terms use (1-y) (:165)
     xnode[i] = 0.5 * (x1 * (1.0 - ynode[i]) + x2 * (1.0 - ynode[i]));
-    weight[i] = (((n + 1) * (n + 1)) / (double)(n * n)) * (x2 - x1) /
+    weight[i] = (((n + 1) * (n + 1)) / (real)(n * n)) * (x2 - x1) /
                 ((1.0 - ynode[i] * ynode[i]) * lgvm_deriv[i] * lgvm_deriv[i]);
   }
 }
@@ -57,7 +62,7 @@ void legendre_gauss_initialize(LegendreGauss &lg, int nstream) {
   lg.tan_ang.resize(nstream);
   lg.hweight.resize(nstream);
   lg.vweight.resize(nstream);
-  double sumh = 0.0, sumv = 0.0;
+  real sumh = 0.0, sumv = 0.0;
   for (int i = 0; i < nstream; ++i) {
     lg.sin_ang[i] = std::sqrt(1.0 - lg.mu[i] * lg.mu[i]);
     lg.tan_ang[i] = lg.sin_ang[i] / lg.mu[i];
@@ -73,30 +78,30 @@ void legendre_gauss_initialize(LegendreGauss &lg, int nstream) {
     lg.vweight[i] = lg.vweight[i] / sumv;
   }
   lg.vadjustment = 1.0;
-  double s = 0.0;
+  real s = 0.0;
   for (int i = 0; i < nstream; ++i) s += lg.weight[i] * lg.sin_ang[i];
   lg.vadjustment2 = (kPi / 4.0) / s;
 }
 
-static inline double fsign(double a, double b) { // Fortran SIGN(a,b)
+static inline real fsign(real a, real b) { // Fortran SIGN(a,b)
   return std::signbit(b) ? -std::fabs(a) : std::fabs(a);
 }
 
 // eigen_decomposition_real: radtool/radtool_eigen_decomposition.F90:51-828
-// (ASYMTX of DISORT: balance, Hessenberg, shifted double-QR, back
+// (ASYMTX of DISORT: balance, Hessenberg, shifted real-QR, back
 // substitution).  1-based indexing is kept internally so that loop bounds and
 // the post-loop values of loop variables (App. B9) read like the Fortran.
 int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &eigenvector) {
-  const double Tol = std::numeric_limits<double>::epsilon();
-  const double C1 = 0.4375, C2 = 0.5, C3 = 0.75, C4 = 0.95, C5 = 16.0, C6 = 256.0;
+  const real Tol = std::numeric_limits<real>::epsilon();
+  const real C1 = 0.4375, C2 = 0.5, C3 = 0.75, C4 = 0.95, C5 = 16.0, C6 = 256.0;
   const int n = norder;
   eigenvalue.assign(n, 0.0);
   eigenvector = Mat(n, n);
   int nerror = 0;
 
   if (n > 2) {
-    std::vector<double> abal_((size_t)(n + 1) * (n + 1), 0.0), evec_((size_t)(n + 1) * (n + 1), 0.0);
-    std::vector<double> eval_(n + 1, 0.0), wkd(2 * n + 1, 0.0);
+    std::vector<real> abal_((size_t)(n + 1) * (n + 1), 0.0), evec_((size_t)(n + 1) * (n + 1), 0.0);
+    std::vector<real> eval_(n + 1, 0.0), wkd(2 * n + 1, 0.0);
 #define ABAL(i, j) abal_[(size_t)(i) + (size_t)(n + 1) * (j)]
 #define EVEC(i, j) evec_[(size_t)(i) + (size_t)(n + 1) * (j)]
     bool is_error = false;
@@ -104,10 +109,10 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
     for (int i = 1; i <= n; ++i)
       for (int j = 1; j <= n; ++j) ABAL(i, j) = amat(i - 1, j - 1);
 
-    double rnorm = 0.0;
+    real rnorm = 0.0;
     int ll = 1, kk = n;
     int ji = 0, jj = 0, jn = 0;
-    double tmp;
+    real tmp;
 
     // Search for rows isolating an eigenvalue and push them down (:184-222)
     bool not_finished = true;
@@ -115,7 +120,7 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
       not_finished = false;
       const int kkk = kk;
       for (jj = kkk; jj >= 1; --jj) {
-        double row = 0.0;
+        real row = 0.0;
         for (ji = 1; ji <= kk; ++ji)
           if (ji != jj) row = row + std::fabs(ABAL(jj, ji));
         // here ji == kk+1 (loop-exit value), so "ji /= kk" below is always true
@@ -148,7 +153,7 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
       not_finished = false;
       const int lll = ll;
       for (jj = lll; jj <= kk; ++jj) {
-        double column = 0.0;
+        real column = 0.0;
         for (ji = ll; ji <= kk; ++ji)
           if (ji != jj) column = column + std::fabs(ABAL(ji, jj));
         if (column == 0.0) {
@@ -180,15 +185,15 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
     while (not_finished) {
       not_finished = false;
       for (ji = ll; ji <= kk; ++ji) {
-        double column = 0.0, row = 0.0;
+        real column = 0.0, row = 0.0;
         for (jj = ll; jj <= kk; ++jj)
           if (jj != ji) {
             column = column + std::fabs(ABAL(jj, ji));
             row = row + std::fabs(ABAL(ji, jj));
           }
-        double ff = 1.0;
-        double gg = row / C5;
-        const double hh = column + row;
+        real ff = 1.0;
+        real gg = row / C5;
+        const real hh = column + row;
         while (column < gg) {
           ff = ff * C5;
           column = column * C6;
@@ -210,26 +215,26 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
     // Reduce to Hessenberg form and accumulate (:313-395)
     if (kk - 1 >= ll + 1) {
       for (jn = ll + 1; jn <= kk - 1; ++jn) {
-        double hh = 0.0;
+        real hh = 0.0;
         wkd[jn + n] = 0.0;
-        double scale = 0.0;
+        real scale = 0.0;
         for (ji = jn; ji <= kk; ++ji) scale = scale + std::fabs(ABAL(ji, jn - 1));
         if (scale != 0.0) {
           for (ji = kk; ji >= jn; --ji) {
             wkd[ji + n] = ABAL(ji, jn - 1) / scale;
             hh = hh + wkd[ji + n] * wkd[ji + n];
           }
-          double gg = -fsign(std::sqrt(hh), wkd[jn + n]);
+          real gg = -fsign(std::sqrt(hh), wkd[jn + n]);
           hh = hh - wkd[jn + n] * gg;
           wkd[jn + n] = wkd[jn + n] - gg;
           hh = 1.0 / hh;
           for (jj = jn; jj <= n; ++jj) {
-            double ff = 0.0;
+            real ff = 0.0;
             for (ji = kk; ji >= jn; --ji) ff = ff + wkd[ji + n] * ABAL(ji, jj);
             for (ji = jn; ji <= kk; ++ji) ABAL(ji, jj) = ABAL(ji, jj) - wkd[ji + n] * ff * hh;
           }
           for (ji = 1; ji <= kk; ++ji) {
-            double ff = 0.0;
+            real ff = 0.0;
             for (jj = kk; jj >= jn; --jj) ff = ff + wkd[jj + n] * ABAL(ji, jj);
             for (jj = jn; jj <= kk; ++jj) ABAL(ji, jj) = ABAL(ji, jj) - wkd[jj + n] * ff * hh;
           }
@@ -239,13 +244,13 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
       }
       for (jn = kk - 2; jn >= ll; --jn) {
         const int n1 = jn + 1, n2 = jn + 2;
-        double ff = ABAL(n1, jn);
+        real ff = ABAL(n1, jn);
         if (ff != 0.0) {
           ff = ff * wkd[jn + 1 + n];
           for (ji = n2; ji <= kk; ++ji) wkd[ji + n] = ABAL(ji, jn);
           if (n1 < kk) {
             for (jj = 1; jj <= n; ++jj) {
-              double gg = 0.0;
+              real gg = 0.0;
               for (ji = n1; ji <= kk; ++ji) gg = gg + wkd[ji + n] * EVEC(ji, jj);
               gg = gg / ff;
               for (ji = n1; ji <= kk; ++ji) EVEC(ji, jj) = EVEC(ji, jj) + gg * wkd[ji + n];
@@ -263,8 +268,8 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
       if (ji < ll || ji > kk) eval_[ji] = ABAL(ji, ji);
     }
     jn = kk;
-    double tt = 0.0;
-    double pp = 0, qq = 0, rr = 0, ss = 0, xx = 0, yy = 0, zz = 0, ww = 0, uu = 0, vv = 0;
+    real tt = 0.0;
+    real pp = 0, qq = 0, rr = 0, ss = 0, xx = 0, yy = 0, zz = 0, ww = 0, uu = 0, vv = 0;
 
     // Search for next eigenvalue (:411-635)
     not_finished = true;
@@ -327,15 +332,16 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
           not_finished = true;
           break;
         }
-        if (in == 30) {
-          // no convergence after 30 iterations (:498-510)
+        if (in == kMaxQrIter) {
+          // no convergence after 30 iterations (:498-510); the quad build gets more
+          // iterations: its tolerance is 1e-34, not 2e-16
           nerror = nerror + 1;
           is_error = true;
           not_finished = false;
           break;
         }
         // Form shift (:513-523)
-        if (in == 10 || in == 20) {
+        if (in == 10 || in == 20 || in == 40 || in == 60) {
           tt = tt + xx;
           for (ji = ll; ji <= jn; ++ji) ABAL(ji, ji) = ABAL(ji, ji) - xx;
           ss = std::fabs(ABAL(jn, n1)) + std::fabs(ABAL(n1, n2));
@@ -451,7 +457,7 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
         for (ji = 1; ji <= n; ++ji)
           if (ji < ll || ji > kk)
             for (jj = ji; jj <= n; ++jj) EVEC(ji, jj) = ABAL(ji, jj);
-        if ((double)kk != 0.0) { // sic (:672)
+        if ((real)kk != 0.0) { // sic (:672)
           for (jj = n; jj >= ll; --jj)
             for (ji = ll; ji <= kk; ++ji) {
               zz = 0.0;
@@ -490,12 +496,12 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
 #undef EVEC
   } else if (n == 2) {
     // :770-803
-    const double a11 = amat(0, 0), a12 = amat(0, 1), a21 = amat(1, 0), a22 = amat(1, 1);
-    const double discriminant = (a11 - a22) * (a11 - a22) + 4.0 * a12 * a21;
+    const real a11 = amat(0, 0), a12 = amat(0, 1), a21 = amat(1, 0), a22 = amat(1, 1);
+    const real discriminant = (a11 - a22) * (a11 - a22) + 4.0 * a12 * a21;
     if (discriminant < 0.0) nerror = nerror + 1;
     eigenvalue[0] = 0.5 * (a11 + a22);
     eigenvalue[1] = eigenvalue[0];
-    const double half_sqrt_disc = 0.5 * std::sqrt(discriminant);
+    const real half_sqrt_disc = 0.5 * std::sqrt(discriminant);
     if (a11 >= a22) {
       eigenvalue[0] = eigenvalue[0] + half_sqrt_disc;
       eigenvalue[1] = eigenvalue[1] - half_sqrt_disc;
@@ -507,7 +513,7 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
     eigenvector(1, 1) = 1.0;
     if (a11 == a22 && (a21 == 0.0 || a12 == 0.0)) {
       // sic: Tol multiplies only the first term (:795-797)
-      const double rnorm =
+      const real rnorm =
           1.0 / (Tol * std::fabs(a11) + std::fabs(a21) + std::fabs(a12) + std::fabs(a22));
       eigenvector(1, 0) = a21 * rnorm;
       eigenvector(0, 1) = a12 * rnorm;
@@ -561,7 +567,7 @@ static void direct_diffuse_part(int ndiff, int ndir, const Vec &exp_lambda_dz,
 }
 
 // calc_matrices_sw_eig: radtool/radtool_calc_matrices_sw_eig.F90:30-298.
-void calc_matrices_sw_eig(int ndiff, int ndir, double dz, double /*mu0 unused*/,
+void calc_matrices_sw_eig(int ndiff, int ndir, real dz, real /*mu0 unused*/,
                           const Mat &gamma0, const Mat &gamma1, const Mat &gamma2,
                           const Mat &gamma3, Mat &reflectance, Mat &transmittance, Mat &s_up,
                           Mat &s_dn, Mat &trans_dir, Mat &int_dir, Mat &int_diff,
@@ -574,7 +580,7 @@ void calc_matrices_sw_eig(int ndiff, int ndir, double dz, double /*mu0 unused*/,
   eigen_decomposition_real(ndiff, gamma_product, eigenval_prod, eigenvec_prod);
   Vec lambda(ndiff), exp_lambda_dz(ndiff);
   for (int i = 0; i < ndiff; ++i) {
-    lambda[i] = std::sqrt(std::max(0.0, eigenval_prod[i]));
+    lambda[i] = std::sqrt(rmax(0.0, eigenval_prod[i]));
     exp_lambda_dz[i] = std::exp(-lambda[i] * dz);
   }
   Mat tmp_mat = neg(solve_mat(gamma_diff, eigenvec_prod));
@@ -631,7 +637,7 @@ void calc_matrices_sw_eig(int ndiff, int ndir, double dz, double /*mu0 unused*/,
 }
 
 // calc_matrices_lw_eig: radtool/radtool_calc_matrices_lw_eig.F90:32-230.
-void calc_matrices_lw_eig(int norder, double dz, const Mat &gamma1, const Mat &gamma2,
+void calc_matrices_lw_eig(int norder, real dz, const Mat &gamma1, const Mat &gamma2,
                           const Vec &emiss_rate, Mat &reflectance, Mat &transmittance,
                           Vec &source, Mat &int_flux, Vec &int_flux_source) {
   const int n = norder;
@@ -642,7 +648,7 @@ void calc_matrices_lw_eig(int norder, double dz, const Mat &gamma1, const Mat &g
   eigen_decomposition_real(n, gamma_product, eigenval_prod, eigenvec_prod);
   Vec lambda(n), exp_lambda_dz(n);
   for (int i = 0; i < n; ++i) {
-    lambda[i] = std::sqrt(std::max(0.0, eigenval_prod[i]));
+    lambda[i] = std::sqrt(rmax(0.0, eigenval_prod[i]));
     exp_lambda_dz[i] = std::exp(-lambda[i] * dz);
   }
   Mat tmp_mat = neg(solve_mat(gamma_diff, eigenvec_prod));

@@ -14,6 +14,9 @@
 // Every routine cites the reference file:line it follows
 // (paths relative to the reference root).
 #pragma once
+#if defined(ORACLE_QUAD)
+#include <stdfloat>
+#endif
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -22,20 +25,33 @@
 
 namespace orc {
 
+// Scalar type of the restatement.  `double` for the two builds the parity
+// tests and the CPU baseline use; `_Float128` (-DORACLE_QUAD) for the
+// extended-precision build that serves as ground truth: the reference
+// algorithm evaluated on the same FP64 inputs with 113 significant bits, so
+// that what remains is the conditioning of the algorithm, not rounding.
+#if defined(ORACLE_QUAD)
+typedef _Float128 real;
+#else
+typedef double real;
+#endif
+inline real rmax(real a, real b) { return (a < b) ? b : a; }  // std::max semantics
+inline real rmin(real a, real b) { return (b < a) ? b : a; }  // std::min semantics
+
 // One dense matrix of ONE spectral interval.  The reference stores
 // (nmat, i, j) with the spectral index fastest (radtool_matrix.F90:18-24) and
 // loops it innermost; no operation mixes spectral intervals, so looping the
 // interval outermost gives identical arithmetic per interval.
 struct Mat {
   int r = 0, c = 0;
-  std::vector<double> a;
+  std::vector<real> a;
   Mat() {}
   Mat(int r_, int c_) : r(r_), c(c_), a((size_t)r_ * c_, 0.0) {}
-  double &operator()(int i, int j) { return a[(size_t)i + (size_t)r * j]; }
-  double operator()(int i, int j) const { return a[(size_t)i + (size_t)r * j]; }
+  real &operator()(int i, int j) { return a[(size_t)i + (size_t)r * j]; }
+  real operator()(int i, int j) const { return a[(size_t)i + (size_t)r * j]; }
   void zero() { std::fill(a.begin(), a.end(), 0.0); }
 };
-typedef std::vector<double> Vec;
+typedef std::vector<real> Vec;
 
 inline Mat operator+(const Mat &A, const Mat &B) {
   Mat C(A.r, A.c);
@@ -94,7 +110,7 @@ inline Mat matmul(const Mat &A, const Mat &B) {
   Mat C(A.r, B.c);
   for (int j2 = 0; j2 < B.c; ++j2)
     for (int j3 = 0; j3 < A.c; ++j3) {
-      const double b = B(j3, j2);
+      const real b = B(j3, j2);
       for (int j1 = 0; j1 < A.r; ++j1) C(j1, j2) = C(j1, j2) + A(j1, j3) * b;
     }
   return C;
@@ -159,17 +175,17 @@ inline Mat lu_factorization(const Mat &A) {
   Mat LU = A;
   for (int j2 = 0; j2 < m; ++j2) {
     for (int j1 = 0; j1 < j2; ++j1) {
-      double s = LU(j1, j2);
+      real s = LU(j1, j2);
       for (int j3 = 0; j3 < j1; ++j3) s = s - LU(j1, j3) * LU(j3, j2);
       LU(j1, j2) = s;
     }
     for (int j1 = j2; j1 < m; ++j1) {
-      double s = LU(j1, j2);
+      real s = LU(j1, j2);
       for (int j3 = 0; j3 < j2; ++j3) s = s - LU(j1, j3) * LU(j3, j2);
       LU(j1, j2) = s;
     }
     if (j2 != m - 1) {
-      const double s = 1.0 / LU(j2, j2);
+      const real s = 1.0 / LU(j2, j2);
       for (int j1 = j2 + 1; j1 < m; ++j1) LU(j1, j2) = LU(j1, j2) * s;
     }
   }
@@ -205,6 +221,60 @@ inline Mat lu_invert(const Mat &LU) {
   return X;
 }
 
+#if defined(ORACLE_QUAD)
+// Ground-truth build only: Gaussian elimination WITH partial pivoting for every solve and
+// inverse.  In exact arithmetic it returns what the reference's LU without pivoting (and its
+// Cramer / explicit order-2 and order-3 forms) returns wherever that is defined; it also
+// returns the value of A^-1 B where the unpivoted form divides by a structurally zero pivot
+// (e.g. the eigenvector matrix of a layer without scattering: streams decouple, and the
+// order in which the QR iteration delivers the eigenvectors decides whether a zero lands on
+// the diagonal - test/simple/test_noscat_in.nc).  So the truth is the value of the
+// reference's FORMULAS, independent of the pivot order.
+inline Mat pivoted_solve(const Mat &A, const Mat &B) {
+  const int m = A.r, nb = B.c;
+  Mat W = A, X = B;
+  for (int k = 0; k < m; ++k) {
+    int p = k;
+    real best = std::fabs(W(k, k));
+    for (int i = k + 1; i < m; ++i)
+      if (std::fabs(W(i, k)) > best) {
+        best = std::fabs(W(i, k));
+        p = i;
+      }
+    if (p != k) {
+      for (int j = 0; j < m; ++j) std::swap(W(k, j), W(p, j));
+      for (int j = 0; j < nb; ++j) std::swap(X(k, j), X(p, j));
+    }
+    const real inv = 1.0 / W(k, k);
+    for (int i = k + 1; i < m; ++i) {
+      const real l = W(i, k) * inv;
+      if (l == 0.0) continue;
+      for (int j = k + 1; j < m; ++j) W(i, j) = W(i, j) - l * W(k, j);
+      for (int j = 0; j < nb; ++j) X(i, j) = X(i, j) - l * X(k, j);
+    }
+  }
+  for (int j = 0; j < nb; ++j)
+    for (int i = m - 1; i >= 0; --i) {
+      real s = X(i, j);
+      for (int k = i + 1; k < m; ++k) s = s - W(i, k) * X(k, j);
+      X(i, j) = s / W(i, i);
+    }
+  return X;
+}
+inline Mat solve_rect_mat(const Mat &A, const Mat &B) { return pivoted_solve(A, B); }
+inline Vec solve_vec(const Mat &A, const Vec &b) {
+  Mat B(A.r, 1);
+  for (int i = 0; i < A.r; ++i) B(i, 0) = b[i];
+  Mat X = pivoted_solve(A, B);
+  return Vec(X.a.begin(), X.a.end());
+}
+inline Mat solve_mat(const Mat &A, const Mat &B) { return pivoted_solve(A, B); }
+inline Mat invert(const Mat &A) {
+  Mat I(A.r, A.r);
+  for (int i = 0; i < A.r; ++i) I(i, i) = 1.0;
+  return pivoted_solve(A, I);
+}
+#else
 // solve_rect_mat radtool_matrix.F90:1119-1135 (always general LU).
 inline Mat solve_rect_mat(const Mat &A, const Mat &B) {
   Mat LU = lu_factorization(A);
@@ -223,20 +293,20 @@ inline Mat solve_rect_mat(const Mat &A, const Mat &B) {
 inline Vec solve_vec(const Mat &A, const Vec &b) {
   const int m = A.r;
   if (m == 2) {
-    const double inv_det = 1.0 / (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
+    const real inv_det = 1.0 / (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
     Vec x(2);
     x[0] = inv_det * (A(1, 1) * b[0] - A(0, 1) * b[1]);
     x[1] = inv_det * (A(0, 0) * b[1] - A(1, 0) * b[0]);
     return x;
   } else if (m == 3) {
-    const double L21 = A(1, 0) / A(0, 0);
-    const double L31 = A(2, 0) / A(0, 0);
-    const double U22 = A(1, 1) - L21 * A(0, 1);
-    const double U23 = A(1, 2) - L21 * A(0, 2);
-    const double L32 = (A(2, 1) - L31 * A(0, 1)) / U22;
-    const double U33 = A(2, 2) - L31 * A(0, 2) - L32 * U23;
-    const double y2 = b[1] - L21 * b[0];
-    const double y3 = b[2] - L31 * b[0] - L32 * y2;
+    const real L21 = A(1, 0) / A(0, 0);
+    const real L31 = A(2, 0) / A(0, 0);
+    const real U22 = A(1, 1) - L21 * A(0, 1);
+    const real U23 = A(1, 2) - L21 * A(0, 2);
+    const real L32 = (A(2, 1) - L31 * A(0, 1)) / U22;
+    const real U33 = A(2, 2) - L31 * A(0, 2) - L32 * U23;
+    const real y2 = b[1] - L21 * b[0];
+    const real y3 = b[2] - L31 * b[0] - L32 * y2;
     Vec x(3);
     x[2] = y3 / U33;
     x[1] = (y2 - U23 * x[2]) / U22;
@@ -252,22 +322,22 @@ inline Mat solve_mat(const Mat &A, const Mat &B) {
   const int m = A.r;
   Mat X(m, m);
   if (m == 2) {
-    const double inv_det = 1.0 / (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
+    const real inv_det = 1.0 / (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
     X(0, 0) = inv_det * (A(1, 1) * B(0, 0) - A(0, 1) * B(1, 0));
     X(1, 0) = inv_det * (A(0, 0) * B(1, 0) - A(1, 0) * B(0, 0));
     X(0, 1) = inv_det * (A(1, 1) * B(0, 1) - A(0, 1) * B(1, 1));
     X(1, 1) = inv_det * (A(0, 0) * B(1, 1) - A(1, 0) * B(0, 1));
     return X;
   } else if (m == 3) {
-    const double L21 = A(1, 0) / A(0, 0);
-    const double L31 = A(2, 0) / A(0, 0);
-    const double U22 = A(1, 1) - L21 * A(0, 1);
-    const double U23 = A(1, 2) - L21 * A(0, 2);
-    const double L32 = (A(2, 1) - L31 * A(0, 1)) / U22;
-    const double U33 = A(2, 2) - L31 * A(0, 2) - L32 * U23;
+    const real L21 = A(1, 0) / A(0, 0);
+    const real L31 = A(2, 0) / A(0, 0);
+    const real U22 = A(1, 1) - L21 * A(0, 1);
+    const real U23 = A(1, 2) - L21 * A(0, 2);
+    const real L32 = (A(2, 1) - L31 * A(0, 1)) / U22;
+    const real U33 = A(2, 2) - L31 * A(0, 2) - L32 * U23;
     for (int j = 0; j < 3; ++j) {
-      const double y2 = B(1, j) - L21 * B(0, j);
-      const double y3 = B(2, j) - L31 * B(0, j) - L32 * y2;
+      const real y2 = B(1, j) - L21 * B(0, j);
+      const real y3 = B(2, j) - L31 * B(0, j) - L32 * y2;
       X(2, j) = y3 / U33;
       X(1, j) = (y2 - U23 * X(2, j)) / U22;
       X(0, j) = (B(0, j) - A(0, 1) * X(1, j) - A(0, 2) * X(2, j)) / A(0, 0);
@@ -279,6 +349,7 @@ inline Mat solve_mat(const Mat &A, const Mat &B) {
 
 // invert radtool_matrix.F90:1203-1235 (general LU for every order).
 inline Mat invert(const Mat &A) { return lu_invert(lu_factorization(A)); }
+#endif
 
 // Column scaling A * diag(d): the `A * spread(d,2,n)` idiom
 // (radtool_calc_matrices_sw_eig.F90:194,205-206).
@@ -292,10 +363,10 @@ inline Mat scale_cols(const Mat &A, const Vec &d) {
 struct LegendreGauss {
   int nstream = 0;
   Vec mu, sin_ang, tan_ang, weight, hweight, vweight;
-  double vadjustment = 1.0, vadjustment2 = 1.0;
+  real vadjustment = 1.0, vadjustment2 = 1.0;
 };
 
-void calc_legendre_gauss(int nnode, double x1, double x2, Vec &xnode, Vec &weight);
+void calc_legendre_gauss(int nnode, real x1, real x2, Vec &xnode, Vec &weight);
 void legendre_gauss_initialize(LegendreGauss &lg, int nstream);
 
 // Returns number of failures (0 or 1) like the optional nerror argument.
@@ -304,12 +375,12 @@ int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &
 void schur_invert_sw(const Mat &g0, const Mat &g1, const Mat &g2, const Mat &g3, Mat &g0i,
                      Mat &g1i, Mat &g2i, Mat &g3i);
 
-void calc_matrices_sw_eig(int ndiff, int ndir, double dz, double mu0, const Mat &gamma0,
+void calc_matrices_sw_eig(int ndiff, int ndir, real dz, real mu0, const Mat &gamma0,
                           const Mat &gamma1, const Mat &gamma2, const Mat &gamma3,
                           Mat &reflectance, Mat &transmittance, Mat &s_up, Mat &s_dn,
                           Mat &trans_dir, Mat &int_dir, Mat &int_diff, Mat &int_dir_diff);
 
-void calc_matrices_lw_eig(int norder, double dz, const Mat &gamma1, const Mat &gamma2,
+void calc_matrices_lw_eig(int norder, real dz, const Mat &gamma1, const Mat &gamma2,
                           const Vec &emiss_rate, Mat &reflectance, Mat &transmittance,
                           Vec &source, Mat &int_flux, Vec &int_flux_source);
 

@@ -91,6 +91,20 @@ def load_case(path, legendre_gauss_init=None):
     return r, expected
 
 
+TRUTH_DIR = os.path.join(GOLDEN_DIR, "truth")
+
+
+def load_truth(case):
+    """Ground truth of a golden case (tests/golden/make_truth.py: the oracle's
+    _Float128 build on the stored inputs), same nested-dict form as `expected`."""
+    npz = np.load(os.path.join(TRUTH_DIR, case if case.endswith(".npz") else case + ".npz"))
+    truth = {}
+    for key in npz.files:
+        name, k = key.split(".", 1)
+        truth.setdefault(name, {})[k] = npz[key]
+    return truth
+
+
 def outputs_of(r):
     """Current outputs of r in the same nested-dict form as `expected`."""
     got = {}

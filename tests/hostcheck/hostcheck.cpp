@@ -166,3 +166,74 @@ extern "C" int hostcheck_radsurf(const ssb200_config *config, const ssb200_canop
   }
   return be.status;
 }
+
+// Unit entry: the register-resident layer formulation (csrc/ssb_layer_math.cuh) for ONE layer
+// of `nreg` regions x NS streams described by scalars (the Gamma matrices are never formed in
+// the product: LayerCoef evaluates their entries).  Outputs are column-major, full size.
+//   lw != 0: R, T, int_flux (n x n), source, int_flux_source (n)         <- emission rate b (n)
+//   lw == 0: R, T, int_diff (n x n), S_up, S_dn, int_dir_diff (n x d), E, int_dir (d x d)
+namespace {
+template <int NREG, int NS>
+int fast_layer_unit(int lw, const ssb200_legendre_gauss *lgc, const double *ext, const double *ssa,
+                    const double *frac, const double *fex, const double *fwall, double wall_ext,
+                    double wall_factor, double cos_sza, double dz, const double *brate, double *out) {
+  constexpr int n = NREG * NS, d = NREG;
+  ssb::LgTable lg;
+  lg.ns = NS;
+  for (int i = 0; i < NS; ++i) {
+    lg.mu[i] = lgc->mu[i];
+    lg.tan_ang[i] = lgc->tan_ang[i];
+    lg.weight[i] = lgc->weight[i];
+    lg.hweight[i] = lgc->hweight[i];
+    lg.vweight[i] = lgc->vweight[i];
+  }
+  lg.vadjustment = lgc->vadjustment;
+  lg.vadjustment2 = lgc->vadjustment2;
+  ssb::LayerCoef<NREG, NS> k;
+  k.set_streams(&lg);
+  for (int rf = 0; rf < NREG; ++rf) {
+    double loss = 0.0;
+    for (int rt = 0; rt < NREG; ++rt) {
+      if (rt == rf) continue;
+      loss += fex[rt + 3 * rf];
+      k.dx[rt + NREG * rf] = fex[rt + 3 * rf];
+    }
+    k.loss[rf] = loss;
+    k.ext[rf] = ext[rf];
+    k.es[rf] = ext[rf] * ssa[rf];
+    k.fw[rf] = fwall[rf];
+    k.frac[rf] = (NREG == 1) ? 1.0 : frac[rf];
+    k.rfrac[rf] = (NREG == 1) ? 1.0 : 1.0 / frac[rf];
+  }
+  k.wall_ext = wall_ext;
+  k.wall_factor = wall_factor;
+  const double zc = cos_sza > 1.0e-6 ? cos_sza : 1.0e-6;
+  k.sin0 = lw ? 0.0 : std::sqrt(1.0 - zc * zc);
+  k.tan0 = lw ? 0.0 : k.sin0 / zc;
+  k.rcos = lw ? 0.0 : 1.0 / zc;
+  const int ne = lw ? 3 * n * n + 2 * n : 3 * n * n + 3 * n * d + 2 * d * d;
+  std::vector<double> P((size_t)ne * ssb::kScratchTile, __builtin_nan(""));
+  double stack[512];
+  const ssb::StateMem st{stack, 1};
+  bool ok;
+  if (lw)
+    ok = ssb::layer_lw_solve<NREG, NS, NREG, 0>(k, brate, dz, P.data(), st);
+  else
+    ok = ssb::layer_sw_solve<NREG, NS, NREG, 0>(k, dz, P.data(), st);
+  for (int e = 0; e < ne; ++e) out[e] = P[(size_t)e * ssb::kScratchTile];
+  return ok ? 0 : 1;
+}
+}  // namespace
+
+extern "C" int hostcheck_fast_layer(int32_t lw, int32_t nreg, const ssb200_legendre_gauss *lg, const double *ext,
+                                    const double *ssa, const double *frac, const double *fex, const double *fwall,
+                                    double wall_ext, double wall_factor, double cos_sza, double dz,
+                                    const double *brate, double *out) {
+#define SSB_UNIT(NR, NSV) \
+  if (nreg == NR && lg->nstream == NSV) \
+    return fast_layer_unit<NR, NSV>(lw, lg, ext, ssa, frac, fex, fwall, wall_ext, wall_factor, cos_sza, dz, brate, out);
+  SSB_UNIT(1, 1) SSB_UNIT(1, 2) SSB_UNIT(1, 4) SSB_UNIT(2, 1) SSB_UNIT(2, 2) SSB_UNIT(2, 4)
+  SSB_UNIT(3, 1) SSB_UNIT(3, 2) SSB_UNIT(3, 3) SSB_UNIT(3, 4)
+#undef SSB_UNIT
+  return -1;
+}

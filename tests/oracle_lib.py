@@ -13,6 +13,8 @@ from spartacus_surface_b200.radsurf_interface import marshal, call_radsurf
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 ORACLE_NOFMA_SO = os.path.join(ROOT, "oracle", "_build", "liboracle_nofma.so")
+# the same restatement with every scalar in _Float128: ground truth of the parity tests
+ORACLE_QUAD_SO = os.path.join(ROOT, "oracle", "_build", "liboracle_quad.so")
 _libs = {}
 
 
@@ -20,9 +22,10 @@ def build():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
 
 
-def load(nofma=False):
-    """nofma=True: the build without FMA contraction (rounding-sensitivity probe)."""
-    path = ORACLE_NOFMA_SO if nofma else ORACLE_SO
+def load(nofma=False, quad=False):
+    """nofma=True: the build without FMA contraction (rounding-sensitivity probe);
+    quad=True: the extended-precision build (ground truth; ~100x slower)."""
+    path = ORACLE_QUAD_SO if quad else (ORACLE_NOFMA_SO if nofma else ORACLE_SO)
     if path not in _libs:
         if not os.path.exists(path):
             build()
@@ -46,12 +49,12 @@ def legendre_gauss_init(nstream, lg_ref):
     return load().oracle_legendre_gauss_init(nstream, lg_ref)
 
 
-def make_solver(nthreads=0, nblocksize=16, nofma=False):
+def make_solver(nthreads=0, nblocksize=16, nofma=False, quad=False):
     """radsurf-compatible callable backed by the oracle."""
     def solver(config, canopy_props, sw, lw, bc_out, istartcol=None, iendcol=None,
                sw_norm_dir=None, sw_norm_diff=None, lw_internal=None, lw_norm=None):
         structs = marshal(config, canopy_props, sw, lw, bc_out, sw_norm_dir, sw_norm_diff, lw_internal, lw_norm)
-        rc = call_radsurf(load(nofma).oracle_radsurf, structs, istartcol, iendcol,
+        rc = call_radsurf(load(nofma, quad).oracle_radsurf, structs, istartcol, iendcol,
                           extra=(C.c_int32(nthreads), C.c_int32(nblocksize)))
         if rc < 0:
             raise RuntimeError(f"oracle_radsurf failed rc={rc}")

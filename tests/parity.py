@@ -1,68 +1,119 @@
 """Parity metric shared by the GPU tests, smoke() and bench.py.
 
-Tolerance (stated once, used everywhere): for every output field of every flux
-object the error of the CUDA path against the oracle, relative to the largest
-magnitude of that field,
-    err = max|gpu - oracle| / max|oracle|,
-must not exceed  max(1e-9, SENS_FACTOR * sens)  where `sens` is the same
-measure between the two builds of the oracle itself (with and without FMA
-contraction, oracle/Makefile): the rounding sensitivity of the reference
-algorithm on that input (LU without pivoting, near-degenerate eigenproblems;
-1e-13 on well-conditioned inputs, up to 1e-6 for 8 streams).  BASELINE.json
-asks for <= 1e-9 relative on fluxes; that bound holds wherever the reference
-algorithm itself is reproducible to 1e-9/SENS_FACTOR.
+Ground truth
+------------
+`truth` = the reference algorithm (the oracle restatement, oracle/src) evaluated
+with every scalar in _Float128 on the same FP64 inputs (oracle/_build/
+liboracle_quad.so; stored for the golden cases in tests/golden/truth/).  With
+113 significant bits the rounding of the algorithm is removed (what remains is
+< 1e-18 even where LU without pivoting loses 16 digits), so it arbitrates the
+ill-conditioned fixtures of the reference where two FP64 builds of the
+reference itself disagree (test/simple noscat/surfaces/overhang, rami5,
+8 streams).
 
-Fields that are tiny compared with the radiation they derive from (e.g. the
-absorption by clear air, ~1e-7 of the incoming flux) are measured against
-SMALL_FIELD_FLOOR x the flux scale of their object (the largest |top/ground
-flux| of that flux object) instead of their own maximum.
+Rule (stated once, used everywhere)
+-----------------------------------
+For every output field of every flux object
+
+    err(gpu, truth)  <=  max(1e-9, 2 * err(reference_fp64, truth))
+
+i.e. BASELINE.json's 1e-9 relative on fluxes, relaxed only where the reference's
+own FP64 arithmetic is demonstrably worse than that on the same input - there
+the CUDA path has to be at least as accurate as the reference (factor 2 for the
+run-to-run scatter of that error).  err(reference_fp64, truth) is the larger of
+the two FP64 builds of the oracle (with and without FMA contraction: what
+`gfortran -O2 -march=native` and plain `gfortran -O2` produce).
+
+Measure `err(a, truth)`:
+ * the four flux-scale fields of an object (top_dn, top_net, ground_dn,
+   ground_net): ELEMENTWISE relative error, max_i |a_i - t_i| / max(|t_i|,
+   ELEM_FLOOR * S) with S the largest magnitude of those four fields in the
+   object (entries below 1e-6 of the flux scale are measured against that
+   floor);
+ * every other field: max_i |a_i - t_i| / max(max_i |t_i|, SMALL_FIELD_FLOOR * S)
+   (absorptions by clear air etc. are ~1e-7 of the flux they derive from and
+   are measured against 1e-3 of the flux scale); sunlit fractions against
+   their own maximum.
 """
 import numpy as np
 
 REL_TOL = 1e-9
-SENS_FACTOR = 50.0
+REF_FACTOR = 2.0
+ELEM_FLOOR = 1e-6
 SMALL_FIELD_FLOOR = 1e-3
 SCALE_FIELDS = ("top_dn", "top_net", "ground_dn", "ground_net")
 
 
-def field_errors(got, expected):
-    """{(object, field): relative-to-field-max error}."""
+def field_errors(got, truth):
+    """{(object, field): err(got, truth)} in the measure defined above."""
     out = {}
-    for name, fields in expected.items():
+    for name, fields in truth.items():
         obj_scale = max([float(np.abs(np.asarray(fields[k])).max()) for k in SCALE_FIELDS
                          if k in fields and np.asarray(fields[k]).size] or [0.0])
-        for k, e in fields.items():
+        for k, t in fields.items():
             g = np.asarray(got[name][k], dtype=np.float64)
-            e = np.asarray(e, dtype=np.float64)
-            assert g.shape == e.shape, (name, k, g.shape, e.shape)
-            if e.size == 0:
+            t = np.asarray(t, dtype=np.float64)
+            assert g.shape == t.shape, (name, k, g.shape, t.shape)
+            if t.size == 0:
                 continue
             if not np.all(np.isfinite(g)):
                 out[(name, k)] = float("inf")
                 continue
-            scale = float(np.abs(e).max())
-            if "sunlit" not in k:
-                scale = max(scale, SMALL_FIELD_FLOOR * obj_scale)
-            diff = float(np.abs(g - e).max())
-            out[(name, k)] = 0.0 if diff == 0.0 else diff / max(scale, 1e-300)
+            diff = np.abs(g - t)
+            if not diff.any():
+                out[(name, k)] = 0.0
+            elif k in SCALE_FIELDS:
+                out[(name, k)] = float((diff / np.maximum(np.abs(t), max(ELEM_FLOOR * obj_scale, 1e-300))).max())
+            else:
+                scale = float(np.abs(t).max())
+                if "sunlit" not in k:
+                    scale = max(scale, SMALL_FIELD_FLOOR * obj_scale)
+                out[(name, k)] = float(diff.max()) / max(scale, 1e-300)
     return out
 
 
-def check(got, oracle_a, oracle_b):
-    """Returns (ok, worst_ratio, report_lines)."""
-    err = field_errors(got, oracle_a)
-    sens = field_errors(oracle_b, oracle_a)
+def reference_errors(truth, *reference_fp64):
+    """err(reference_fp64, truth) per field: the largest over the given FP64 builds."""
+    ref = {}
+    for r in reference_fp64:
+        for key, e in field_errors(r, truth).items():
+            ref[key] = max(ref.get(key, 0.0), e)
+    return ref
+
+
+def check(got, truth, *reference_fp64):
+    """Returns (ok, worst err/bound, report lines)."""
+    err = field_errors(got, truth)
+    ref = reference_errors(truth, *reference_fp64)
     lines, ok, worst = [], True, 0.0
     for key in sorted(err):
-        bound = max(REL_TOL, SENS_FACTOR * sens.get(key, 0.0))
-        ratio = err[key] / bound
-        worst = max(worst, ratio)
+        bound = max(REL_TOL, REF_FACTOR * ref.get(key, 0.0))
+        worst = max(worst, err[key] / bound)
         if err[key] > bound:
             ok = False
-            lines.append(f"{key[0]}.{key[1]}: err={err[key]:.3e} > bound={bound:.3e} (sens={sens.get(key, 0.0):.3e})")
+            lines.append(f"{key[0]}.{key[1]}: err_vs_truth={err[key]:.3e} > bound={bound:.3e} "
+                         f"(reference_fp64 err_vs_truth={ref.get(key, 0.0):.3e})")
     return ok, worst, lines
 
 
-def max_err(got, expected):
-    e = field_errors(got, expected)
+def summary(got, truth, *reference_fp64):
+    """Numbers for the parity table (profiles/r02_parity_table.json)."""
+    err = field_errors(got, truth)
+    ref = reference_errors(truth, *reference_fp64)
+    worst_key = max(err, key=lambda k: err[k]) if err else None
+    bounds = {k: max(REL_TOL, REF_FACTOR * ref.get(k, 0.0)) for k in err}
+    ratio_key = max(err, key=lambda k: err[k] / bounds[k]) if err else None
+    return {
+        "err_gpu": max(err.values()) if err else 0.0,
+        "err_gpu_field": ".".join(worst_key) if worst_key else None,
+        "err_ref_fp64": max(ref.values()) if ref else 0.0,
+        "bound_max": max(bounds.values()) if bounds else REL_TOL,
+        "worst_err_over_bound": (err[ratio_key] / bounds[ratio_key]) if ratio_key else 0.0,
+        "worst_err_over_bound_field": ".".join(ratio_key) if ratio_key else None,
+        "fields_above_1e-9": sorted(".".join(k) for k in err if err[k] > REL_TOL),
+    }
+
+
+def max_err(got, truth):
+    e = field_errors(got, truth)
     return max(e.values()) if e else 0.0
