@@ -191,6 +191,11 @@ struct Context {
   int sort_columns = 0;
   int sort_group = 512;  // ... inside groups of this many neighbouring columns
   int partition = 1;  // group layer problems by solved sub-block before the fast layer kernels
+  // column-resident kernels (ssb_fused.cuh) where they exist (1 and 2 streams); 0: split path
+  int fused_mode = 1;
+  int fused_sort = 1;
+  int fused_sort_group = 4096;
+  int sm_count = 0;
 };
 Context g_ctx;
 
@@ -203,9 +208,11 @@ struct CudaBackend {
       : cx(c), lane(lane_), budget(budget_ ? budget_ : c.budget_doubles) {}
   const int *dev_cols(const ssb::Plan &, size_t off) { return (const int *)cx.d_cols.p + off; }
   // columns of the chunk ordered by their segment pattern (device radix sort, stable)
+  // (always for the column-resident kernels: a thread walks the layers of its column, so the
+  // warps only stay on one code path when neighbouring columns have the same segment pattern)
   const int *order_chunk(const ssb::ClassArgs &a, const int *) {
-    if (!cx.fast_mode || !cx.sort_columns || !cx.partition || a.ncols < 64 || a.cfg.ns > 4 ||
-        cx.first_error != cudaSuccess)
+    const bool want = a.fused ? cx.fused_sort != 0 : (cx.sort_columns && cx.partition);
+    if (!cx.fast_mode || !want || a.ncols < 64 || a.cfg.ns > 4 || cx.first_error != cudaSuccess)
       return a.cols;
     const size_t n = (size_t)a.ncols, pad = (n + 63) & ~(size_t)63;
     typedef unsigned long long Key;
@@ -220,7 +227,8 @@ struct CudaBackend {
     char *base = (char *)cx.d_sort[lane].p;
     Key *keys = (Key *)(base + temp_bytes), *keys_out = keys + pad;
     int *cols_out = (int *)(keys_out + pad);
-    const int group = cx.sort_group > 0 ? cx.sort_group : 0x7fffffff;
+    const int group = a.fused ? (cx.fused_sort_group > 0 ? cx.fused_sort_group : 0x7fffffff)
+                              : (cx.sort_group > 0 ? cx.sort_group : 0x7fffffff);
     k_column_keys<<<(unsigned)((n + 127) / 128), 128, 0, cx.stream>>>(a, keys, group);
     cub::DeviceRadixSort::SortPairs(base, temp_bytes, keys, keys_out, a.cols, cols_out, (int)n, 0, 64, cx.stream);
     g_launches += 2;
@@ -323,6 +331,29 @@ struct CudaBackend {
       if (done) return;
     }
     launch(ssb::launch_sweeps_lw<NS>, a, nt, 3);
+  }
+  bool fused_shape(const ssb::SolveCfg &c, bool lw, int *pe, int *oe, int *geo) {
+    if (!cx.fast_mode || !cx.fused_mode || c.ns > 2) return false;
+    return ssb::fused_shape(c, lw, pe, oe, geo);
+  }
+  int fused_slots() {
+    if (cx.sm_count <= 0) {
+      int dev = 0, n = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      cx.sm_count = n > 0 ? n : 148;
+    }
+    return 2 * cx.sm_count;  // __launch_bounds__(128, 2)
+  }
+  void fused_run(const ssb::ClassArgs &a, bool lw, long width) {
+    if (width <= 0 || cx.first_error != cudaSuccess) return;
+    const int fam = lw ? 2 : 0;  // booked under the layer families (kernel_times: sw_layer / lw_layer)
+    tick(fam, true);
+    const long tiles = (width + ssb::kScratchTile - 1) / ssb::kScratchTile;
+    const int grid = (int)(tiles < (long)fused_slots() ? tiles : (long)fused_slots());
+    ssb::fused_launch(a, lw, width, grid, cx.stream);
+    check_launch();
+    tick(fam, false);
   }
   void surface(const ssb::SurfaceArgs &s, int nsw_threads, int nlw_threads) {
     const int nt = nsw_threads > nlw_threads ? nsw_threads : nlw_threads;
@@ -839,6 +870,18 @@ int ssb200_set_option(const char *name, int64_t value) {
   }
   if (n == "pipeline_max_blocks") {
     g_ctx.pipeline_max_blocks = value < 1 ? 1 : (int)value;
+    return 0;
+  }
+  if (n == "fused_kernels") {  // column-resident kernels where they exist (1 and 2 streams)
+    g_ctx.fused_mode = value != 0;
+    return 0;
+  }
+  if (n == "fused_sort") {
+    g_ctx.fused_sort = value != 0;
+    return 0;
+  }
+  if (n == "fused_sort_group") {
+    g_ctx.fused_sort_group = (int)value;
     return 0;
   }
   if (n == "partition_layers") {

@@ -157,6 +157,10 @@ struct CallArgs {
 //   template<int NS> void layer_sw/layer_lw(const ClassArgs&, long nthreads)
 //   template<int NS> void sweeps_sw/sweeps_lw(const ClassArgs&, long nthreads)
 //   void surface(const SurfaceArgs&, int nsw_threads, int nlw_threads)
+//   bool fused_shape(const SolveCfg&, bool lw, int *private_elems, int *op_elems, int *geo_first)
+//        false: no column-resident kernel for this shape (or disabled): split path
+//   int fused_slots()                                private tiles (= resident thread blocks)
+//   void fused_run(const ClassArgs&, bool lw, long width)
 template <class Backend>
 struct Dispatcher {
   Backend &be;
@@ -172,9 +176,18 @@ struct Dispatcher {
     const size_t el = lw ? lw_layer_elems(n, c.nreg) : sw_layer_elems(n, d);
     const size_t es = lw ? lw_sweep_elems(n, m, c.nreg, nrb) : sw_sweep_elems(n, d, m, nrb, c.nreg, nrb);
     const size_t budget = be.scratch_budget_doubles();
+    // column-resident path where the backend has it (1 and 2 streams): one private tile per
+    // resident thread block plus one operator record per (problem, level)
+    int f_private = 0, f_op = 0, f_geo = 0;
+    const bool fused = be.fused_shape(c, lw, &f_private, &f_op, &f_geo);
+    const size_t f_tiles = fused ? (size_t)be.fused_slots() * (size_t)f_private * kScratchTile : 0;
     // class columns are ascending: restrict to the window by binary search
     size_t pos = (size_t)(std::lower_bound(k.cols.begin(), k.cols.end(), col_lo) - k.cols.begin());
     const size_t ntot = (size_t)(std::lower_bound(k.cols.begin(), k.cols.end(), col_hi) - k.cols.begin());
+    auto need_of = [&](size_t lm, size_t wd) {
+      return fused ? f_tiles + scratch_doubles((size_t)f_op, lm > 0 ? lm : 1, wd)
+                   : scratch_doubles(el, lm, wd) + scratch_doubles(es, lm + 1, wd);
+    };
     while (pos < ntot) {
       // grow the chunk while its scratch (sized by the tallest column) fits the budget
       int lmax = 0;
@@ -183,8 +196,7 @@ struct Dispatcher {
         const int nl = plan.nlay[k.cols[pos + cnt]];
         const int lm = std::max(lmax, nl);
         const size_t wd = (cnt + 1) * (size_t)c.nspec;
-        const size_t need = scratch_doubles(el, (size_t)lm, wd) + scratch_doubles(es, (size_t)lm + 1, wd);
-        if (need > budget && cnt > 0) break;
+        if (need_of((size_t)lm, wd) > budget && cnt > 0) break;
         lmax = lm;
         ++cnt;
       }
@@ -193,12 +205,26 @@ struct Dispatcher {
       a.cols = be.dev_cols(plan, col_offset + pos);
       // the backend may reorder the columns of the chunk (every problem is independent; scratch
       // positions follow the order of a.cols, global arrays are addressed through it)
+      a.fused = fused ? 1 : 0;
       a.cols = be.order_chunk(a, plan.host_cols(col_offset + pos));
       const size_t width = cnt * (size_t)c.nspec;
-      double *s = be.scratch(scratch_doubles(el, (size_t)lmax, width) + scratch_doubles(es, (size_t)lmax + 1, width));
+      double *s = be.scratch(need_of((size_t)lmax, width));
+      if (fused) {
+        a.layer = s;
+        a.sweep = s + f_tiles;
+        a.lmax = lmax > 0 ? lmax : 1;
+        a.ne_layer = f_private;
+        a.ne_layer_geo = f_geo;
+        a.ne_sweep = f_op;
+        a.save_profile = (a.f1.flux_dn_layer_top || a.f2.flux_dn_layer_top) ? 1 : 0;
+        be.fused_run(a, lw, (long)width);
+        pos += cnt;
+        continue;
+      }
       a.layer = s;
       a.sweep = s + scratch_doubles(el, (size_t)lmax, width);
       a.ne_layer = (int)el;
+      a.ne_layer_geo = (int)el - kGeoElems;
       a.ne_sweep = (int)es;
       if (lmax > 0) {
         if (lw)

@@ -39,4 +39,22 @@ SSB_FAST_HOOK(fast_layer_lw)
 SSB_FAST_HOOK(fast_sweeps_sw)
 SSB_FAST_HOOK(fast_sweeps_lw)
 #undef SSB_FAST_HOOK
+
+// column-resident kernels (ssb_g_ns*_{sw,lw}.cu): 1 and 2 streams
+#define SSB_FUSED_DECL(k)                                                                \
+  bool fused_shape_sw_ns##k(const SolveCfg &, int *, int *, int *);                     \
+  bool fused_shape_lw_ns##k(const SolveCfg &, int *, int *, int *);                     \
+  bool fused_sw_ns##k(const ClassArgs &, long, int, cudaStream_t);                      \
+  bool fused_lw_ns##k(const ClassArgs &, long, int, cudaStream_t);
+SSB_FUSED_DECL(1)
+SSB_FUSED_DECL(2)
+#undef SSB_FUSED_DECL
+inline bool fused_shape(const SolveCfg &c, bool lw, int *pe, int *oe, int *geo) {
+  if (lw) return c.ns == 1 ? fused_shape_lw_ns1(c, pe, oe, geo) : (c.ns == 2 ? fused_shape_lw_ns2(c, pe, oe, geo) : false);
+  return c.ns == 1 ? fused_shape_sw_ns1(c, pe, oe, geo) : (c.ns == 2 ? fused_shape_sw_ns2(c, pe, oe, geo) : false);
+}
+inline bool fused_launch(const ClassArgs &a, bool lw, long nt, int grid, cudaStream_t st) {
+  if (lw) return a.cfg.ns == 1 ? fused_lw_ns1(a, nt, grid, st) : (a.cfg.ns == 2 ? fused_lw_ns2(a, nt, grid, st) : false);
+  return a.cfg.ns == 1 ? fused_sw_ns1(a, nt, grid, st) : (a.cfg.ns == 2 ? fused_sw_ns2(a, nt, grid, st) : false);
+}
 }  // namespace ssb

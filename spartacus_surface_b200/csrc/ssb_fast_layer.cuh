@@ -50,7 +50,7 @@ SSB_HDI void fast_sw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
   k.tan0 = op.tan0;
   k.sin0 = op.sin0;
   k.rcos = 1.0 / (a.cfg.urban ? op.zcos : op.cos_sza);
-  double *P = a.layer + sidx(0, lev, a.lmax, a.ne_layer, q);
+  double *P = a.layer + layer_sidx(a, 0, lev, q);
   const bool ok = layer_sw_solve<NREG, NS, NR, R0>(k, op.dz, P, st);
   count_failure(a.status, ok ? 0 : 1);
 }
@@ -71,7 +71,7 @@ SSB_HDI void load_geometry_inputs(const ClassArgs &a, int il, double &bf, double
 // layer geometry from the geometry block of the layer scratch (written by fast_prepare_level)
 template <int NREG>
 SSB_HDI void load_layer_geom(const ClassArgs &a, int q, int lev, LayerGeom &gm) {
-  const double *P = a.layer + sidx(a.ne_layer - kGeoElems, lev, a.lmax, a.ne_layer, q);
+  const double *P = a.layer + layer_sidx(a, a.ne_layer_geo, lev, q);
   SSB_UNROLL
   for (int i = 0; i < 9; ++i) gm.f_exchange[i] = 0.0;
   SSB_UNROLL
@@ -183,7 +183,7 @@ SSB_HDI void fast_lw_branch(const ClassArgs &a, int q, int lev, const LayerGeom 
     for (int js = 0; js < NS; ++js)
       brate[js + r * NS] = (a.lg.hweight[js] / a.lg.mu[js]) * volume_emiss + (0.5 * a.lg.vweight[js]) * wall_emiss;
   }
-  double *P = a.layer + sidx(0, lev, a.lmax, a.ne_layer, q);
+  double *P = a.layer + layer_sidx(a, 0, lev, q);
   const bool ok = layer_lw_solve<NREG, NS, NR, R0>(k, brate, op.dz, P, st);
   count_failure(a.status, ok ? 0 : 1);
 }
@@ -229,23 +229,22 @@ SSB_HDI void fast_layer_problem_lw_impl(const ClassArgs &a, int q, int lev, cons
   SSB_UNROLL
   for (int js = 0; js < NS; ++js) emiss_factor += a.lg.hweight[js] / a.lg.mu[js];
   emiss_factor = 2.0 * emiss_factor;
-  const int nlev = a.lmax, width = a.ne_layer;
   const int e_book = 3 * n * n + 2 * n;
   double wsum = 0.0;
   SSB_UNROLL
   for (int Rr = 0; Rr < NREG; ++Rr) {
     const double volume_emiss = gm.frac[Rr] * (op.ext[Rr] * (1.0 - op.ssa[Rr]) * op.planck[Rr]);
-    a.layer[sidx(e_book + Rr, lev, nlev, width, q)] = emiss_factor * volume_emiss;
+    a.layer[layer_sidx(a, e_book + Rr, lev, q)] = emiss_factor * volume_emiss;
     double e_air = 0.0, e_veg = 0.0;
     if (Rr > 0) {
       e_air = emiss_factor * gm.frac[Rr] * op.ext[0] * (1.0 - op.ssa[0]) * vaplanck;
       e_veg = emiss_factor * gm.frac[Rr] * ve * (1.0 - vssa) * vplanck * gm.od_scaling[Rr];
     }
-    a.layer[sidx(e_book + d + Rr, lev, nlev, width, q)] = e_air;
-    a.layer[sidx(e_book + 2 * d + Rr, lev, nlev, width, q)] = e_veg;
+    a.layer[layer_sidx(a, e_book + d + Rr, lev, q)] = e_air;
+    a.layer[layer_sidx(a, e_book + 2 * d + Rr, lev, q)] = e_veg;
     wsum += gm.norm_perim_wall[Rr];
   }
-  a.layer[sidx(e_book + 3 * d, lev, nlev, width, q)] = c.urban ? (wsum * a.lg.vadjustment) * wall_emission : 0.0;
+  a.layer[layer_sidx(a, e_book + 3 * d, lev, q)] = c.urban ? (wsum * a.lg.vadjustment) * wall_emission : 0.0;
 
   if (SEG >= 0) {
     constexpr int NR = (SEG <= 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
@@ -306,7 +305,7 @@ SSB_HDI int fast_prepare_level(const ClassArgs &a, int q, int k) {
   LayerGeom gm;
   layer_geometry(c, bf, bs, vf, vs, vcf, vfsd, c.lw ? a.lg.vadjustment2 : 1.0, gm);
   const int seg = branch_segment(gm, c.nreg);
-  double *P = a.layer + sidx(a.ne_layer - kGeoElems, k, a.lmax, a.ne_layer, q);
+  double *P = a.layer + layer_sidx(a, a.ne_layer_geo, k, q);
   for (int r = 0; r < 3; ++r) {
     P[(size_t)r * kScratchTile] = gm.f_wall[r];
     P[(size_t)(3 + r) * kScratchTile] = gm.od_scaling[r];

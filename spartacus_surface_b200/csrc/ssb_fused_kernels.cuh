@@ -1,0 +1,130 @@
+// ssb_fused_kernels.cuh - kernels around the column-resident bodies (ssb_fused.cuh).  Included by
+// ssb_g_ns*_{sw,lw}.cu with SSB_NS, SSB_FUSED_TU and SSB_KIND_SW / SSB_KIND_LW defined.
+//
+// Persistent grid: as many blocks as the device holds at once (2 per SM); a block walks over
+// tiles of 128 (column, interval) problems and owns ONE private scratch tile for all of them, so
+// the layer matrices of the ~38 k problems in flight (75 MB at 2 streams) stay in the 126 MB L2.
+#pragma once
+#include "ssb_fast.cuh"
+#define SSB_CAT2(a, b) a##b
+#define SSB_CAT(a, b) SSB_CAT2(a, b)
+#include "ssb_fused.cuh"
+
+namespace ssb {
+
+constexpr int kFusedBlock = kScratchTile;  // one thread per problem of a tile
+
+#ifdef SSB_KIND_SW
+template <int NREG, int NS, bool URBAN>
+__global__ void __launch_bounds__(kFusedBlock, 2) k_fused_sw(ClassArgs a, long nt) {
+  extern __shared__ double ssb_stack[];  // [element][thread]: conflict-free per-thread slices
+  const StateMem st{ssb_stack + threadIdx.x, kFusedBlock};
+  const long ntiles = (nt + kFusedBlock - 1) / kFusedBlock;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long q = tile * kFusedBlock + threadIdx.x;
+    if (q < nt) fused_column_sw<NREG, NS, URBAN>(a, (int)q, st);
+  }
+}
+template <int NREG, int NS, bool URBAN>
+static void launch_fused_sw(const ClassArgs &a, long nt, int grid, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = sizeof(double) * SwFused<NREG, NS, URBAN>::smem_doubles * kFusedBlock;
+  if (!configured) {
+    fast_note(cudaFuncSetAttribute(k_fused_sw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  k_fused_sw<NREG, NS, URBAN><<<grid, kFusedBlock, smem, st>>>(a, nt);
+  fast_note(cudaGetLastError());
+}
+// sizes of the two scratch areas: private tile elements, operator record elements
+bool SSB_CAT(fused_shape_sw_ns, SSB_NS)(const SolveCfg &c, int *private_elems, int *op_elems, int *geo_first) {
+  if (c.ns != SSB_NS) return false;
+#define SSB_SHAPE(NR, UR)                                             \
+  {                                                                    \
+    *private_elems = SwFused<NR, SSB_NS, UR>::private_elems;          \
+    *op_elems = SwFused<NR, SSB_NS, UR>::op_elems;                    \
+    *geo_first = SwSweepLayout<NR, SSB_NS, UR>::oGeo;                 \
+    return true;                                                       \
+  }
+  switch (c.nreg * 2 + (c.urban ? 1 : 0)) {
+    case 2: SSB_SHAPE(1, false)
+    case 3: SSB_SHAPE(1, true)
+    case 4: SSB_SHAPE(2, false)
+    case 5: SSB_SHAPE(2, true)
+    case 6: SSB_SHAPE(3, false)
+    case 7: SSB_SHAPE(3, true)
+    default: return false;
+  }
+#undef SSB_SHAPE
+}
+bool SSB_CAT(fused_sw_ns, SSB_NS)(const ClassArgs &a, long nt, int grid, cudaStream_t st) {
+  if (a.cfg.ns != SSB_NS || !a.fused) return false;
+  switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
+    case 2: launch_fused_sw<1, SSB_NS, false>(a, nt, grid, st); return true;
+    case 3: launch_fused_sw<1, SSB_NS, true>(a, nt, grid, st); return true;
+    case 4: launch_fused_sw<2, SSB_NS, false>(a, nt, grid, st); return true;
+    case 5: launch_fused_sw<2, SSB_NS, true>(a, nt, grid, st); return true;
+    case 6: launch_fused_sw<3, SSB_NS, false>(a, nt, grid, st); return true;
+    case 7: launch_fused_sw<3, SSB_NS, true>(a, nt, grid, st); return true;
+    default: return false;
+  }
+}
+#endif
+
+#ifdef SSB_KIND_LW
+template <int NREG, int NS, bool URBAN>
+__global__ void __launch_bounds__(kFusedBlock, 2) k_fused_lw(ClassArgs a, long nt) {
+  extern __shared__ double ssb_stack[];
+  const StateMem st{ssb_stack + threadIdx.x, kFusedBlock};
+  const long ntiles = (nt + kFusedBlock - 1) / kFusedBlock;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long q = tile * kFusedBlock + threadIdx.x;
+    if (q < nt) fused_column_lw<NREG, NS, URBAN>(a, (int)q, st);
+  }
+}
+template <int NREG, int NS, bool URBAN>
+static void launch_fused_lw(const ClassArgs &a, long nt, int grid, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = sizeof(double) * LwFused<NREG, NS, URBAN>::smem_doubles * kFusedBlock;
+  if (!configured) {
+    fast_note(cudaFuncSetAttribute(k_fused_lw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  k_fused_lw<NREG, NS, URBAN><<<grid, kFusedBlock, smem, st>>>(a, nt);
+  fast_note(cudaGetLastError());
+}
+bool SSB_CAT(fused_shape_lw_ns, SSB_NS)(const SolveCfg &c, int *private_elems, int *op_elems, int *geo_first) {
+  if (c.ns != SSB_NS) return false;
+#define SSB_SHAPE(NR, UR)                                             \
+  {                                                                    \
+    *private_elems = LwFused<NR, SSB_NS, UR>::private_elems;          \
+    *op_elems = LwFused<NR, SSB_NS, UR>::op_elems;                    \
+    *geo_first = LwSweepLayout<NR, SSB_NS, UR>::oGeo;                 \
+    return true;                                                       \
+  }
+  switch (c.nreg * 2 + (c.urban ? 1 : 0)) {
+    case 2: SSB_SHAPE(1, false)
+    case 3: SSB_SHAPE(1, true)
+    case 4: SSB_SHAPE(2, false)
+    case 5: SSB_SHAPE(2, true)
+    case 6: SSB_SHAPE(3, false)
+    case 7: SSB_SHAPE(3, true)
+    default: return false;
+  }
+#undef SSB_SHAPE
+}
+bool SSB_CAT(fused_lw_ns, SSB_NS)(const ClassArgs &a, long nt, int grid, cudaStream_t st) {
+  if (a.cfg.ns != SSB_NS || !a.fused) return false;
+  switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
+    case 2: launch_fused_lw<1, SSB_NS, false>(a, nt, grid, st); return true;
+    case 3: launch_fused_lw<1, SSB_NS, true>(a, nt, grid, st); return true;
+    case 4: launch_fused_lw<2, SSB_NS, false>(a, nt, grid, st); return true;
+    case 5: launch_fused_lw<2, SSB_NS, true>(a, nt, grid, st); return true;
+    case 6: launch_fused_lw<3, SSB_NS, false>(a, nt, grid, st); return true;
+    case 7: launch_fused_lw<3, SSB_NS, true>(a, nt, grid, st); return true;
+    default: return false;
+  }
+}
+#endif
+
+}  // namespace ssb

@@ -1,0 +1,5 @@
+// column-resident lw kernels, 2 stream(s) per hemisphere
+#define SSB_NS 2
+#define SSB_KIND_LW
+#define SSB_FUSED_TU
+#include "ssb_fused_kernels.cuh"

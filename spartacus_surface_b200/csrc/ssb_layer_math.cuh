@@ -315,7 +315,8 @@ SSB_HDI void layer_vm_row(const LayerCoef<NR, NS> &c, const StateMem &st, int i,
 #define SSB_OUT(P, e) (P)[(size_t)(e) * kScratchTile]
 // final value of an element: not read again in this kernel, consumed by the sweeps hundreds of
 // megabytes later - a streaming (evict-first) store keeps it from displacing the parked rows
-#if defined(__CUDA_ARCH__)
+// (column-resident kernels: the tile is private and re-read within microseconds - plain stores)
+#if defined(__CUDA_ARCH__) && !defined(SSB_FUSED_TU)
 #define SSB_FINAL(P, e, v) __stcs((P) + (size_t)(e) * kScratchTile, (v))
 #else
 #define SSB_FINAL(P, e, v) ((P)[(size_t)(e) * kScratchTile] = (v))

@@ -51,15 +51,34 @@ struct ClassArgs {
   double *layer;              // layer-matrix scratch (ne_layer elements x lmax levels)
   double *sweep;              // interface scratch (ne_sweep elements x lmax+1 levels)
   int ne_layer, ne_sweep;
+  int ne_layer_geo;           // first element of the geometry block in the layer scratch
   int *perm;                  // fast path: layer problems grouped by solved sub-block (3 segments of nt)
   int *perm_count;            // [3] problems per segment
   int *status;                // failure counter
+  // column-resident ("fused") path: `layer` is a set of PRIVATE one-level tiles, one per thread
+  // block (re-used for every layer of every column the block solves, so it stays in L2), and
+  // `sweep` holds the per-level down-pass operator records (ssb_fused.cuh)
+  int fused;
+  int save_profile;           // flux profiles requested (decides whether their operator rows are formed)
 };
 
 constexpr int kScratchTile = 128;
 SSB_HDI size_t sidx(int e, int lev, int nlev, int nelem, int q) {
   return (((size_t)(q / kScratchTile) * (size_t)nlev + (size_t)lev) * (size_t)nelem + (size_t)e) * kScratchTile +
          (size_t)(q % kScratchTile);
+}
+// Layer scratch of problem q: per (tile, level) in the split path; in the fused path the tile of the
+// calling thread block (slot = blockIdx.x on the device, 0 in the serial host build), one level.
+SSB_HDI size_t layer_sidx(const ClassArgs &a, int e, int lev, int q) {
+  if (a.fused) {
+#if defined(__CUDA_ARCH__)
+    const size_t slot = blockIdx.x;
+#else
+    const size_t slot = 0;
+#endif
+    return (slot * (size_t)a.ne_layer + (size_t)e) * kScratchTile + (size_t)(q % kScratchTile);
+  }
+  return sidx(e, lev, a.lmax, a.ne_layer, q);
 }
 // doubles of a scratch area of `nelem` elements x `nlev` levels for `width` problems
 SSB_HDI size_t scratch_doubles(size_t nelem, size_t nlev, size_t width) {

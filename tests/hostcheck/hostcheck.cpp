@@ -9,6 +9,7 @@
 #include "../../spartacus_surface_b200/csrc/ssb_driver.hpp"
 #include "../../spartacus_surface_b200/csrc/ssb_fast_layer.cuh"
 #include "../../spartacus_surface_b200/csrc/ssb_fast_sweeps.cuh"
+#include "../../spartacus_surface_b200/csrc/ssb_fused.cuh"
 
 namespace {
 
@@ -17,6 +18,66 @@ struct HostBackend {
   std::vector<double> buf;
   int status = 0;
   bool fast = false;  // use the register-resident bodies where they exist (ns <= 4)
+  bool fused = false;  // ... and the column-resident ones (ssb_fused.cuh; ns <= 2)
+  template <int NSA, int NREG, bool URBAN>
+  bool fused_shape_t(bool lw, int *pe, int *oe, int *geo) {
+    if (lw) {
+      *pe = ssb::LwFused<NREG, NSA, URBAN>::private_elems;
+      *oe = ssb::LwFused<NREG, NSA, URBAN>::op_elems;
+      *geo = ssb::LwSweepLayout<NREG, NSA, URBAN>::oGeo;
+    } else {
+      *pe = ssb::SwFused<NREG, NSA, URBAN>::private_elems;
+      *oe = ssb::SwFused<NREG, NSA, URBAN>::op_elems;
+      *geo = ssb::SwSweepLayout<NREG, NSA, URBAN>::oGeo;
+    }
+    return true;
+  }
+  template <int NSA>
+  bool fused_shape_ns(const ssb::SolveCfg &c, bool lw, int *pe, int *oe, int *geo) {
+    switch (c.nreg * 2 + (c.urban ? 1 : 0)) {
+      case 2: return fused_shape_t<NSA, 1, false>(lw, pe, oe, geo);
+      case 3: return fused_shape_t<NSA, 1, true>(lw, pe, oe, geo);
+      case 4: return fused_shape_t<NSA, 2, false>(lw, pe, oe, geo);
+      case 5: return fused_shape_t<NSA, 2, true>(lw, pe, oe, geo);
+      case 6: return fused_shape_t<NSA, 3, false>(lw, pe, oe, geo);
+      case 7: return fused_shape_t<NSA, 3, true>(lw, pe, oe, geo);
+      default: return false;
+    }
+  }
+  bool fused_shape(const ssb::SolveCfg &c, bool lw, int *pe, int *oe, int *geo) {
+    if (!fused) return false;
+    if (c.ns == 1) return fused_shape_ns<1>(c, lw, pe, oe, geo);
+    if (c.ns == 2) return fused_shape_ns<2>(c, lw, pe, oe, geo);
+    return false;
+  }
+  int fused_slots() { return 1; }
+  template <int NSA, int NREG, bool URBAN>
+  void fused_cols(const ssb::ClassArgs &a, bool lw, long width) {
+    double stack[512];
+    const ssb::StateMem st{stack, 1};
+    for (long t = 0; t < width; ++t) {
+      if (lw)
+        ssb::fused_column_lw<NREG, NSA, URBAN>(a, (int)t, st);
+      else
+        ssb::fused_column_sw<NREG, NSA, URBAN>(a, (int)t, st);
+    }
+  }
+  template <int NSA>
+  void fused_run_ns(const ssb::ClassArgs &a, bool lw, long width) {
+    switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
+      case 2: fused_cols<NSA, 1, false>(a, lw, width); break;
+      case 3: fused_cols<NSA, 1, true>(a, lw, width); break;
+      case 4: fused_cols<NSA, 2, false>(a, lw, width); break;
+      case 5: fused_cols<NSA, 2, true>(a, lw, width); break;
+      case 6: fused_cols<NSA, 3, false>(a, lw, width); break;
+      case 7: fused_cols<NSA, 3, true>(a, lw, width); break;
+      default: break;
+    }
+  }
+  void fused_run(const ssb::ClassArgs &a, bool lw, long width) {
+    if (a.cfg.ns == 1) fused_run_ns<1>(a, lw, width);
+    else fused_run_ns<2>(a, lw, width);
+  }
   size_t budget = (size_t)1 << 22;  // small on purpose: exercises the chunk loop
   const int *dev_cols(const ssb::Plan &p, size_t off) { return p.all_cols.data() + off; }
   // reversed column order inside every chunk: results must not depend on it
@@ -158,6 +219,7 @@ extern "C" int hostcheck_radsurf(const ssb200_config *config, const ssb200_canop
   be.plan = &plan;
   if (budget_doubles > 0) be.budget = (size_t)budget_doubles;
   be.fast = fast != 0;
+  be.fused = fast == 2;
   ssb::Dispatcher<HostBackend> disp(be);
   rc = disp.run(ca, plan, err);
   if (rc) {
