@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--generic", action="store_true", help="force the generic kernels")
     ap.add_argument("--split", action="store_true", help="split layer / sweeps kernels instead of the column-resident ones")
     ap.add_argument("--fused-sort-group", type=int, default=None, help="tuning: -1 no column ordering, 0 whole chunk")
+    ap.add_argument("--opt", action="append", default=[], help="tuning: name=value passed to ssb200_set_option")
     ap.add_argument("--sort-group", type=int, default=None, help="tuning: column ordering group (0 = whole chunk)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -267,6 +268,9 @@ def main():
     if args.fused_sort_group is not None:
         lib.ssb200_set_option(b"fused_sort", 0 if args.fused_sort_group < 0 else 1)
         lib.ssb200_set_option(b"fused_sort_group", max(args.fused_sort_group, 0))
+    for kv in args.opt:
+        k, v = kv.split("=")
+        assert lib.ssb200_set_option(k.encode(), int(v)) == 0, kv
     if args.sort_group is not None:
         lib.ssb200_set_option(b"sort_columns", 0 if args.sort_group < 0 else 1)
         lib.ssb200_set_option(b"sort_group", max(args.sort_group, 0))

@@ -185,6 +185,44 @@ int ssb200_radsurf(const ssb200_config *config,
                    ssb200_canopy_flux *lw_internal,
                    ssb200_canopy_flux *lw_norm);
 
+/* What the reference DRIVER does around `radsurf` for every block of columns
+ * (driver/spartacus_surface_driver.F90:206-261), as ONE call that keeps the four
+ * normalised flux objects on the device:
+ *   calc_simple_spectrum_lw      radsurf/radsurf_simple_spectrum.F90:41-66   (emission from temperatures)
+ *   radsurf                      radsurf/radsurf_interface.F90:20-317
+ *   sw_norm_dir%scale(top_dir); sw_norm_diff%scale(top_dn - top_dir); sw_flux%sum(...)    driver:250-256
+ *   lw_norm%scale(top_dn_lw);   lw_flux%sum(lw_internal, lw_norm)                         driver:258-261
+ * plus the defaults read_input fills in when the input file lacks a variable
+ * (driver/spartacus_surface_read_input.F90:155-166,258-269,311-344,362-365), evaluated on
+ * the device for members passed as NULL:
+ *   sw%air_ext, lw%air_ext = 1e-5; sw%air_ssa = 0.999; lw%air_ssa = 0; sw%wall_specular_frac = 0;
+ *   sw%roof_albedo_dir = sw%roof_albedo;
+ *   canopy_props%veg_contact_fraction = min(1, veg_fraction / max(min_vegetation_fraction, 1 - building_fraction));
+ *   lw%{ground,roof,wall}_emission, lw%{clear_air,veg,veg_air}_planck from the temperatures below.
+ * Only the inputs that carry information and the two summed flux objects cross PCIe
+ * (16 instead of 25 input doubles and 2 instead of 4 flux objects per layer).
+ * HOST pointers throughout; every array (nspec, ncol) or (ntotlay), reference layout. */
+typedef struct ssb200_driver_inputs {
+  const double *top_flux_dn_sw;         /* (nsw, ncol) total downwelling SW at canopy top */
+  const double *top_flux_dn_direct_sw;  /* (nsw, ncol) its direct part */
+  const double *top_flux_dn_lw;         /* (nlw, ncol) */
+  const double *ground_temperature;     /* (ncol)    K; used for NULL members of lw_spectral_props */
+  const double *roof_temperature, *wall_temperature;                          /* (ntotlay) */
+  const double *clear_air_temperature, *veg_temperature, *veg_air_temperature; /* (ntotlay) */
+} ssb200_driver_inputs;
+
+/* sw_flux / lw_flux: the summed flux objects (the members that are allocated decide what is
+ * computed, like canopy_flux_type%sum); bc_out as in ssb200_radsurf.  Either flux object may
+ * be NULL when the corresponding do_sw / do_lw is false. */
+int ssb200_radsurf_fluxes(const ssb200_config *config,
+                          const ssb200_canopy_properties *canopy_props,
+                          const ssb200_sw_spectral_properties *sw_spectral_props,
+                          const ssb200_lw_spectral_properties *lw_spectral_props,
+                          const ssb200_driver_inputs *driver_inputs,
+                          ssb200_boundary_conds_out *bc_out,
+                          int32_t istartcol, int32_t iendcol,
+                          ssb200_canopy_flux *sw_flux, ssb200_canopy_flux *lw_flux);
+
 /* Device-resident variant.  The three per-column index arrays of
  * `canopy_props` (nlay, istartlay, i_representation) stay HOST pointers (they
  * define the launch plan, which is cached between calls while they do not

@@ -1736,7 +1736,21 @@ static void store_reals(double *dst, const real *src, size_t n) {
 // ---------------------------------------------------------------------------
 // C entry points of liboracle.so (loaded by tests / bench cpu_baseline only)
 // ---------------------------------------------------------------------------
+namespace orc {
+static bool g_count_flops = false;
+static double g_flops_total = 0.0;
+}
+
 extern "C" {
+
+// Instrumented flop counter of the radtool layer (see oracle_radtool.hpp): enable, run
+// oracle_radsurf, read.  Elementwise work outside radtool (Gamma assembly, flux partition)
+// is not counted - it is a few hundred flops per layer.
+void oracle_flops_enable(int on) {
+  orc::g_count_flops = on != 0;
+  orc::g_flops_total = 0.0;
+}
+double oracle_flops_read(void) { return orc::g_flops_total; }
 
 int oracle_legendre_gauss_init(int32_t nstream, ssb200_legendre_gauss *out) {
   if (!out || nstream < 1 || nstream > SSB200_MAX_NSTREAM) return SSB200_ERR_ARG;
@@ -1788,6 +1802,7 @@ int oracle_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   for (int jb = 0; jb < nblock; ++jb) {
     const int c1 = icol1 - 1 + jb * nblocksize;
     const int c2 = std::min(c1 + nblocksize, icol2);
+    orc::g_flops = 0.0;
     for (int jcol = c1; jcol < c2; ++jcol) {
       int rc = orc::radsurf_column(*config, *cp, sw, lw, bc, jcol, sw_norm_dir, sw_norm_diff, lw_internal,
                                    lw_norm, lg_sw_f, lg_sw_u, lg_lw_f, lg_lw_u);
@@ -1797,6 +1812,12 @@ int oracle_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
 #endif
         rc_all = rc;
       }
+    }
+    if (orc::g_count_flops) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+      orc::g_flops_total += orc::g_flops;
     }
   }
   (void)simple_present;

@@ -92,6 +92,7 @@ static inline real fsign(real a, real b) { // Fortran SIGN(a,b)
 // substitution).  1-based indexing is kept internally so that loop bounds and
 // the post-loop values of loop variables (App. B9) read like the Fortran.
 int eigen_decomposition_real(int norder, const Mat &amat, Vec &eigenvalue, Mat &eigenvector) {
+  count_flops(norder >= 3 ? 25.0 * norder * norder * norder : (norder == 2 ? 20.0 : 1.0));
   const real Tol = std::numeric_limits<real>::epsilon();
   const real C1 = 0.4375, C2 = 0.5, C3 = 0.75, C4 = 0.95, C5 = 16.0, C6 = 256.0;
   const int n = norder;

@@ -38,6 +38,13 @@ typedef double real;
 inline real rmax(real a, real b) { return (a < b) ? b : a; }  // std::max semantics
 inline real rmin(real a, real b) { return (b < a) ? b : a; }  // std::min semantics
 
+// Instrumented flop counter (SURVEY.md App. C asks the oracle to publish a measured constant
+// next to the closed-form estimate): every radtool routine adds the flops its loops execute
+// (mul, add, div, sqrt, exp = 1 each; the eigen-solver the 25 k^3 of the SURVEY convention for
+// order k >= 3).  Per thread; oracle_radsurf sums the threads into g_flops_total when enabled.
+extern thread_local double g_flops;
+inline void count_flops(double n) { g_flops += n; }
+
 // One dense matrix of ONE spectral interval.  The reference stores
 // (nmat, i, j) with the spectral index fastest (radtool_matrix.F90:18-24) and
 // loops it innermost; no operation mixes spectral intervals, so looping the
@@ -96,6 +103,7 @@ inline void paste(Mat &A, int i0, int j0, const Mat &B) {
 // radtool_matrix.F90:71-118,125-159,166-199,206-240: y(j1) = sum_j2 A(j1,j2) b(j2),
 // accumulated from zero in ascending j2.
 inline Vec matvec(const Mat &A, const Vec &b) {
+  count_flops(2.0 * A.r * A.c);
   Vec y(A.r, 0.0);
   for (int j1 = 0; j1 < A.r; ++j1)
     for (int j2 = 0; j2 < A.c; ++j2) y[j1] = y[j1] + A(j1, j2) * b[j2];
@@ -107,6 +115,7 @@ inline Vec matvec(const Mat &A, const Vec &b) {
 // accumulated from zero in ascending j3 (dense pattern only; the
 // IMatrixPatternShortwave branch has no callers).
 inline Mat matmul(const Mat &A, const Mat &B) {
+  count_flops(2.0 * A.r * A.c * B.c);
   Mat C(A.r, B.c);
   for (int j2 = 0; j2 < B.c; ++j2)
     for (int j3 = 0; j3 < A.c; ++j3) {
@@ -124,6 +133,7 @@ inline Mat expandedmat_x_mat(int m, int o, int s, const Mat &A, const Mat &B) {
   for (int j1 = 0; j1 < m; ++j1)
     for (int j3 = 0; j3 < o; ++j3)
       if (A(j1, j3) != 0.0) {
+        count_flops(2.0 * s * p);
         const int offset2 = (j3 - j1) * s;
         for (int jj2 = 0; jj2 < p; ++jj2)
           for (int jj1 = j1 * s; jj1 < (j1 + 1) * s; ++jj1)
@@ -140,6 +150,7 @@ inline Mat mat_x_expandedmat(int m, int o, int s, const Mat &A, const Mat &B) {
   for (int j2 = 0; j2 < o; ++j2)
     for (int j3 = 0; j3 < m; ++j3)
       if (B(j3, j2) != 0.0) {
+        count_flops(2.0 * s * p);
         const int offset3 = (j3 - j2) * s;
         for (int jj1 = 0; jj1 < p; ++jj1)
           for (int jj2 = j2 * s; jj2 < (j2 + 1) * s; ++jj2)
@@ -154,6 +165,7 @@ inline Vec expandedmat_x_vec(int m, int k, int s, const Mat &A, const Vec &b) {
   for (int j1 = 0; j1 < m; ++j1)
     for (int j3 = 0; j3 < k; ++j3)
       if (A(j1, j3) != 0.0) {
+        count_flops(2.0 * s);
         const int offset2 = (j3 - j1) * s;
         for (int jj1 = j1 * s; jj1 < (j1 + 1) * s; ++jj1)
           y[jj1] = y[jj1] + A(j1, j3) * b[jj1 + offset2];
@@ -163,6 +175,7 @@ inline Vec expandedmat_x_vec(int m, int k, int s, const Mat &A, const Vec &b) {
 
 // identity_minus_mat_x_mat radtool_matrix.F90:655-691.
 inline Mat identity_minus_mat_x_mat(const Mat &A, const Mat &B) {
+  count_flops((double)A.r);
   Mat C = matmul(A, B);
   for (size_t k = 0; k < C.a.size(); ++k) C.a[k] = -C.a[k];
   for (int j = 0; j < C.r; ++j) C(j, j) = 1.0 + C(j, j);
@@ -172,6 +185,7 @@ inline Mat identity_minus_mat_x_mat(const Mat &A, const Mat &B) {
 // lu_factorization radtool_matrix.F90:982-1017: Crout-style, NO pivoting.
 inline Mat lu_factorization(const Mat &A) {
   const int m = A.r;
+  count_flops(2.0 / 3.0 * m * m * m);
   Mat LU = A;
   for (int j2 = 0; j2 < m; ++j2) {
     for (int j1 = 0; j1 < j2; ++j1) {
@@ -195,6 +209,7 @@ inline Mat lu_factorization(const Mat &A) {
 // lu_substitution radtool_matrix.F90:1024-1049.
 inline Vec lu_substitution(const Mat &LU, const Vec &b) {
   const int m = LU.r;
+  count_flops(2.0 * m * m);
   Vec x(b.begin(), b.begin() + m);
   for (int j2 = 1; j2 < m; ++j2)
     for (int j1 = 0; j1 < j2; ++j1) x[j2] = x[j2] - x[j1] * LU(j2, j1);
@@ -208,6 +223,7 @@ inline Vec lu_substitution(const Mat &LU, const Vec &b) {
 // lu_invert radtool_matrix.F90:1057-1090 (identity right-hand sides).
 inline Mat lu_invert(const Mat &LU) {
   const int m = LU.r;
+  count_flops(2.0 * m * m * m);
   Mat X(m, m);
   for (int j3 = 0; j3 < m; ++j3) {
     X(j3, j3) = 1.0;
@@ -292,6 +308,8 @@ inline Mat solve_rect_mat(const Mat &A, const Mat &B) {
 // and solve_vec_3 (:827-864, explicit LU); re-factorises on every call.
 inline Vec solve_vec(const Mat &A, const Vec &b) {
   const int m = A.r;
+  if (m == 2) count_flops(10.0);
+  if (m == 3) count_flops(25.0);
   if (m == 2) {
     const real inv_det = 1.0 / (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
     Vec x(2);
@@ -321,6 +339,8 @@ inline Vec solve_vec(const Mat &A, const Vec &b) {
 inline Mat solve_mat(const Mat &A, const Mat &B) {
   const int m = A.r;
   Mat X(m, m);
+  if (m == 2) count_flops(16.0);
+  if (m == 3) count_flops(53.0);
   if (m == 2) {
     const real inv_det = 1.0 / (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
     X(0, 0) = inv_det * (A(1, 1) * B(0, 0) - A(0, 1) * B(1, 0));
@@ -354,6 +374,7 @@ inline Mat invert(const Mat &A) { return lu_invert(lu_factorization(A)); }
 // Column scaling A * diag(d): the `A * spread(d,2,n)` idiom
 // (radtool_calc_matrices_sw_eig.F90:194,205-206).
 inline Mat scale_cols(const Mat &A, const Vec &d) {
+  count_flops((double)A.r * A.c);
   Mat B(A.r, A.c);
   for (int j = 0; j < A.c; ++j)
     for (int i = 0; i < A.r; ++i) B(i, j) = A(i, j) * d[j];
@@ -384,9 +405,5 @@ void calc_matrices_lw_eig(int norder, real dz, const Mat &gamma1, const Mat &gam
                           const Vec &emiss_rate, Mat &reflectance, Mat &transmittance,
                           Vec &source, Mat &int_flux, Vec &int_flux_source);
 
-// Instrumented flop counter (SURVEY.md App. C asks the oracle to publish a
-// measured constant next to the closed-form estimate).  Counted analytically
-// per call from the loop bounds; disabled unless enabled by the test.
-extern thread_local double g_flops;
 
 } // namespace orc

@@ -110,9 +110,17 @@ class BoundaryCondsOut(C.Structure):
 
 # Every symbol include/spartacus_b200.h declares (tests check the built library
 # exports all of them).
+class DriverInputs(C.Structure):
+    """ssb200_driver_inputs: what the reference driver feeds around radsurf (top-of-canopy
+    fluxes for scale/sum, temperatures for the LW emission stage)."""
+    _fields_ = [(k, _dp) for k in ("top_flux_dn_sw", "top_flux_dn_direct_sw", "top_flux_dn_lw",
+                                   "ground_temperature", "roof_temperature", "wall_temperature",
+                                   "clear_air_temperature", "veg_temperature", "veg_air_temperature")]
+
+
 EXPORTED_SYMBOLS = [
     "ssb200_version", "ssb200_abi_sizes", "ssb200_last_error", "ssb200_device_count", "ssb200_set_device",
-    "ssb200_legendre_gauss_init", "ssb200_radsurf", "ssb200_radsurf_device",
+    "ssb200_legendre_gauss_init", "ssb200_radsurf", "ssb200_radsurf_device", "ssb200_radsurf_fluxes",
     "ssb200_kernel_launch_count", "ssb200_set_profiling", "ssb200_last_kernel_times_ms", "ssb200_last_kernel_counts",
     "ssb200_release", "ssb200_set_option", "ssb200_canopy_flux_scale_device", "ssb200_canopy_flux_sum_device",
     "ssb200_canopy_flux_check_device", "ssb200_calc_simple_spectrum_lw_device", "ssb200_measure_fp64_peak_tflops",

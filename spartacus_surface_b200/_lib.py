@@ -35,6 +35,9 @@ def _declare(lib):
     lib.ssb200_radsurf.restype = C.c_int
     lib.ssb200_radsurf_device.argtypes = radsurf_args + [C.c_void_p, P(C.c_int32)]
     lib.ssb200_radsurf_device.restype = C.c_int
+    lib.ssb200_radsurf_fluxes.argtypes = (radsurf_args[:4] + [P(_abi.DriverInputs)] + radsurf_args[4:7]
+                                          + [P(_abi.CanopyFlux), P(_abi.CanopyFlux)])
+    lib.ssb200_radsurf_fluxes.restype = C.c_int
     lib.ssb200_kernel_launch_count.restype = C.c_int64
     lib.ssb200_set_profiling.argtypes = [C.c_int]
     lib.ssb200_last_kernel_times_ms.argtypes = [P(C.c_double)]

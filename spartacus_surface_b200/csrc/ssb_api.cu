@@ -124,6 +124,49 @@ __global__ void k_sigma_t4(double *out, const double *emissivity, const double *
   out[(size_t)nspec * i] = emissivity ? (sb * emissivity[(size_t)nspec * i]) * (t2 * t2) : sb * (t2 * t2);
 }
 
+// ---- stages around radsurf for ssb200_radsurf_fluxes ----------------------------------------
+__global__ void k_fill(double *p, double v, long i0, long i1) {
+  const long i = i0 + blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < i1) p[i] = v;
+}
+// read_input's default veg_contact_fraction (driver/spartacus_surface_read_input.F90:155-166)
+__global__ void k_vcf_default(double *vcf, const double *vf, const double *bf, double min_veg, long i0, long i1) {
+  const long i = i0 + blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < i1) vcf[i] = fmin(1.0, vf[i] / fmax(min_veg, 1.0 - bf[i]));
+}
+__global__ void k_lay2col(const int *nlay, const int *istartlay, const int *irep, int ncol, int *lay2col) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncol || irep[j] == SSB200_TILE_FLAT) return;
+  const int l0 = istartlay[j] - 1;
+  for (int l = 0; l < nlay[j]; ++l) lay2col[l0 + l] = j;
+}
+// out = a * fa + b * fb per (interval, column) factor, every product and the sum rounded separately
+// so that the result equals canopy_flux_type%scale followed by %sum bit for bit
+// (radsurf/radsurf_canopy_flux.F90:212-282,399-460).  fa NULL: 1.  fb_minus non-NULL: fb - fb_minus.
+// Non-spectral members (sunlit fractions) are summed unscaled.  Window: columns [c0, c1), layers [l0, l1).
+__global__ void k_scale_sum(FieldList fl, const double *fa, const double *fb, const double *fb_minus,
+                            const int *lay2col, int nspec, long c0, long c1, long l0, long l1) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  for (int f = 0; f < fl.n; ++f) {
+    const int w = fl.spectral[f] ? nspec : 1;
+    const long lo = (fl.per_layer[f] ? l0 : c0) * w, hi = (fl.per_layer[f] ? l1 : c1) * w;
+    const long i = lo + t;
+    if (i >= hi) continue;
+    const double a = fl.a[f][i], b = fl.b[f][i];
+    if (!fl.spectral[f]) {
+      fl.p[f][i] = __dadd_rn(a, b);
+      continue;
+    }
+    const long idx = i / nspec;
+    const int g = (int)(i % nspec);
+    const long col = fl.per_layer[f] ? lay2col[idx] : idx;
+    const size_t k = (size_t)g + (size_t)nspec * (size_t)col;
+    const double xa = fa ? __dmul_rn(fa[k], a) : a;
+    const double fbk = fb_minus ? __dadd_rn(fb[k], -fb_minus[k]) : fb[k];
+    fl.p[f][i] = __dadd_rn(xa, __dmul_rn(fbk, b));
+  }
+}
+
 // register-resident independent DFMA chains: FP64 roofline denominator
 __global__ void k_fp64_peak(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
@@ -185,6 +228,8 @@ struct Context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaError_t first_error = cudaSuccess;
   int fast_mode = 1;
+  size_t l2_set_aside = 0;
+  long lay2col_generation = -1;
   // order the columns of a launch by their segment pattern (fast kernels).  Measured on B200
   // (256k columns, S2): layer kernels 10.1 -> 8.8 ms (full-sector scratch writes), sweeps
   // 9.1 -> 10.7 ms (fewer bytes but longer load latency): off by default.
@@ -192,9 +237,12 @@ struct Context {
   int sort_group = 512;  // ... inside groups of this many neighbouring columns
   int partition = 1;  // group layer problems by solved sub-block before the fast layer kernels
   // column-resident kernels (ssb_fused.cuh) where they exist (1 and 2 streams); 0: split path
-  int fused_mode = 1;
+  int fused_mode = 0;  // measured on B200: 40 % fewer DRAM bytes, 28 % slower - off by default
   int fused_sort = 1;
-  int fused_sort_group = 4096;
+  int fused_sort_group = 0;   // 0: the whole chunk
+  int fused_sync = 0;         // block-aligned phases (ssb_fused.cuh: phase_sync): measured, no gain
+  int fused_blocks_per_sm = 2;
+  int fused_l2_persist = 0;   // pin the private tiles in L2 (access policy window): measured, 25 % slower
   int sm_count = 0;
 };
 Context g_ctx;
@@ -343,7 +391,34 @@ struct CudaBackend {
       cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
       cx.sm_count = n > 0 ? n : 148;
     }
-    return 2 * cx.sm_count;  // __launch_bounds__(128, 2)
+    return cx.fused_blocks_per_sm * cx.sm_count;  // __launch_bounds__(128, 2)
+  }
+  int fused_flags() { return 1 | (cx.fused_sync ? 2 : 0); }
+  // The private tiles are re-read and re-written for every layer of every column while the operator
+  // records, inputs and outputs stream through L2 once: keep the former resident with a persisting
+  // access-policy window on the launch stream (the set-aside is capped by the device limit).
+  void l2_window(const void *base, size_t bytes) {
+    if (!cx.fused_l2_persist) return;
+    int dev = 0, max_persist = 0, max_window = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_persist <= 0 || max_window <= 0) return;
+    const size_t set_aside = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+    if (bytes > 0 && cx.l2_set_aside != set_aside) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess) cx.l2_set_aside = set_aside;
+      cudaGetLastError();
+    }
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+    v.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    v.accessPolicyWindow.hitRatio = bytes > 0 ? (float)((double)set_aside / (double)bytes) : 0.0f;
+    if (v.accessPolicyWindow.hitRatio > 1.0f) v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cudaStreamSetAttribute(cx.stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
   }
   void fused_run(const ssb::ClassArgs &a, bool lw, long width) {
     if (width <= 0 || cx.first_error != cudaSuccess) return;
@@ -351,8 +426,10 @@ struct CudaBackend {
     tick(fam, true);
     const long tiles = (width + ssb::kScratchTile - 1) / ssb::kScratchTile;
     const int grid = (int)(tiles < (long)fused_slots() ? tiles : (long)fused_slots());
+    l2_window(a.layer, (size_t)grid * (size_t)a.ne_layer * ssb::kScratchTile * sizeof(double));
     ssb::fused_launch(a, lw, width, grid, cx.stream);
     check_launch();
+    l2_window(nullptr, 0);
     tick(fam, false);
   }
   void surface(const ssb::SurfaceArgs &s, int nsw_threads, int nlw_threads) {
@@ -468,6 +545,53 @@ int run_window(Context &cx, const ssb::CallArgs &ca, int lane, size_t budget, in
   return 0;
 }
 
+static int collect_fields(ssb200_canopy_flux *o, const ssb200_canopy_flux *a, const ssb200_canopy_flux *b,
+                          FieldList &fl, bool with_sunlit) {
+  fl.n = 0;
+  auto add = [&](double *p, const double *pa, const double *pb, int per_layer, int spectral) {
+    if (!p) return;
+    if (a && (!pa || !pb)) return;
+    fl.p[fl.n] = p;
+    fl.a[fl.n] = pa;
+    fl.b[fl.n] = pb;
+    fl.per_layer[fl.n] = per_layer;
+    fl.spectral[fl.n] = spectral;
+    ++fl.n;
+  };
+#define F(m, pl, sp) add(o->m, a ? a->m : nullptr, b ? b->m : nullptr, pl, sp)
+  F(ground_dn, 0, 1);
+  F(ground_net, 0, 1);
+  F(ground_vertical_diff, 0, 1);
+  F(top_dn, 0, 1);
+  F(top_net, 0, 1);
+  F(ground_dn_dir, 0, 1);
+  F(top_dn_dir, 0, 1);
+  F(roof_in, 1, 1);
+  F(roof_net, 1, 1);
+  F(wall_in, 1, 1);
+  F(wall_net, 1, 1);
+  F(roof_in_dir, 1, 1);
+  F(wall_in_dir, 1, 1);
+  F(clear_air_abs, 1, 1);
+  F(veg_abs, 1, 1);
+  F(veg_air_abs, 1, 1);
+  F(veg_abs_dir, 1, 1);
+  F(flux_dn_layer_top, 1, 1);
+  F(flux_up_layer_top, 1, 1);
+  F(flux_dn_layer_base, 1, 1);
+  F(flux_up_layer_base, 1, 1);
+  F(flux_dn_dir_layer_top, 1, 1);
+  F(flux_dn_dir_layer_base, 1, 1);
+  if (with_sunlit) {
+    F(ground_sunlit_frac, 0, 0);
+    F(roof_sunlit_frac, 1, 0);
+    F(wall_sunlit_frac, 1, 0);
+    F(veg_sunlit_frac, 1, 0);
+  }
+#undef F
+  return fl.n;
+}
+
 // --- host-pointer staging --------------------------------------------------
 struct Stager {
   Context &cx;
@@ -494,6 +618,18 @@ struct Stager {
       return nullptr;
     }
     arrs.push_back(Arr{const_cast<double *>(host), (double *)b.p, width, per_layer, upload, download});
+    return (double *)b.p;
+  }
+  // device-only array (no host counterpart: never copied)
+  double *device_only(size_t total) {
+    if (rc) return nullptr;
+    if ((size_t)next >= cx.stage.size()) cx.stage.resize((size_t)next + 16);
+    DevBuf &b = cx.stage[next++];
+    cudaError_t e = b.reserve((total > 0 ? total : 1) * sizeof(double));
+    if (e != cudaSuccess) {
+      rc = fail(SSB200_ERR_CUDA, std::string("staging allocation: ") + cudaGetErrorString(e));
+      return nullptr;
+    }
     return (double *)b.p;
   }
   // copy the slices of columns [c0, c1) / packed layers [l0, l1) on stream `st`
@@ -617,14 +753,28 @@ int ssb200_radsurf_device(const ssb200_config *config, const ssb200_canopy_prope
   return radsurf_device_locked(g_ctx, ca, istartcol, iendcol, (cudaStream_t)stream, status_out);
 }
 
-int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *cp,
-                   const ssb200_sw_spectral_properties *sw, const ssb200_lw_spectral_properties *lw,
-                   ssb200_boundary_conds_out *bc, int32_t istartcol, int32_t iendcol, ssb200_canopy_flux *sw_dir,
-                   ssb200_canopy_flux *sw_diff, ssb200_canopy_flux *lw_int, ssb200_canopy_flux *lw_norm) {
+// Body of both host entries.  drv == NULL: ssb200_radsurf (the four normalised flux objects are
+// host arrays).  drv != NULL: ssb200_radsurf_fluxes - the normalised objects exist on the device
+// only (shaped like sw_flux / lw_flux), NULL inputs take read_input's defaults or are derived from
+// the temperatures, and every window ends with the fused scale + sum into sw_flux / lw_flux.
+static int radsurf_host(const ssb200_config *config, const ssb200_canopy_properties *cp,
+                        const ssb200_sw_spectral_properties *sw, const ssb200_lw_spectral_properties *lw,
+                        const ssb200_driver_inputs *drv, ssb200_boundary_conds_out *bc, int32_t istartcol,
+                        int32_t iendcol, ssb200_canopy_flux *sw_dir, ssb200_canopy_flux *sw_diff,
+                        ssb200_canopy_flux *lw_int, ssb200_canopy_flux *lw_norm, ssb200_canopy_flux *sw_flux,
+                        ssb200_canopy_flux *lw_flux) {
   int rc = ensure_device();
   if (rc) return rc;
   std::lock_guard<std::mutex> lock(g_mutex);
   Context &cx = g_ctx;
+  if (!config || !cp || !bc) return fail(SSB200_ERR_ARG, "config, canopy_props and bc_out must not be NULL");
+  if (drv) {
+    if ((config->do_sw && (!sw_flux || !drv->top_flux_dn_sw || !drv->top_flux_dn_direct_sw)) ||
+        (config->do_lw && (!lw_flux || !drv->top_flux_dn_lw)))
+      return fail(SSB200_ERR_ARG, "radsurf_fluxes: flux object or top-of-canopy flux missing");
+    sw_dir = sw_diff = sw_flux;  // shape donors for the argument checks
+    lw_int = lw_norm = lw_flux;
+  }
   {
     ssb::CallArgs probe{config, cp, sw, lw, bc, sw_dir, sw_diff, lw_int, lw_norm};
     std::string err;
@@ -655,6 +805,8 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   }
   if (l2 < l1) l1 = l2 = 0;
   const size_t cO = (size_t)(c1 - 1), cN = (size_t)(c2 - c1 + 1), lN = l2 - l1;
+  if (drv && !contiguous)
+    return fail(SSB200_ERR_UNSUPPORTED, "radsurf_fluxes needs the packed layers of the selected columns to be contiguous");
   Stager sg(cx, st);
   ssb200_canopy_properties dcp = *cp;
   auto lay1 = [&](const double *h) { return (const double *)sg.mirror(h, ntot, 1, true, true, false); };
@@ -667,6 +819,29 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   dcp.veg_ext = lay1(cp->veg_ext);
   dcp.veg_fsd = lay1(cp->veg_fsd);
   dcp.veg_contact_fraction = lay1(cp->veg_contact_fraction);
+  // read_input's defaults for members the caller leaves NULL (ssb200_radsurf_fluxes only)
+  struct Fill {
+    double *p;
+    double v;
+    size_t n;
+  };
+  struct Emis {  // out = sigma [emissivity] T^4 on the device, per window
+    double *out;
+    const double *emissivity, *temperature;
+    bool per_layer;
+  };
+  std::vector<Emis> emis;
+  std::vector<Fill> fills;
+  auto filled = [&](size_t width, double v) -> const double * {
+    double *p = sg.device_only(ntot * width);
+    fills.push_back(Fill{p, v, ntot * width});
+    return p;
+  };
+  double *d_vcf_default = nullptr;
+  if (drv && !cp->veg_contact_fraction && cp->veg_fraction && cp->building_fraction) {
+    d_vcf_default = sg.device_only(ntot);
+    dcp.veg_contact_fraction = d_vcf_default;
+  }
   ssb200_sw_spectral_properties dsw;
   ssb200_lw_spectral_properties dlw;
   memset(&dsw, 0, sizeof(dsw));
@@ -685,6 +860,11 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
     dsw.wall_specular_frac = L(sw->wall_specular_frac);
     dsw.ground_albedo_dir = Cc(sw->ground_albedo_dir);
     dsw.roof_albedo_dir = L(sw->roof_albedo_dir);
+    if (drv) {  // driver/spartacus_surface_read_input.F90:258-269,335-344 (roof_albedo_dir NULL: the kernels use roof_albedo)
+      if (!sw->air_ext) dsw.air_ext = filled(g, 1.0e-5);
+      if (!sw->air_ssa) dsw.air_ssa = filled(g, 0.999);
+      if (!sw->wall_specular_frac && sw->wall_albedo) dsw.wall_specular_frac = filled(g, 0.0);
+    }
   }
   if (config->do_lw) {
     const size_t g = (size_t)config->nlw;
@@ -703,6 +883,31 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
     dlw.wall_emissivity = L(lw->wall_emissivity);
     dlw.roof_emission = L(lw->roof_emission);
     dlw.wall_emission = L(lw->wall_emission);
+    if (drv) {  // driver/spartacus_surface_read_input.F90:362-365; radsurf_simple_spectrum.F90:41-66
+      if (!lw->air_ext) dlw.air_ext = filled(g, 1.0e-5);
+      if (!lw->air_ssa) dlw.air_ssa = filled(g, 0.0);
+      auto T1 = [&](const double *h, size_t rows, bool per_layer) {
+        return (const double *)sg.mirror(h, rows, 1, per_layer, true, false);
+      };
+      const bool need_t = !lw->ground_emission || !lw->roof_emission || !lw->wall_emission ||
+                          !lw->clear_air_planck || !lw->veg_planck || !lw->veg_air_planck;
+      if (need_t && g != 1)
+        return fail(SSB200_ERR_ARG, "Simple longwave spectrum only possible with one input spectral interval");
+      if (!lw->ground_emission && drv->ground_temperature) {
+        emis.push_back(Emis{sg.device_only(ncol), dlw.ground_emissivity, T1(drv->ground_temperature, ncol, false), false});
+        dlw.ground_emission = emis.back().out;
+      }
+      auto layer_emis = [&](const double *host_out, const double *&slot, const double *emissivity, const double *t) {
+        if (host_out || !t) return;
+        emis.push_back(Emis{sg.device_only(ntot), emissivity, T1(t, ntot, true), true});
+        slot = emis.back().out;
+      };
+      layer_emis(lw->roof_emission, dlw.roof_emission, dlw.roof_emissivity, drv->roof_temperature);
+      layer_emis(lw->wall_emission, dlw.wall_emission, dlw.wall_emissivity, drv->wall_temperature);
+      layer_emis(lw->clear_air_planck, dlw.clear_air_planck, nullptr, drv->clear_air_temperature);
+      layer_emis(lw->veg_planck, dlw.veg_planck, nullptr, drv->veg_temperature);
+      layer_emis(lw->veg_air_planck, dlw.veg_air_planck, nullptr, drv->veg_air_temperature);
+    }
   }
   // outputs: per-column members are uploaded first (Flat tiles and night-time
   // columns leave some of them untouched); per-layer members are fully
@@ -755,16 +960,66 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
     d.flux_dn_dir_layer_top = L(h->flux_dn_dir_layer_top);
     d.flux_dn_dir_layer_base = L(h->flux_dn_dir_layer_base);
   };
-  ssb200_canopy_flux d1, d2, d3, d4;
-  if (config->do_sw) {
-    stage_flux(sw_dir, d1);
-    stage_flux(sw_diff, d2);
-  }
-  if (config->do_lw) {
-    stage_flux(lw_int, d3);
-    stage_flux(lw_norm, d4);
+  // a normalised flux object that lives on the device only, with the members of `tmpl`
+  std::vector<std::pair<double *, size_t>> zeroed;
+  auto device_flux = [&](const ssb200_canopy_flux *tmpl, ssb200_canopy_flux &d) {
+    d = *tmpl;
+    const size_t g = (size_t)tmpl->nspec;
+    auto make = [&](double *present, size_t total, bool always_zero) -> double * {
+      if (!present) return nullptr;
+      double *p = sg.device_only(total);
+      // members the kernels may leave untouched start from zero (canopy_flux_type%zero_all, driver:184)
+      if (always_zero || !contiguous) zeroed.push_back({p, total});
+      return p;
+    };
+#define SSB_DC(m) d.m = make(tmpl->m, ncol * g, true)
+#define SSB_DL(m) d.m = make(tmpl->m, ntot * g, false)
+    SSB_DC(ground_dn); SSB_DC(ground_net); SSB_DC(ground_vertical_diff); SSB_DC(top_dn); SSB_DC(top_net);
+    SSB_DC(ground_dn_dir); SSB_DC(top_dn_dir);
+    d.ground_sunlit_frac = make(tmpl->ground_sunlit_frac, ncol, true);
+    SSB_DL(roof_in); SSB_DL(roof_net); SSB_DL(wall_in); SSB_DL(wall_net); SSB_DL(roof_in_dir); SSB_DL(wall_in_dir);
+    d.roof_sunlit_frac = make(tmpl->roof_sunlit_frac, ntot, false);
+    d.wall_sunlit_frac = make(tmpl->wall_sunlit_frac, ntot, false);
+    SSB_DL(clear_air_abs); SSB_DL(veg_abs); SSB_DL(veg_air_abs); SSB_DL(veg_abs_dir);
+    d.veg_sunlit_frac = make(tmpl->veg_sunlit_frac, ntot, false);
+    SSB_DL(flux_dn_layer_top); SSB_DL(flux_up_layer_top); SSB_DL(flux_dn_layer_base); SSB_DL(flux_up_layer_base);
+    SSB_DL(flux_dn_dir_layer_top); SSB_DL(flux_dn_dir_layer_base);
+#undef SSB_DC
+#undef SSB_DL
+  };
+  ssb200_canopy_flux d1, d2, d3, d4, dsum_sw, dsum_lw;
+  const double *d_top_sw = nullptr, *d_top_dir = nullptr, *d_top_lw = nullptr;
+  if (drv) {
+    if (config->do_sw) {
+      device_flux(sw_flux, d1);
+      device_flux(sw_flux, d2);
+      stage_flux(sw_flux, dsum_sw);
+      d_top_sw = sg.mirror(drv->top_flux_dn_sw, ncol, (size_t)config->nsw, false, true, false);
+      d_top_dir = sg.mirror(drv->top_flux_dn_direct_sw, ncol, (size_t)config->nsw, false, true, false);
+    }
+    if (config->do_lw) {
+      device_flux(lw_flux, d3);
+      device_flux(lw_flux, d4);
+      stage_flux(lw_flux, dsum_lw);
+      d_top_lw = sg.mirror(drv->top_flux_dn_lw, ncol, (size_t)config->nlw, false, true, false);
+    }
+  } else {
+    if (config->do_sw) {
+      stage_flux(sw_dir, d1);
+      stage_flux(sw_diff, d2);
+    }
+    if (config->do_lw) {
+      stage_flux(lw_int, d3);
+      stage_flux(lw_norm, d4);
+    }
   }
   if (sg.rc) return sg.rc;
+  for (const Fill &f : fills)
+    if (f.n > 0) {
+      k_fill<<<(unsigned)((f.n + 255) / 256), 256, 0, st>>>(f.p, f.v, 0, (long)f.n);
+      ++g_launches;
+    }
+  for (const auto &z : zeroed) SSB_CUDA(cudaMemsetAsync(z.first, 0, z.second * sizeof(double), st));
   ssb::CallArgs ca{config, &dcp, config->do_sw ? &dsw : nullptr, config->do_lw ? &dlw : nullptr, &dbc,
                    config->do_sw ? &d1 : nullptr, config->do_sw ? &d2 : nullptr,
                    config->do_lw ? &d3 : nullptr, config->do_lw ? &d4 : nullptr};
@@ -774,6 +1029,13 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   int range[2];
   rc = radsurf_device_locked(cx, ca, c1, c2, st, nullptr, range);
   if (rc) return rc;
+  if (drv && cx.lay2col_generation != cx.plan.generation) {
+    SSB_CUDA(cx.d_lay2col.reserve(sizeof(int) * (ntot + 1)));
+    k_lay2col<<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>((const int *)cx.d_nlay.p, (const int *)cx.d_istart.p,
+                                                               (const int *)cx.d_irep.p, (int)ncol, (int *)cx.d_lay2col.p);
+    ++g_launches;
+    cx.lay2col_generation = cx.plan.generation;
+  }
   SSB_CUDA(cudaStreamSynchronize(st));  // plan upload and status reset are visible to every lane
   const size_t total_work = lN + cN;
   int nblk = 1;
@@ -810,8 +1072,37 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
       SSB_CUDA(cudaEventRecord(cx.blk_events[2 * b], s_up));
       SSB_CUDA(cudaStreamWaitEvent(s_run, cx.blk_events[2 * b], 0));
     }
+    if (drv) {  // input stage of the window: default contact fraction, emission from temperatures
+      if (d_vcf_default && lb1 > lb0) {
+        k_vcf_default<<<(unsigned)((lb1 - lb0 + 255) / 256), 256, 0, s_run>>>(
+            d_vcf_default, dcp.veg_fraction, dcp.building_fraction, config->min_vegetation_fraction, (long)lb0, (long)lb1);
+        ++g_launches;
+      }
+      for (const Emis &e : emis) {
+        const long i0 = e.per_layer ? (long)lb0 : (long)cb0, i1 = e.per_layer ? (long)lb1 : (long)cb1;
+        if (i1 <= i0) continue;
+        k_sigma_t4<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, s_run>>>(e.out, e.emissivity, e.temperature, 1, i0, i1);
+        ++g_launches;
+      }
+    }
     rc = run_window(cx, ca, 1, cx.budget_doubles, cb0, cb1);
     if (rc) return rc;
+    if (drv) {  // scale + sum of the window (driver:250-261), still on the kernel lane
+      const long cnt = (long)std::max((size_t)(cb1 - cb0), lb1 - lb0);
+      auto scale_sum = [&](ssb200_canopy_flux &o, ssb200_canopy_flux &x, ssb200_canopy_flux &y, const double *fa,
+                           const double *fb, const double *fbm, int nspec) {
+        FieldList fl;
+        collect_fields(&o, &x, &y, fl, true);
+        const long nthr = cnt * nspec;
+        if (fl.n == 0 || nthr <= 0) return;
+        k_scale_sum<<<(unsigned)((nthr + 255) / 256), 256, 0, s_run>>>(fl, fa, fb, fbm, (const int *)cx.d_lay2col.p, nspec,
+                                                                       (long)cb0, (long)cb1, (long)lb0, (long)lb1);
+        ++g_launches;
+      };
+      if (config->do_sw) scale_sum(dsum_sw, d1, d2, d_top_dir, d_top_sw, d_top_dir, config->nsw);
+      if (config->do_lw) scale_sum(dsum_lw, d3, d4, nullptr, d_top_lw, nullptr, config->nlw);
+      SSB_CUDA(cudaGetLastError());
+    }
     if (nblk > 1) {
       SSB_CUDA(cudaEventRecord(cx.blk_events[2 * b + 1], s_run));
       SSB_CUDA(cudaStreamWaitEvent(s_down, cx.blk_events[2 * b + 1], 0));
@@ -823,6 +1114,23 @@ int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
   int status = 0;
   SSB_CUDA(cudaMemcpy(&status, cx.d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
   return status;
+}
+
+int ssb200_radsurf(const ssb200_config *config, const ssb200_canopy_properties *cp,
+                   const ssb200_sw_spectral_properties *sw, const ssb200_lw_spectral_properties *lw,
+                   ssb200_boundary_conds_out *bc, int32_t istartcol, int32_t iendcol, ssb200_canopy_flux *sw_dir,
+                   ssb200_canopy_flux *sw_diff, ssb200_canopy_flux *lw_int, ssb200_canopy_flux *lw_norm) {
+  return radsurf_host(config, cp, sw, lw, nullptr, bc, istartcol, iendcol, sw_dir, sw_diff, lw_int, lw_norm, nullptr,
+                      nullptr);
+}
+
+int ssb200_radsurf_fluxes(const ssb200_config *config, const ssb200_canopy_properties *cp,
+                          const ssb200_sw_spectral_properties *sw, const ssb200_lw_spectral_properties *lw,
+                          const ssb200_driver_inputs *drv, ssb200_boundary_conds_out *bc, int32_t istartcol,
+                          int32_t iendcol, ssb200_canopy_flux *sw_flux, ssb200_canopy_flux *lw_flux) {
+  if (!drv) return fail(SSB200_ERR_ARG, "driver_inputs must not be NULL");
+  return radsurf_host(config, cp, sw, lw, drv, bc, istartcol, iendcol, nullptr, nullptr, nullptr, nullptr, sw_flux,
+                      lw_flux);
 }
 
 int64_t ssb200_kernel_launch_count(void) { return (int64_t)g_launches; }
@@ -884,6 +1192,18 @@ int ssb200_set_option(const char *name, int64_t value) {
     g_ctx.fused_sort_group = (int)value;
     return 0;
   }
+  if (n == "fused_blocks_per_sm") {
+    g_ctx.fused_blocks_per_sm = value < 1 ? 1 : (value > 2 ? 2 : (int)value);
+    return 0;
+  }
+  if (n == "fused_sync") {
+    g_ctx.fused_sync = value != 0;
+    return 0;
+  }
+  if (n == "fused_l2_persist") {
+    g_ctx.fused_l2_persist = value != 0;
+    return 0;
+  }
   if (n == "partition_layers") {
     g_ctx.partition = value != 0;
     return 0;
@@ -908,53 +1228,6 @@ int ssb200_release(void) {
   cx.plan_uploaded = false;
   cx.budget_doubles = 0;
   return 0;
-}
-
-static int collect_fields(ssb200_canopy_flux *o, const ssb200_canopy_flux *a, const ssb200_canopy_flux *b,
-                          FieldList &fl, bool with_sunlit) {
-  fl.n = 0;
-  auto add = [&](double *p, const double *pa, const double *pb, int per_layer, int spectral) {
-    if (!p) return;
-    if (a && (!pa || !pb)) return;
-    fl.p[fl.n] = p;
-    fl.a[fl.n] = pa;
-    fl.b[fl.n] = pb;
-    fl.per_layer[fl.n] = per_layer;
-    fl.spectral[fl.n] = spectral;
-    ++fl.n;
-  };
-#define F(m, pl, sp) add(o->m, a ? a->m : nullptr, b ? b->m : nullptr, pl, sp)
-  F(ground_dn, 0, 1);
-  F(ground_net, 0, 1);
-  F(ground_vertical_diff, 0, 1);
-  F(top_dn, 0, 1);
-  F(top_net, 0, 1);
-  F(ground_dn_dir, 0, 1);
-  F(top_dn_dir, 0, 1);
-  F(roof_in, 1, 1);
-  F(roof_net, 1, 1);
-  F(wall_in, 1, 1);
-  F(wall_net, 1, 1);
-  F(roof_in_dir, 1, 1);
-  F(wall_in_dir, 1, 1);
-  F(clear_air_abs, 1, 1);
-  F(veg_abs, 1, 1);
-  F(veg_air_abs, 1, 1);
-  F(veg_abs_dir, 1, 1);
-  F(flux_dn_layer_top, 1, 1);
-  F(flux_up_layer_top, 1, 1);
-  F(flux_dn_layer_base, 1, 1);
-  F(flux_up_layer_base, 1, 1);
-  F(flux_dn_dir_layer_top, 1, 1);
-  F(flux_dn_dir_layer_base, 1, 1);
-  if (with_sunlit) {
-    F(ground_sunlit_frac, 0, 0);
-    F(roof_sunlit_frac, 1, 0);
-    F(wall_sunlit_frac, 1, 0);
-    F(veg_sunlit_frac, 1, 0);
-  }
-#undef F
-  return fl.n;
 }
 
 int ssb200_canopy_flux_scale_device(ssb200_canopy_flux *flux, const int32_t *nlay, const int32_t *istartlay,

@@ -160,6 +160,7 @@ struct CallArgs {
 //   bool fused_shape(const SolveCfg&, bool lw, int *private_elems, int *op_elems, int *geo_first)
 //        false: no column-resident kernel for this shape (or disabled): split path
 //   int fused_slots()                                private tiles (= resident thread blocks)
+//   int fused_flags()                                ClassArgs::fused (bit 0 set; bit 1: block-aligned phases)
 //   void fused_run(const ClassArgs&, bool lw, long width)
 template <class Backend>
 struct Dispatcher {
@@ -205,7 +206,7 @@ struct Dispatcher {
       a.cols = be.dev_cols(plan, col_offset + pos);
       // the backend may reorder the columns of the chunk (every problem is independent; scratch
       // positions follow the order of a.cols, global arrays are addressed through it)
-      a.fused = fused ? 1 : 0;
+      a.fused = fused ? be.fused_flags() : 0;
       a.cols = be.order_chunk(a, plan.host_cols(col_offset + pos));
       const size_t width = cnt * (size_t)c.nspec;
       double *s = be.scratch(need_of((size_t)lmax, width));

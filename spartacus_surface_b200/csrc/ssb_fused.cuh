@@ -36,6 +36,18 @@
 
 namespace ssb {
 
+// Phase alignment of the warps of a block (device only; a.fused bit 1): the loop body of a column
+// is ~250 KB of straight-line code, far more than the instruction caches hold, so warps that
+// drift apart each stream it from L2 on their own (ncu: 3 stalled warps per issue on
+// `no_instruction`); four warps that enter a phase together fetch it once.
+SSB_HDI void phase_sync(const ClassArgs &a) {
+#if defined(__CUDA_ARCH__)
+  if (a.fused & 2) __syncthreads();
+#else
+  (void)a;
+#endif
+}
+
 SSB_HDI bool region_solved(int seg, int r) { return seg == 0 || (seg == 1 ? r == 0 : r > 0); }
 // class of an element (see seg_class) with a run-time column region
 SSB_HDI bool keep_rc(int seg, int ri, int rj) {
@@ -63,10 +75,10 @@ template <int NREG, int NS, bool URBAN>
 struct SwFused {
   typedef SwSweepLayout<NREG, NS, URBAN> L;
   static constexpr int n = NREG * NS, d = NREG;
-  // private tile: layer elements, geometry block, carried state, parked a_below | d_below
+  // private tile: layer elements, geometry block, carried state (a_below and d_below are parked
+  // over R and S_up)
   static constexpr int oState = L::oGeo + kGeoElems;  // a_above (n x n), d_above (n x d)
-  static constexpr int oPark = oState + n * n + n * d;
-  static constexpr int private_elems = oPark + n * n + n * d;
+  static constexpr int private_elems = oState + n * n + n * d;
   // operator record of one level
   static constexpr int NF = 4;   // clear_air_abs, veg_air_abs, veg_abs, wall_in (diffuse part)
   static constexpr int NFD = 6;  // ... and veg_abs_dir, wall_in_dir
@@ -179,73 +191,13 @@ SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Sc
     }
   }
   const bool prof = a.save_profile != 0;
-  // ---- columns of the diffuse part (rolled: the same code for every column) -----------------
-  SSB_ROLLED
-  for (int j = 0; j < n; ++j) {
-    const int rj = j / NS;
-    if (!region_solved(seg, rj)) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) Lp.st(F::oPark + i + n * j, 0, 0.0);
-      continue;
-    }
-    double p[n], x[n];
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      p[i] = sm(F::sT + i + n * j);
-      x[i] = 0.0;
-    }
-    SSB_UNROLL
-    for (int k = 0; k < n; ++k) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) x[i] = fma(sm(F::sAa + i + n * k), p[k], x[i]);
-    }
-    sm_lu_solve_left<n, 1>(LU, p);
-    sm_lu_solve_left<n, 1>(LU, x);
-    double ab[n], ap[n];
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      ab[i] = Lp.ldp(Lay::oR + i + n * j, 0, keep_rc(seg, i / NS, rj));
-      ap[i] = 0.0;
-    }
-    SSB_UNROLL
-    for (int k = 0; k < n; ++k) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        ab[i] = fma(sm(F::sT + i + n * k), x[k], ab[i]);
-        ap[i] = fma(sm(F::sAa + i + n * k), p[k], ap[i]);
-      }
-    }
-    double sab = 0.0, sap = 0.0;
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      Lp.st(F::oPark + i + n * j, 0, ab[i]);
-      Mo.st(F::mP + i + n * j, jl, p[i]);
-      sab += ab[i];
-      sap += ap[i];
-    }
-    if (prof) {
-      Mo.st(F::mProf + j, jl, sab);
-      Mo.st(F::mProf + (n + d) + j, jl, sap);
-    }
-    // c = e_j - a_below_j - (p - a_above p); functionals W c
-    double fx[NF];
-    SSB_UNROLL
-    for (int f = 0; f < NF; ++f) fx[f] = 0.0;
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      const double c = ((i == j) ? 1.0 : 0.0) - ab[i] - p[i] + ap[i];
-      SSB_UNROLL
-      for (int f = 0; f < NF; ++f) fx[f] = fma(W[f + NF * i], c, fx[f]);
-    }
-    SSB_UNROLL
-    for (int f = 0; f < NF; ++f) Mo.st(F::mFx + f + NF * j, jl, fx[f]);
-  }
-  // ---- columns of the direct part ------------------------------------------------------------
+  // ---- columns of the direct part (first: they read all of R, which the diffuse columns then
+  //      overwrite with a_below, column by column) ----------------------------------------------
   SSB_ROLLED
   for (int j = 0; j < d; ++j) {
     if (!region_solved(seg, j)) {
       SSB_UNROLL
-      for (int i = 0; i < n; ++i) Lp.st(F::oPark + n * n + i + n * j, 0, 0.0);
+      for (int i = 0; i < n; ++i) Lp.st(Lay::oSup + i + n * j, 0, 0.0);
       continue;
     }
     double ecol[d], v[n], q[n], w[n];
@@ -296,7 +248,7 @@ SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Sc
     double sdb = 0.0, sua = 0.0;
     SSB_UNROLL
     for (int i = 0; i < n; ++i) {
-      Lp.st(F::oPark + n * n + i + n * j, 0, db[i]);
+      Lp.st(Lay::oSup + i + n * j, 0, db[i]);  // d_below over S_up (read above)
       Mo.st(F::mQ + i + n * j, jl, q[i]);
       sdb += db[i];
       sua += aq[i] + v[i];
@@ -325,6 +277,67 @@ SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Sc
     SSB_UNROLL
     for (int f = 0; f < NFD; ++f) Mo.st(F::mFd + f + NFD * j, jl, fd[f]);
   }
+  // ---- columns of the diffuse part (rolled: the same code for every column) -----------------
+  SSB_ROLLED
+  for (int j = 0; j < n; ++j) {
+    const int rj = j / NS;
+    if (!region_solved(seg, rj)) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) Lp.st(Lay::oR + i + n * j, 0, 0.0);
+      continue;
+    }
+    double p[n], x[n];
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      p[i] = sm(F::sT + i + n * j);
+      x[i] = 0.0;
+    }
+    SSB_UNROLL
+    for (int k = 0; k < n; ++k) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) x[i] = fma(sm(F::sAa + i + n * k), p[k], x[i]);
+    }
+    sm_lu_solve_left<n, 1>(LU, p);
+    sm_lu_solve_left<n, 1>(LU, x);
+    double ab[n], ap[n];
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      ab[i] = Lp.ldp(Lay::oR + i + n * j, 0, keep_rc(seg, i / NS, rj));
+      ap[i] = 0.0;
+    }
+    SSB_UNROLL
+    for (int k = 0; k < n; ++k) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) {
+        ab[i] = fma(sm(F::sT + i + n * k), x[k], ab[i]);
+        ap[i] = fma(sm(F::sAa + i + n * k), p[k], ap[i]);
+      }
+    }
+    double sab = 0.0, sap = 0.0;
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      Lp.st(Lay::oR + i + n * j, 0, ab[i]);  // a_below over R (column j is not read again)
+      Mo.st(F::mP + i + n * j, jl, p[i]);
+      sab += ab[i];
+      sap += ap[i];
+    }
+    if (prof) {
+      Mo.st(F::mProf + j, jl, sab);
+      Mo.st(F::mProf + (n + d) + j, jl, sap);
+    }
+    // c = e_j - a_below_j - (p - a_above p); functionals W c
+    double fx[NF];
+    SSB_UNROLL
+    for (int f = 0; f < NF; ++f) fx[f] = 0.0;
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      const double c = ((i == j) ? 1.0 : 0.0) - ab[i] - p[i] + ap[i];
+      SSB_UNROLL
+      for (int f = 0; f < NF; ++f) fx[f] = fma(W[f + NF * i], c, fx[f]);
+    }
+    SSB_UNROLL
+    for (int f = 0; f < NF; ++f) Mo.st(F::mFx + f + NF * j, jl, fx[f]);
+  }
   Mo.st(F::mScal, jl, Lp.ld(Lay::oGeo + 6, 0));
   Mo.st(F::mScal + 1, jl, (double)seg);
   // ---- roofs, overlap: state above the next interface (into the private tile) ---------------
@@ -349,13 +362,13 @@ SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Sc
   {
     double Ab[n * n];
     SSB_UNROLL
-    for (int i = 0; i < n * n; ++i) Ab[i] = Lp.ld(F::oPark + i, 0);
+    for (int i = 0; i < n * n; ++i) Ab[i] = Lp.ld(Lay::oR + i, 0);
     overlap_matrix<NREG, NRB, NS>(Ab, rb, U, V, stt, 0);
   }
   {
     double Db[n * d];
     SSB_UNROLL
-    for (int i = 0; i < n * d; ++i) Db[i] = Lp.ld(F::oPark + n * n + i, 0);
+    for (int i = 0; i < n * d; ++i) Db[i] = Lp.ld(Lay::oSup + i, 0);
     SSB_UNROLL
     for (int jt = 0; jt < NS; ++jt) {
       double DV[NREG * NREG];
@@ -393,11 +406,12 @@ SSB_HD inline void fused_layer_sw(const ClassArgs &a, int q, int lev, const Stat
 }
 
 template <int NREG, int NS, bool URBAN>
-SSB_HD inline void fused_column_sw(const ClassArgs &a, int q, const StateMem &st) {
+SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, const StateMem &st) {
   typedef SwFused<NREG, NS, URBAN> F;
   constexpr int n = NREG * NS, d = NREG, NRB = URBAN ? NREG + 1 : NREG, NF = F::NF, NFD = F::NFD;
   const SolveCfg &c = a.cfg;
   const int nspec = c.nspec;
+  const int q = active ? q_in : 0;  // (idle threads of the last tile only keep the barriers company)
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
   const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
@@ -416,9 +430,17 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q, const StateMem &st
     }
   }
   const bool own = (g == itransp);
-  if (!(cos_sza > 0.0)) {  // night: every member of the column is zero (radsurf_interface.F90:193-196)
+  const bool live = active && (cos_sza > 0.0);
+  if (active && !live) {  // night: every member of the column is zero (radsurf_interface.F90:193-196)
     zero_column(fdir, nspec, g, col, il1, nlay, own);
     zero_column(fdif, nspec, g, col, il1, nlay, own);
+  }
+  if (!live) {
+    if (a.fused & 2)
+      for (int jl = 0; jl < a.lmax; ++jl) {
+        phase_sync(a);
+        phase_sync(a);
+      }
     return;
   }
   zero_unwritten_sw<NREG, URBAN>(fdir, nspec, g, col, il1, nlay, own, true);
@@ -450,9 +472,12 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q, const StateMem &st
       }
     }
   }
-  for (int jl = 0; jl < nlay; ++jl) {
-    fused_layer_sw<NREG, NS>(a, q, jl, st);
-    fused_up_step_sw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st, zcos, sin0);
+  const int nloop = (a.fused & 2) ? a.lmax : nlay;
+  for (int jl = 0; jl < nloop; ++jl) {
+    phase_sync(a);
+    if (jl < nlay) fused_layer_sw<NREG, NS>(a, q, jl, st);
+    phase_sync(a);
+    if (jl < nlay) fused_up_step_sw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st, zcos, sin0);
   }
   double talb_diff = 0.0, talb_dir = 0.0;
   {
@@ -708,8 +733,7 @@ struct LwFused {
   typedef LwSweepLayout<NREG, NS, URBAN> L;
   static constexpr int n = NREG * NS, d = NREG;
   static constexpr int oState = L::oGeo + kGeoElems;  // a_above (n x n), source_above (n)
-  static constexpr int oPark = oState + n * n + n;
-  static constexpr int private_elems = oPark + n * n + n;
+  static constexpr int private_elems = oState + n * n + n;
   static constexpr int NF = 4;  // clear_air_abs, veg_air_abs, veg_abs, wall_in
   static constexpr int mFx = 0;                // NF x n
   static constexpr int mF0 = mFx + NF * n;     // NF constants (internal emission pass) + emitted wall power
@@ -807,61 +831,6 @@ SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Sc
     f0[NF] = Lp.ld(Lay::oBook + 3 * d, 0) * dz;
   }
   const bool prof = a.save_profile != 0;
-  SSB_ROLLED
-  for (int j = 0; j < n; ++j) {
-    const int rj = j / NS;
-    if (!region_solved(seg, rj)) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) Lp.st(F::oPark + i + n * j, 0, 0.0);
-      continue;
-    }
-    double p[n], x[n];
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      p[i] = sm(F::sT + i + n * j);
-      x[i] = 0.0;
-    }
-    SSB_UNROLL
-    for (int k = 0; k < n; ++k) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) x[i] = fma(sm(F::sAa + i + n * k), p[k], x[i]);
-    }
-    sm_lu_solve_left<n, 1>(LU, p);
-    sm_lu_solve_left<n, 1>(LU, x);
-    double ab[n], ap[n];
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      ab[i] = Lp.ldp(Lay::oR + i + n * j, 0, keep_rc(seg, i / NS, rj));
-      ap[i] = 0.0;
-    }
-    SSB_UNROLL
-    for (int k = 0; k < n; ++k) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        ab[i] = fma(sm(F::sT + i + n * k), x[k], ab[i]);
-        ap[i] = fma(sm(F::sAa + i + n * k), p[k], ap[i]);
-      }
-    }
-    double sab = 0.0, sap = 0.0, fx[NF];
-    SSB_UNROLL
-    for (int f = 0; f < NF; ++f) fx[f] = 0.0;
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      Lp.st(F::oPark + i + n * j, 0, ab[i]);
-      Mo.st(F::mP + i + n * j, jl, p[i]);
-      sab += ab[i];
-      sap += ap[i];
-      const double c = ((i == j) ? 1.0 : 0.0) + ap[i];  // int_flux acts on x_below + up_above
-      SSB_UNROLL
-      for (int f = 0; f < NF; ++f) fx[f] = fma(W[f + NF * i], c, fx[f]);
-    }
-    SSB_UNROLL
-    for (int f = 0; f < NF; ++f) Mo.st(F::mFx + f + NF * j, jl, fx[f]);
-    if (prof) {
-      Mo.st(F::mProf + j, jl, sab);
-      Mo.st(F::mProf + (n + 1) + j, jl, sap);
-    }
-  }
   {
     // the emission column: p0 = D^-1 (R s_above + src), source_below = src + T D^-1 (s_above + a_above src)
     double src[n], p0[n], w0[n];
@@ -900,7 +869,7 @@ SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Sc
     double ssb_ = 0.0, sua = 0.0;
     SSB_UNROLL
     for (int i = 0; i < n; ++i) {
-      Lp.st(F::oPark + n * n + i, 0, sb[i]);
+      Lp.st(Lay::oSrc + i, 0, sb[i]);  // source_below over the layer source
       Mo.st(F::mP0 + i, jl, p0[i]);
       ssb_ += sb[i];
       sua += ua0[i];
@@ -912,6 +881,61 @@ SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Sc
     if (prof) {
       Mo.st(F::mProf + n, jl, ssb_);
       Mo.st(F::mProf + (n + 1) + n, jl, sua);
+    }
+  }
+  SSB_ROLLED
+  for (int j = 0; j < n; ++j) {
+    const int rj = j / NS;
+    if (!region_solved(seg, rj)) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) Lp.st(Lay::oR + i + n * j, 0, 0.0);
+      continue;
+    }
+    double p[n], x[n];
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      p[i] = sm(F::sT + i + n * j);
+      x[i] = 0.0;
+    }
+    SSB_UNROLL
+    for (int k = 0; k < n; ++k) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) x[i] = fma(sm(F::sAa + i + n * k), p[k], x[i]);
+    }
+    sm_lu_solve_left<n, 1>(LU, p);
+    sm_lu_solve_left<n, 1>(LU, x);
+    double ab[n], ap[n];
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      ab[i] = Lp.ldp(Lay::oR + i + n * j, 0, keep_rc(seg, i / NS, rj));
+      ap[i] = 0.0;
+    }
+    SSB_UNROLL
+    for (int k = 0; k < n; ++k) {
+      SSB_UNROLL
+      for (int i = 0; i < n; ++i) {
+        ab[i] = fma(sm(F::sT + i + n * k), x[k], ab[i]);
+        ap[i] = fma(sm(F::sAa + i + n * k), p[k], ap[i]);
+      }
+    }
+    double sab = 0.0, sap = 0.0, fx[NF];
+    SSB_UNROLL
+    for (int f = 0; f < NF; ++f) fx[f] = 0.0;
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      Lp.st(Lay::oR + i + n * j, 0, ab[i]);  // a_below over R
+      Mo.st(F::mP + i + n * j, jl, p[i]);
+      sab += ab[i];
+      sap += ap[i];
+      const double c = ((i == j) ? 1.0 : 0.0) + ap[i];  // int_flux acts on x_below + up_above
+      SSB_UNROLL
+      for (int f = 0; f < NF; ++f) fx[f] = fma(W[f + NF * i], c, fx[f]);
+    }
+    SSB_UNROLL
+    for (int f = 0; f < NF; ++f) Mo.st(F::mFx + f + NF * j, jl, fx[f]);
+    if (prof) {
+      Mo.st(F::mProf + j, jl, sab);
+      Mo.st(F::mProf + (n + 1) + j, jl, sap);
     }
   }
   Mo.st(F::mScal, jl, (double)seg);
@@ -938,13 +962,13 @@ SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Sc
   {
     double Ab[n * n];
     SSB_UNROLL
-    for (int i = 0; i < n * n; ++i) Ab[i] = Lp.ld(F::oPark + i, 0);
+    for (int i = 0; i < n * n; ++i) Ab[i] = Lp.ld(Lay::oR + i, 0);
     overlap_matrix<NREG, NRB, NS>(Ab, rb, U, V, stt, 0);
   }
   {
     double Sb[n];
     SSB_UNROLL
-    for (int i = 0; i < n; ++i) Sb[i] = Lp.ld(F::oPark + n * n + i, 0);
+    for (int i = 0; i < n; ++i) Sb[i] = Lp.ld(Lay::oSrc + i, 0);
     SSB_UNROLL
     for (int u = 0; u < NREG; ++u) {
       SSB_UNROLL
@@ -967,15 +991,24 @@ SSB_HD inline void fused_layer_lw(const ClassArgs &a, int q, int lev, const Stat
 }
 
 template <int NREG, int NS, bool URBAN>
-SSB_HD inline void fused_column_lw(const ClassArgs &a, int q, const StateMem &st) {
+SSB_HD inline void fused_column_lw(const ClassArgs &a, int q_in, bool active, const StateMem &st) {
   typedef LwFused<NREG, NS, URBAN> F;
   constexpr int n = NREG * NS, NRB = URBAN ? NREG + 1 : NREG, NF = F::NF;
   const SolveCfg &c = a.cfg;
   const int nspec = c.nspec;
+  const int q = active ? q_in : 0;
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
   const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
   const ssb200_canopy_flux &fint = a.f1, &fnorm = a.f2;
+  if (!active) {
+    if (a.fused & 2)
+      for (int jl = 0; jl < a.lmax; ++jl) {
+        phase_sync(a);
+        phase_sync(a);
+      }
+    return;
+  }
   zero_unwritten_lw<NREG, URBAN>(fint, nspec, g, col, il1, nlay);
   zero_unwritten_lw<NREG, URBAN>(fnorm, nspec, g, col, il1, nlay);
   double hw[NS], tang[NS];
@@ -1005,9 +1038,12 @@ SSB_HD inline void fused_column_lw(const ClassArgs &a, int q, const StateMem &st
       Lp.st(F::oState + n * n + jt + r * NS, 0, (hw[jt] * frac0[r]) * gemission);
     }
   }
-  for (int jl = 0; jl < nlay; ++jl) {
-    fused_layer_lw<NREG, NS>(a, q, jl, st);
-    fused_up_step_lw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st);
+  const int nloop = (a.fused & 2) ? a.lmax : nlay;
+  for (int jl = 0; jl < nloop; ++jl) {
+    phase_sync(a);
+    if (jl < nlay) fused_layer_lw<NREG, NS>(a, q, jl, st);
+    phase_sync(a);
+    if (jl < nlay) fused_up_step_lw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st);
   }
   double top_emissivity, top_emission = 0.0;
   {

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(kFusedBlock, 2) k_fused_sw(ClassArgs a, long n
   const long ntiles = (nt + kFusedBlock - 1) / kFusedBlock;
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long q = tile * kFusedBlock + threadIdx.x;
-    if (q < nt) fused_column_sw<NREG, NS, URBAN>(a, (int)q, st);
+    fused_column_sw<NREG, NS, URBAN>(a, (int)q, q < nt, st);
   }
 }
 template <int NREG, int NS, bool URBAN>
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kFusedBlock, 2) k_fused_lw(ClassArgs a, long n
   const long ntiles = (nt + kFusedBlock - 1) / kFusedBlock;
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long q = tile * kFusedBlock + threadIdx.x;
-    if (q < nt) fused_column_lw<NREG, NS, URBAN>(a, (int)q, st);
+    fused_column_lw<NREG, NS, URBAN>(a, (int)q, q < nt, st);
   }
 }
 template <int NREG, int NS, bool URBAN>

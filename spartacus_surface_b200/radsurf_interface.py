@@ -65,3 +65,30 @@ def radsurf(config, canopy_props, sw_spectral_props, lw_spectral_props, bc_out,
     if rc < 0:
         raise RadsurfError(f"ssb200_radsurf failed (rc={rc}): {last_error()}")
     return rc
+
+
+def radsurf_fluxes(config, canopy_props, sw_spectral_props, lw_spectral_props, bc_out, istartcol=None, iendcol=None,
+                   sw_flux=None, lw_flux=None, top_flux_dn_sw=None, top_flux_dn_direct_sw=None, top_flux_dn_lw=None,
+                   ground_temperature=None, roof_temperature=None, wall_temperature=None,
+                   clear_air_temperature=None, veg_temperature=None, veg_air_temperature=None):
+    """The reference driver's sequence for a block of columns in one call
+    (driver/spartacus_surface_driver.F90:206-261): calc_simple_spectrum_lw, radsurf,
+    scale of the normalised fluxes by the top-of-canopy fluxes and sum into `sw_flux` / `lw_flux`.
+    The four normalised flux objects never leave the device; members of the spectral property
+    objects that are None take read_input's defaults or are derived from the temperatures
+    (include/spartacus_b200.h: ssb200_radsurf_fluxes).  Host (numpy) arrays."""
+    from . import _abi
+    lib = load()
+    structs = marshal(config, canopy_props, sw_spectral_props, lw_spectral_props, bc_out)
+    keep = [np_ for np_ in (top_flux_dn_sw, top_flux_dn_direct_sw, top_flux_dn_lw, ground_temperature,
+                            roof_temperature, wall_temperature, clear_air_temperature, veg_temperature,
+                            veg_air_temperature)]
+    drv = _abi.DriverInputs(*[_abi.dptr(a) for a in keep])
+    fsw = sw_flux.as_struct() if sw_flux is not None else None
+    flw = lw_flux.as_struct() if lw_flux is not None else None
+    s = structs
+    rc = lib.ssb200_radsurf_fluxes(_ref(s["config"]), _ref(s["canopy"]), _ref(s["sw"]), _ref(s["lw"]), C.byref(drv),
+                                   _ref(s["bc"]), int(istartcol or 0), int(iendcol or 0), _ref(fsw), _ref(flw))
+    if rc < 0:
+        raise RadsurfError(f"ssb200_radsurf_fluxes failed (rc={rc}): {last_error()}")
+    return rc

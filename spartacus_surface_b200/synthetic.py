@@ -1,7 +1,8 @@
 """Synthetic vegetated-urban canopy profiles of the BASELINE shape
 (SURVEY.md §8d "Value distributions"): every column has `nlay` layers,
 i_representation = VegetatedUrban, monotonically decreasing building fraction,
-vegetation in the lowest L_v layers only (clear-only sub-block aloft).
+vegetation in the lowest L_v layers only (clear-only sub-block aloft); in a quarter of
+the columns the buildings end 1..4 layers below the canopy top (no-building branch).
 
 Values are a pure function of (seed, global column index, field) through a
 counter-based hash, so a column's inputs do not depend on how columns are
@@ -85,6 +86,11 @@ def make_synthetic(config, ncol, nlay=16, col_offset=0, device=None, seed=SEED):
     # b0 (1-x)(1-(p-1)x): monotone decreasing like b0 (1-x)^p but free of pow(), whose last bit
     # differs between numpy and torch/CUDA
     bf = b0[:, None] * ((1.0 - lfrac[None, :]) * (1.0 - (p[:, None] - 1.0) * lfrac[None, :]))
+    # SURVEY 8(d) wants the top layers of some columns to fall below min_building_fraction (the
+    # no-building branch of the urban solvers); neither its power law nor the polynomial above gets
+    # there in 16 layers, so in a quarter of the columns the buildings end 1..4 layers below the top
+    lb = where(u(23) < 0.25, float(nlay) - 1.0 - floor(4.0 * u(24)), float(nlay) + 0.0 * u(24))
+    bf = where(lfrac[None, :] * float(nlay) < lb[:, None], bf, 0.0 * bf)
     cp.building_fraction = flat(bf)
     cp.building_scale = flat((20.0 + 20.0 * u(5))[:, None] + 0.0 * bf)
     lv = 4.0 + floor(9.0 * u(6))

@@ -51,15 +51,16 @@ struct HostBackend {
     return false;
   }
   int fused_slots() { return 1; }
+  int fused_flags() { return 1; }
   template <int NSA, int NREG, bool URBAN>
   void fused_cols(const ssb::ClassArgs &a, bool lw, long width) {
     double stack[512];
     const ssb::StateMem st{stack, 1};
     for (long t = 0; t < width; ++t) {
       if (lw)
-        ssb::fused_column_lw<NREG, NSA, URBAN>(a, (int)t, st);
+        ssb::fused_column_lw<NREG, NSA, URBAN>(a, (int)t, true, st);
       else
-        ssb::fused_column_sw<NREG, NSA, URBAN>(a, (int)t, st);
+        ssb::fused_column_sw<NREG, NSA, URBAN>(a, (int)t, true, st);
     }
   }
   template <int NSA>

@@ -41,6 +41,8 @@ def load(nofma=False, quad=False):
         lib.oracle_calc_matrices_sw_eig.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_double] + [dp] * 12
         lib.oracle_calc_matrices_lw_eig.argtypes = [C.c_int32, C.c_double] + [dp] * 8
         lib.oracle_schur_invert_sw.argtypes = [C.c_int32, C.c_int32] + [dp] * 8
+        lib.oracle_flops_enable.argtypes = [C.c_int]
+        lib.oracle_flops_read.restype = C.c_double
         _libs[path] = lib
     return _libs[path]
 
