@@ -230,7 +230,10 @@ int ssb200_radsurf_fluxes(const ssb200_config *config,
  * reference layout.  Work is enqueued on `stream` (a cudaStream_t passed as
  * void*; NULL = default stream) and the call returns without synchronising;
  * `status_out` (device int32[1], may be NULL) receives the count of flagged
- * problems. */
+ * problems.  Calls share one context (scratch, plan buffers): a call on a
+ * stream other than the previous call's waits (on the device, through an
+ * event) for that call's kernels, so results are correct from any stream, but
+ * calls do not overlap each other. */
 int ssb200_radsurf_device(const ssb200_config *config,
                           const ssb200_canopy_properties *canopy_props,
                           const ssb200_sw_spectral_properties *sw_spectral_props,

@@ -1383,15 +1383,15 @@ static void spartacus_lw(bool urban, const ssb200_config &cfg, int nlw, int ns, 
 
 // ---------------------------------------------------------------------------
 // simple_urban_sw: radsurf_simple_urban_sw.F90:28-294.  icol, ilay 0-based.
-// The reference indexes several (nspec,ncol) fields with ilay (App. B6); this
-// is mirrored literally, guarded only against leaving the array.
+// The reference indexes several (nspec,ncol) fields with ilay (:193,219,253-256; App. B6), which
+// is only defined when istartlay(icol) = icol (as in test/single_layer).  They are indexed with
+// icol here: identical whenever the reference is well defined, in bounds otherwise.
 // ---------------------------------------------------------------------------
 static int simple_urban_sw(const ssb200_config &cfg, bool is_infinite_street, int nsw, int icol,
                            int ilay, real cos_sza, const ssb200_canopy_properties &cp,
                            const ssb200_sw_spectral_properties &sw,
                            const double *ground_albedo_diff, const double *ground_albedo_dir,
                            ssb200_canopy_flux *ndir, ssb200_canopy_flux *ndiff) {
-  if (ilay >= cp.ncol) return SSB200_ERR_ARG; // would index outside (nspec,ncol)
   const real dz = cp.dz[ilay];
   const double building_fraction = cp.building_fraction[ilay];
   const double building_scale = cp.building_scale[ilay];
@@ -1430,7 +1430,7 @@ static int simple_urban_sw(const ssb200_config &cfg, bool is_infinite_street, in
     sol = solve_vec(im, src);
     XC(ndir, ground_dn_dir, g, icol) = view_dir_ground * (1.0 - building_fraction);
     XC(ndir, ground_dn, g, icol) = XC(ndir, ground_dn_dir, g, icol) + sol[0];
-    XC(ndir, ground_net, g, icol) = XC(ndir, ground_dn_dir, g, ilay) * (1.0 - ground_albedo_dir[g]) +
+    XC(ndir, ground_net, g, icol) = XC(ndir, ground_dn_dir, g, icol) * (1.0 - ground_albedo_dir[g]) +
                                     sol[0] * (1.0 - ground_albedo_diff[g]);
     ndir->ground_sunlit_frac[icol] = view_dir_ground;
     XC(ndir, roof_in_dir, g, ilay) = building_fraction;
@@ -1448,24 +1448,24 @@ static int simple_urban_sw(const ssb200_config &cfg, bool is_infinite_street, in
     XC(ndir, top_dn, g, icol) = 1.0;
     XC(ndir, top_net, g, icol) =
         1.0 - building_fraction * roof_albedo -
-        (XC(ndir, ground_dn, g, ilay) - XC(ndir, ground_net, g, ilay)) * view_ground_sky -
+        (XC(ndir, ground_dn, g, icol) - XC(ndir, ground_net, g, icol)) * view_ground_sky -
         (XC(ndir, wall_in, g, ilay) - XC(ndir, wall_net, g, ilay)) * view_wall_ground;
     if (ndir->flux_dn_layer_top) {
       XC(ndir, flux_dn_dir_layer_top, g, ilay) = (1.0 - building_fraction);
       XC(ndir, flux_dn_layer_top, g, ilay) = (1.0 - building_fraction);
       XC(ndir, flux_up_layer_top, g, ilay) =
-          (XC(ndir, ground_dn, g, ilay) - XC(ndir, ground_net, g, ilay)) * view_ground_sky +
+          (XC(ndir, ground_dn, g, icol) - XC(ndir, ground_net, g, icol)) * view_ground_sky +
           (XC(ndir, wall_in, g, ilay) - XC(ndir, wall_net, g, ilay)) * view_wall_ground;
-      XC(ndir, flux_dn_dir_layer_base, g, ilay) = XC(ndir, ground_dn_dir, g, ilay);
-      XC(ndir, flux_dn_layer_base, g, ilay) = XC(ndir, ground_dn, g, ilay);
-      XC(ndir, flux_up_layer_base, g, ilay) = XC(ndir, ground_dn, g, ilay) - XC(ndir, ground_net, g, ilay);
+      XC(ndir, flux_dn_dir_layer_base, g, ilay) = XC(ndir, ground_dn_dir, g, icol);
+      XC(ndir, flux_dn_layer_base, g, ilay) = XC(ndir, ground_dn, g, icol);
+      XC(ndir, flux_up_layer_base, g, ilay) = XC(ndir, ground_dn, g, icol) - XC(ndir, ground_net, g, icol);
     }
     src[0] = view_ground_sky * (1.0 - building_fraction);
     src[1] = view_ground_wall * (1.0 - building_fraction);
     sol = solve_vec(im, src);
-    XC(ndiff, ground_dn_dir, g, ilay) = 0.0;
-    XC(ndiff, ground_dn, g, ilay) = sol[0];
-    XC(ndiff, ground_net, g, ilay) = XC(ndiff, ground_dn, g, ilay) * (1.0 - ground_albedo_diff[g]);
+    XC(ndiff, ground_dn_dir, g, icol) = 0.0;
+    XC(ndiff, ground_dn, g, icol) = sol[0];
+    XC(ndiff, ground_net, g, icol) = XC(ndiff, ground_dn, g, icol) * (1.0 - ground_albedo_diff[g]);
     XC(ndiff, roof_in, g, ilay) = building_fraction;
     XC(ndiff, roof_net, g, ilay) = building_fraction * (1.0 - roof_albedo);
     XC(ndiff, wall_in, g, ilay) = sol[1];
@@ -1474,15 +1474,15 @@ static int simple_urban_sw(const ssb200_config &cfg, bool is_infinite_street, in
     XC(ndiff, top_dn, g, icol) = 1.0;
     XC(ndiff, top_net, g, icol) =
         1.0 - building_fraction * roof_albedo -
-        (XC(ndiff, ground_dn, g, ilay) - XC(ndiff, ground_net, g, ilay)) * view_ground_sky -
+        (XC(ndiff, ground_dn, g, icol) - XC(ndiff, ground_net, g, icol)) * view_ground_sky -
         (XC(ndiff, wall_in, g, ilay) - XC(ndiff, wall_net, g, ilay)) * view_wall_ground;
     if (ndiff->flux_dn_layer_top) {
       XC(ndiff, flux_dn_layer_top, g, ilay) = (1.0 - building_fraction);
       XC(ndiff, flux_up_layer_top, g, ilay) =
-          (XC(ndiff, ground_dn, g, ilay) - XC(ndiff, ground_net, g, ilay)) * view_ground_sky +
+          (XC(ndiff, ground_dn, g, icol) - XC(ndiff, ground_net, g, icol)) * view_ground_sky +
           (XC(ndiff, wall_in, g, ilay) - XC(ndiff, wall_net, g, ilay)) * view_wall_ground;
-      XC(ndiff, flux_dn_layer_base, g, ilay) = XC(ndiff, ground_dn, g, ilay);
-      XC(ndiff, flux_up_layer_base, g, ilay) = XC(ndiff, ground_dn, g, ilay) - XC(ndiff, ground_net, g, ilay);
+      XC(ndiff, flux_dn_layer_base, g, ilay) = XC(ndiff, ground_dn, g, icol);
+      XC(ndiff, flux_up_layer_base, g, ilay) = XC(ndiff, ground_dn, g, icol) - XC(ndiff, ground_net, g, icol);
     }
   }
   return 0;
@@ -1493,7 +1493,6 @@ static int simple_urban_lw(const ssb200_config &cfg, bool is_infinite_street, in
                            int ilay, const ssb200_canopy_properties &cp,
                            const ssb200_lw_spectral_properties &lw, ssb200_canopy_flux *lint,
                            ssb200_canopy_flux *lnorm) {
-  if (ilay >= cp.ncol) return SSB200_ERR_ARG;
   const int nsw = nlw;
   const real dz = cp.dz[ilay];
   const double building_fraction = cp.building_fraction[ilay];
@@ -1541,21 +1540,21 @@ static int simple_urban_lw(const ssb200_config &cfg, bool is_infinite_street, in
     XC(lint, top_dn, g, icol) = 0.0;
     XC(lint, top_net, g, icol) =
         -building_fraction * roof_emission -
-        (XC(lint, ground_dn, g, ilay) - XC(lint, ground_net, g, ilay)) * view_ground_sky -
+        (XC(lint, ground_dn, g, icol) - XC(lint, ground_net, g, icol)) * view_ground_sky -
         (XC(lint, wall_in, g, ilay) - XC(lint, wall_net, g, ilay)) * view_wall_ground;
     if (lint->flux_dn_layer_top) {
       XC(lint, flux_dn_layer_top, g, ilay) = 0.0;
       XC(lint, flux_up_layer_top, g, ilay) =
-          (XC(lint, ground_dn, g, ilay) - XC(lint, ground_net, g, ilay)) * view_ground_sky +
+          (XC(lint, ground_dn, g, icol) - XC(lint, ground_net, g, icol)) * view_ground_sky +
           (XC(lint, wall_in, g, ilay) - XC(lint, wall_net, g, ilay)) * view_wall_ground;
-      XC(lint, flux_dn_layer_base, g, ilay) = XC(lint, ground_dn, g, ilay);
-      XC(lint, flux_up_layer_base, g, ilay) = XC(lint, ground_dn, g, ilay) - XC(lint, ground_net, g, ilay);
+      XC(lint, flux_dn_layer_base, g, ilay) = XC(lint, ground_dn, g, icol);
+      XC(lint, flux_up_layer_base, g, ilay) = XC(lint, ground_dn, g, icol) - XC(lint, ground_net, g, icol);
     }
     src[0] = view_ground_sky * (1.0 - building_fraction);
     src[1] = view_ground_wall * (1.0 - building_fraction);
     sol = solve_vec(im, src);
-    XC(lnorm, ground_dn, g, ilay) = sol[0];
-    XC(lnorm, ground_net, g, ilay) = XC(lnorm, ground_dn, g, ilay) * ground_emissivity;
+    XC(lnorm, ground_dn, g, icol) = sol[0];
+    XC(lnorm, ground_net, g, icol) = XC(lnorm, ground_dn, g, icol) * ground_emissivity;
     XC(lnorm, roof_in, g, ilay) = building_fraction;
     XC(lnorm, roof_net, g, ilay) = building_fraction * roof_emissivity;
     XC(lnorm, wall_in, g, ilay) = sol[1];
@@ -1563,15 +1562,15 @@ static int simple_urban_lw(const ssb200_config &cfg, bool is_infinite_street, in
     XC(lnorm, top_dn, g, icol) = 1.0;
     XC(lnorm, top_net, g, icol) =
         1.0 - building_fraction * (1.0 - roof_emissivity) -
-        (XC(lnorm, ground_dn, g, ilay) - XC(lnorm, ground_net, g, ilay)) * view_ground_sky -
+        (XC(lnorm, ground_dn, g, icol) - XC(lnorm, ground_net, g, icol)) * view_ground_sky -
         (XC(lnorm, wall_in, g, ilay) - XC(lnorm, wall_net, g, ilay)) * view_wall_ground;
     if (lnorm->flux_dn_layer_top) {
       XC(lnorm, flux_dn_layer_top, g, ilay) = 1.0 - building_fraction;
       XC(lnorm, flux_up_layer_top, g, ilay) =
-          (XC(lnorm, ground_dn, g, ilay) - XC(lnorm, ground_net, g, ilay)) * view_ground_sky +
+          (XC(lnorm, ground_dn, g, icol) - XC(lnorm, ground_net, g, icol)) * view_ground_sky +
           (XC(lnorm, wall_in, g, ilay) - XC(lnorm, wall_net, g, ilay)) * view_wall_ground;
-      XC(lnorm, flux_dn_layer_base, g, ilay) = XC(lnorm, ground_dn, g, ilay);
-      XC(lnorm, flux_up_layer_base, g, ilay) = XC(lnorm, ground_dn, g, ilay) - XC(lnorm, ground_net, g, ilay);
+      XC(lnorm, flux_dn_layer_base, g, ilay) = XC(lnorm, ground_dn, g, icol);
+      XC(lnorm, flux_up_layer_base, g, ilay) = XC(lnorm, ground_dn, g, icol) - XC(lnorm, ground_net, g, icol);
     }
   }
   return 0;
@@ -1796,7 +1795,6 @@ int oracle_radsurf(const ssb200_config *config, const ssb200_canopy_properties *
     if (cp->i_representation[j] >= SSB200_TILE_SIMPLE_URBAN) simple_present = true;
 #ifdef _OPENMP
   int nt = nthreads > 0 ? nthreads : omp_get_max_threads();
-  if (simple_present) nt = 1; // App. B6 cross-column indexing is order dependent
 #pragma omp parallel for schedule(dynamic) num_threads(nt)
 #endif
   for (int jb = 0; jb < nblock; ++jb) {

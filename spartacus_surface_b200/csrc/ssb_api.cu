@@ -226,6 +226,9 @@ struct Context {
   double times_ms[5] = {0, 0, 0, 0, 0};
   long long counts[5] = {0, 0, 0, 0, 0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_done = nullptr;  // end of the last device-entry call (cross-stream ordering)
+  cudaStream_t last_stream = nullptr;
+  bool last_stream_valid = false;
   cudaError_t first_error = cudaSuccess;
   int fast_mode = 1;
   size_t l2_set_aside = 0;
@@ -491,6 +494,11 @@ int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, i
     cx.plan.valid = false;
     return fail(rc, err);
   }
+  rc = ssb::validate_members(ca, cx.plan, err);
+  if (rc) return fail(rc, err);
+  // One Context (scratch, status word, plan buffers) serves every call: work of an earlier call
+  // that is still in flight on ANOTHER stream must finish before this call reuses them.
+  if (cx.ev_done && cx.last_stream_valid && cx.last_stream != stream) SSB_CUDA(cudaStreamWaitEvent(stream, cx.ev_done, 0));
   if (cx.plan.generation != cx.uploaded_generation) cx.plan_uploaded = false;
   if (!cx.plan_uploaded) {
     rc = upload_plan(cx, cp);
@@ -527,6 +535,10 @@ int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, i
     return fail(SSB200_ERR_CUDA, std::string("kernel launch / scratch allocation: ") + cudaGetErrorString(cx.first_error));
   if (status_out)
     SSB_CUDA(cudaMemcpyAsync(status_out, cx.d_status.p, sizeof(int), cudaMemcpyDeviceToDevice, stream));
+  if (!cx.ev_done) SSB_CUDA(cudaEventCreateWithFlags(&cx.ev_done, cudaEventDisableTiming));
+  SSB_CUDA(cudaEventRecord(cx.ev_done, stream));
+  cx.last_stream = stream;
+  cx.last_stream_valid = true;
   return 0;
 }
 
@@ -886,8 +898,15 @@ static int radsurf_host(const ssb200_config *config, const ssb200_canopy_propert
     if (drv) {  // driver/spartacus_surface_read_input.F90:362-365; radsurf_simple_spectrum.F90:41-66
       if (!lw->air_ext) dlw.air_ext = filled(g, 1.0e-5);
       if (!lw->air_ssa) dlw.air_ssa = filled(g, 0.0);
+      // (the same host array given for several temperatures - the driver passes one air temperature
+      // for clear air, vegetation and the air in vegetation - is uploaded once)
+      std::vector<std::pair<const double *, const double *>> t_seen;
       auto T1 = [&](const double *h, size_t rows, bool per_layer) {
-        return (const double *)sg.mirror(h, rows, 1, per_layer, true, false);
+        for (const auto &s : t_seen)
+          if (s.first == h) return s.second;
+        const double *d = (const double *)sg.mirror(h, rows, 1, per_layer, true, false);
+        t_seen.push_back({h, d});
+        return d;
       };
       const bool need_t = !lw->ground_emission || !lw->roof_emission || !lw->wall_emission ||
                           !lw->clear_air_planck || !lw->veg_planck || !lw->veg_air_planck;
@@ -1062,6 +1081,16 @@ static int radsurf_host(const ssb200_config *config, const ssb200_canopy_propert
       if (cp->i_representation[j] != SSB200_TILE_FLAT && cp->nlay[j] > 0) return (size_t)cp->istartlay[j] - 1;
     return l2;
   };
+  // an error return inside the loop must not leave queued copies reading / writing the caller's
+  // host arrays after the function has returned (the caller may free them): drain the lanes first
+  struct LaneDrain {
+    Context &cx;
+    bool armed = true;
+    ~LaneDrain() {
+      if (armed)
+        for (int l = 0; l < Context::kLanes; ++l) cudaStreamSynchronize(cx.lane_stream[l]);
+    }
+  } drain{cx};
   for (int b = 0; b < nblk; ++b) {
     const int cb0 = (c1 - 1) + (int)(((long long)cN * b) / nblk), cb1 = (c1 - 1) + (int)(((long long)cN * (b + 1)) / nblk);
     if (cb1 <= cb0) continue;
@@ -1111,6 +1140,7 @@ static int radsurf_host(const ssb200_config *config, const ssb200_canopy_propert
     if (rc) return rc;
   }
   for (int l = 0; l < Context::kLanes; ++l) SSB_CUDA(cudaStreamSynchronize(cx.lane_stream[l]));
+  drain.armed = false;
   int status = 0;
   SSB_CUDA(cudaMemcpy(&status, cx.d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
   return status;

@@ -119,7 +119,10 @@ inline int build_plan(const ssb200_config &cfg, const ssb200_canopy_properties &
         plan.surface_cols.push_back(j);
         break;
       default:
-        break;  // unknown codes are skipped like the reference's select case
+        // the reference's select case would skip the column; a code outside the six tile types is
+        // an input error, and reporting it keeps stale staging data from reaching the caller
+        err = "column " + std::to_string(j + 1) + ": unknown i_representation " + std::to_string(irep);
+        return SSB200_ERR_ARG;
     }
   }
   for (auto &k : plan.classes) {
@@ -364,6 +367,78 @@ inline int validate_call(const CallArgs &ca, std::string &err) {
       err = "longwave spectral resolution mismatch (config%nlw vs arrays)";
       return SSB200_ERR_SHAPE;
     }
+  }
+  return 0;
+}
+
+// The members each tile class present in the plan dereferences (the kernels do not test them):
+// a NULL one is an argument error here instead of an illegal address on the device, which would
+// poison the CUDA context of the whole process.
+inline int validate_members(const CallArgs &ca, const Plan &plan, std::string &err) {
+  const ssb200_config &cfg = *ca.config;
+  const ssb200_canopy_properties &cp = *ca.cp;
+  bool layered = false, urban = false, veg = false, three = false, simple = false;
+  for (const auto &k : plan.classes) {
+    if (k.cols.empty()) continue;
+    layered = true;
+    urban = urban || k.urban;
+    veg = veg || k.nreg > 1 || !k.urban;
+    three = three || k.nreg == 3;
+  }
+  for (int j : plan.surface_cols) simple = simple || plan.irep[j] >= SSB200_TILE_SIMPLE_URBAN;
+  std::string missing;
+  auto need = [&](const void *p, const char *name) {
+    if (!p) missing += (missing.empty() ? "" : ", ") + std::string(name);
+  };
+  if (layered || simple) need(cp.dz, "canopy_props%dz");
+  if (urban || simple) {
+    need(cp.building_fraction, "canopy_props%building_fraction");
+    need(cp.building_scale, "canopy_props%building_scale");
+  }
+  if (veg) {
+    need(cp.veg_fraction, "canopy_props%veg_fraction");
+    need(cp.veg_scale, "canopy_props%veg_scale");
+    need(cp.veg_ext, "canopy_props%veg_ext");
+  }
+  if (three) need(cp.veg_fsd, "canopy_props%veg_fsd");
+  if (cfg.do_sw) {
+    const ssb200_sw_spectral_properties &sw = *ca.sw;
+    need(sw.ground_albedo, "sw%ground_albedo");
+    if (layered) {
+      need(sw.air_ext, "sw%air_ext");
+      need(sw.air_ssa, "sw%air_ssa");
+    }
+    if (veg) need(sw.veg_ssa, "sw%veg_ssa");
+    if (urban || simple) {
+      need(sw.roof_albedo, "sw%roof_albedo");
+      need(sw.wall_albedo, "sw%wall_albedo");
+    }
+    if (urban) need(sw.wall_specular_frac, "sw%wall_specular_frac");
+  }
+  if (cfg.do_lw) {
+    const ssb200_lw_spectral_properties &lw = *ca.lw;
+    need(lw.ground_emissivity, "lw%ground_emissivity");
+    need(lw.ground_emission, "lw%ground_emission");
+    if (layered) {
+      need(lw.air_ext, "lw%air_ext");
+      need(lw.air_ssa, "lw%air_ssa");
+      need(lw.clear_air_planck, "lw%clear_air_planck");
+    }
+    if (veg) {
+      need(lw.veg_ssa, "lw%veg_ssa");
+      need(lw.veg_planck, "lw%veg_planck");
+      need(lw.veg_air_planck, "lw%veg_air_planck");
+    }
+    if (urban || simple) {
+      need(lw.roof_emissivity, "lw%roof_emissivity");
+      need(lw.wall_emissivity, "lw%wall_emissivity");
+      need(lw.roof_emission, "lw%roof_emission");
+      need(lw.wall_emission, "lw%wall_emission");
+    }
+  }
+  if (!missing.empty()) {
+    err = "members needed by the tile types present are not allocated: " + missing;
+    return SSB200_ERR_ARG;
   }
   return 0;
 }

@@ -136,15 +136,19 @@ struct LayerCoef {
 // diagonal mass; from then on it applies identity rotations only, so its result does not
 // depend on how many more sweeps its warp neighbours need (the sweeps stop when all lanes
 // have converged or after `max_sweeps`).
+// Returns false when the scaled criterion is still violated after `max_sweeps` sweeps (the
+// reference counts such problems in nerror / ierror, radtool_eigen_decomposition.F90:92-100,
+// 498-510); the caller reports it through the status word.
 template <int N>
-SSB_HDI void sm_jacobi_sym(double *Y, double *U, int max_sweeps) {
+SSB_HDI bool sm_jacobi_sym(double *Y, double *U, int max_sweeps) {
 #define SSB_YS(a, b) Y[((a) >= (b)) ? ((a) + N * (b)) : ((b) + N * (a))]
   SSB_UNROLL
   for (int j = 0; j < N; ++j) {
     SSB_UNROLL
     for (int i = 0; i < N; ++i) U[i + N * j] = (i == j) ? 1.0 : 0.0;
   }
-  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+  bool done = false;
+  for (int sweep = 0; sweep <= max_sweeps; ++sweep) {
     // scaled criterion |a_pq| <= tol sqrt(a_pp a_qq) for every pair: what gives the small
     // eigenvalues of a graded matrix their RELATIVE accuracy (a test against the total diagonal
     // mass stops while the entries that couple the small eigenvalues are still 1e-4 of them:
@@ -156,7 +160,8 @@ SSB_HDI void sm_jacobi_sym(double *Y, double *U, int max_sweeps) {
       for (int q = p + 1; q < N; ++q)
         converged = converged && (Y[q + N * p] * Y[q + N * p] <= kJacobiTol2 * fabs(Y[p + N * p] * Y[q + N * q]));
     }
-    if (all_lanes(converged)) break;
+    done = converged;
+    if (sweep == max_sweeps || all_lanes(converged)) break;  // (the last pass only tests)
     SSB_UNROLL
     for (int p = 0; p < N - 1; ++p) {
       SSB_UNROLL
@@ -193,17 +198,19 @@ SSB_HDI void sm_jacobi_sym(double *Y, double *U, int max_sweeps) {
     }
   }
 #undef SSB_YS
+  return done;
 }
 
 // Eigen-system of P = D S: Cholesky of -N D, Y = L^T K L, Jacobi.  Leaves U, L, L^-1 in
 // the stack slice and returns lambda = sqrt(eigenvalue), e = exp(-lambda dz) and the
 // eigenvalues themselves.
 template <int NR, int NS>
-SSB_HDI void layer_eigen(const LayerCoef<NR, NS> &c, double dz, const StateMem &st, double *lam2, double *lam,
+SSB_HDI bool layer_eigen(const LayerCoef<NR, NS> &c, double dz, const StateMem &st, double *lam2, double *lam,
                          double *e) {
   typedef LayerStack<NR, NS> Stk;
   constexpr int N = NR * NS;
   double U[N * N];
+  bool converged;
   {
     double Y[N * N];  // lower triangle
     {
@@ -270,7 +277,7 @@ SSB_HDI void layer_eigen(const LayerCoef<NR, NS> &c, double dz, const StateMem &
         for (int i = j; i < N; i += NS) st(Stk::oL + lslot<NR, NS>(i, j)) = L[i + N * j];
       }
     }
-    sm_jacobi_sym<N>(Y, U, kJacobiSweeps(N));
+    converged = sm_jacobi_sym<N>(Y, U, kJacobiSweeps(N));
     SSB_UNROLL
     for (int k = 0; k < N; ++k) lam2[k] = Y[k + N * k];
   }
@@ -281,6 +288,7 @@ SSB_HDI void layer_eigen(const LayerCoef<NR, NS> &c, double dz, const StateMem &
     lam[k] = sqrt(dmax(0.0, lam2[k]));
     e[k] = exp(-lam[k] * dz);
   }
+  return converged;
 }
 
 // rows i of V = N^-1 L U and M = L^-T U diag(lam) from the stack slice
@@ -369,6 +377,7 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
   constexpr int oU0 = Stk::oX, oEps = oU0 + D * D, oSq = oEps + D, oRsq = oSq + D;
   // ---- direct beam: g0 = B0 diag(1/frac) with B0 symmetric -> symmetric Jacobi ----------
   double g0inv[D * D];
+  bool jac0;
   {
     double sq[D], rsq[D], Y0[D * D], U0[D * D];
     SSB_UNROLL
@@ -381,7 +390,7 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
       SSB_UNROLL
       for (int i = j; i < D; ++i) Y0[i + D * j] = c.g0(i, j) * sq[j] * rsq[i];
     }
-    sm_jacobi_sym<D>(Y0, U0, kJacobiSweeps(D));
+    jac0 = sm_jacobi_sym<D>(Y0, U0, kJacobiSweeps(D));
     double e0[D], reps[D];
     SSB_UNROLL
     for (int k = 0; k < D; ++k) {
@@ -447,9 +456,8 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
   }
   // ---- diffuse eigen-system and the two-point solve ---------------------------------------
   double lam2[N], lam[N], e[N];
-  layer_eigen<NR, NS>(c, dz, st_in, lam2, lam, e);
+  bool bad = !layer_eigen<NR, NS>(c, dz, st_in, lam2, lam, e) || !jac0;
   const StateMem st = opaque(st_in);
-  bool bad = false;
   {
     // sum (sigma = +1) then difference (-1) problem; rows of B pass through the T slot, X+ is
     // parked in the R slot.  Rolled loops: the same code serves both stages and all rows.
@@ -521,7 +529,16 @@ SSB_HDI bool layer_sw_solve(const LayerCoef<NR, NS> &c, double dz, double *P, co
         double s = 0.0;
         SSB_UNROLL
         for (int i = 0; i < N; ++i) s = fma(st(Stk::oU + i + N * k), w[i], s);
-        t[k] = 2.0 * s / fma(eps, eps, -lam2[k]);
+        // eps^2 = lambda_k^2 (a direct-beam mode decaying exactly like a diffuse mode) is a removable
+        // singularity of S_up / S_dn, but a pole of this particular solution (the reference's
+        // Gamma1 - Q Gamma2 - eps I is singular there too, radtool_calc_matrices_sw_eig.F90:232-253):
+        // keep the two apart by 1e-8 relative, which perturbs the sources by that order instead of
+        // returning Inf / NaN
+        const double e2 = eps * eps;
+        double den = e2 - lam2[k];
+        const double dmin = 1.0e-8 * (e2 + fabs(lam2[k]));
+        if (fabs(den) < dmin) den = (den < 0.0) ? -dmin : dmin;
+        t[k] = 2.0 * s / den;
       }
       SSB_UNROLL
       for (int i = 0; i < N; ++i) {
@@ -643,9 +660,8 @@ SSB_HDI bool layer_lw_solve(const LayerCoef<NR, NS> &c, const double *brate, dou
     for (int i = 0; i < N; ++i) st_in(Stk::oX + i) = y[i];
   }
   double lam2[N], lam[N], e[N];
-  layer_eigen<NR, NS>(c, dz, st_in, lam2, lam, e);
+  bool bad = !layer_eigen<NR, NS>(c, dz, st_in, lam2, lam, e);
   const StateMem st = opaque(st_in);
-  bool bad = false;
   {
     double A[N * N], z[N], y[N];
     SSB_UNROLL

@@ -1149,9 +1149,10 @@ SSB_HD inline void surface_column_sw(const SurfaceArgs &a, int ic, int g) {
     SSB_FC(ff, top_net) = 1.0 - galb;
     return;
   }
-  // simple_urban_sw (radsurf_simple_urban_sw.F90:28-294); the reference indexes
-  // some (nspec,ncol) members with the layer index, which is kept (it equals
-  // the column index when every column has one layer).
+  // simple_urban_sw (radsurf_simple_urban_sw.F90:28-294).  The reference indexes some
+  // (nspec,ncol) members with the LAYER index (:193,219,253-256), which is only defined when
+  // istartlay(j) = j (every earlier column has exactly one layer, as in test/single_layer): the
+  // column index is used here - equal whenever the reference is well defined, in bounds otherwise.
   const int il = a.istartlay[col] - 1;
   const int nlay = a.nlay[col];
   const double cos_sza = a.cp.cos_sza[col];
@@ -1176,7 +1177,7 @@ SSB_HD inline void surface_column_sw(const SurfaceArgs &a, int ic, int g) {
 #define XC(f, member, c_) (f.member[(size_t)g + (size_t)nspec * (c_)])
   XC(fd, ground_dn_dir, col) = vdg * (1.0 - bf);
   XC(fd, ground_dn, col) = XC(fd, ground_dn_dir, col) + sol[0];
-  XC(fd, ground_net, col) = XC(fd, ground_dn_dir, il) * (1.0 - galb_dir) + sol[0] * (1.0 - galb);
+  XC(fd, ground_net, col) = XC(fd, ground_dn_dir, col) * (1.0 - galb_dir) + sol[0] * (1.0 - galb);
   if (g == 0) fd.ground_sunlit_frac[col] = vdg;
   XC(fd, roof_in_dir, il) = bf;
   XC(fd, roof_in, il) = bf;
@@ -1191,37 +1192,37 @@ SSB_HD inline void surface_column_sw(const SurfaceArgs &a, int ic, int g) {
   }
   XC(fd, top_dn_dir, col) = 1.0;
   XC(fd, top_dn, col) = 1.0;
-  XC(fd, top_net, col) = 1.0 - bf * ralb - (XC(fd, ground_dn, il) - XC(fd, ground_net, il)) * vgs -
+  XC(fd, top_net, col) = 1.0 - bf * ralb - (XC(fd, ground_dn, col) - XC(fd, ground_net, col)) * vgs -
                          (XC(fd, wall_in, il) - XC(fd, wall_net, il)) * vwg;
   if (fd.flux_dn_layer_top) {
     XC(fd, flux_dn_dir_layer_top, il) = (1.0 - bf);
     XC(fd, flux_dn_layer_top, il) = (1.0 - bf);
-    XC(fd, flux_up_layer_top, il) = (XC(fd, ground_dn, il) - XC(fd, ground_net, il)) * vgs +
+    XC(fd, flux_up_layer_top, il) = (XC(fd, ground_dn, col) - XC(fd, ground_net, col)) * vgs +
                                     (XC(fd, wall_in, il) - XC(fd, wall_net, il)) * vwg;
-    XC(fd, flux_dn_dir_layer_base, il) = XC(fd, ground_dn_dir, il);
-    XC(fd, flux_dn_layer_base, il) = XC(fd, ground_dn, il);
-    XC(fd, flux_up_layer_base, il) = XC(fd, ground_dn, il) - XC(fd, ground_net, il);
+    XC(fd, flux_dn_dir_layer_base, il) = XC(fd, ground_dn_dir, col);
+    XC(fd, flux_dn_layer_base, il) = XC(fd, ground_dn, col);
+    XC(fd, flux_up_layer_base, il) = XC(fd, ground_dn, col) - XC(fd, ground_net, col);
   }
   srcv[0] = vgs * (1.0 - bf);
   srcv[1] = vgw * (1.0 - bf);
   solve_vec(2, im, srcv, sol, wk);
-  XC(ff, ground_dn_dir, il) = 0.0;
-  XC(ff, ground_dn, il) = sol[0];
-  XC(ff, ground_net, il) = XC(ff, ground_dn, il) * (1.0 - galb);
+  XC(ff, ground_dn_dir, col) = 0.0;
+  XC(ff, ground_dn, col) = sol[0];
+  XC(ff, ground_net, col) = XC(ff, ground_dn, col) * (1.0 - galb);
   XC(ff, roof_in, il) = bf;
   XC(ff, roof_net, il) = bf * (1.0 - ralb);
   XC(ff, wall_in, il) = sol[1];
   XC(ff, wall_net, il) = XC(ff, wall_in, il) * (1.0 - walb);
   XC(ff, top_dn_dir, col) = 0.0;
   XC(ff, top_dn, col) = 1.0;
-  XC(ff, top_net, col) = 1.0 - bf * ralb - (XC(ff, ground_dn, il) - XC(ff, ground_net, il)) * vgs -
+  XC(ff, top_net, col) = 1.0 - bf * ralb - (XC(ff, ground_dn, col) - XC(ff, ground_net, col)) * vgs -
                          (XC(ff, wall_in, il) - XC(ff, wall_net, il)) * vwg;
   if (ff.flux_dn_layer_top) {
     XC(ff, flux_dn_layer_top, il) = (1.0 - bf);
-    XC(ff, flux_up_layer_top, il) = (XC(ff, ground_dn, il) - XC(ff, ground_net, il)) * vgs +
+    XC(ff, flux_up_layer_top, il) = (XC(ff, ground_dn, col) - XC(ff, ground_net, col)) * vgs +
                                     (XC(ff, wall_in, il) - XC(ff, wall_net, il)) * vwg;
-    XC(ff, flux_dn_layer_base, il) = XC(ff, ground_dn, il);
-    XC(ff, flux_up_layer_base, il) = XC(ff, ground_dn, il) - XC(ff, ground_net, il);
+    XC(ff, flux_dn_layer_base, il) = XC(ff, ground_dn, col);
+    XC(ff, flux_up_layer_base, il) = XC(ff, ground_dn, col) - XC(ff, ground_net, col);
   }
 }
 
@@ -1275,33 +1276,33 @@ SSB_HD inline void surface_column_lw(const SurfaceArgs &a, int ic, int g) {
   XC(fi, wall_in, il) = sol[1];
   XC(fi, wall_net, il) = sol[1] * wemis - wemission * npw * dz;
   XC(fi, top_dn, col) = 0.0;
-  XC(fi, top_net, col) = -bf * remission - (XC(fi, ground_dn, il) - XC(fi, ground_net, il)) * vgs -
+  XC(fi, top_net, col) = -bf * remission - (XC(fi, ground_dn, col) - XC(fi, ground_net, col)) * vgs -
                          (XC(fi, wall_in, il) - XC(fi, wall_net, il)) * vwg;
   if (fi.flux_dn_layer_top) {
     XC(fi, flux_dn_layer_top, il) = 0.0;
-    XC(fi, flux_up_layer_top, il) = (XC(fi, ground_dn, il) - XC(fi, ground_net, il)) * vgs +
+    XC(fi, flux_up_layer_top, il) = (XC(fi, ground_dn, col) - XC(fi, ground_net, col)) * vgs +
                                     (XC(fi, wall_in, il) - XC(fi, wall_net, il)) * vwg;
-    XC(fi, flux_dn_layer_base, il) = XC(fi, ground_dn, il);
-    XC(fi, flux_up_layer_base, il) = XC(fi, ground_dn, il) - XC(fi, ground_net, il);
+    XC(fi, flux_dn_layer_base, il) = XC(fi, ground_dn, col);
+    XC(fi, flux_up_layer_base, il) = XC(fi, ground_dn, col) - XC(fi, ground_net, col);
   }
   srcv[0] = vgs * (1.0 - bf);
   srcv[1] = vgw * (1.0 - bf);
   solve_vec(2, im, srcv, sol, wk);
-  XC(fn, ground_dn, il) = sol[0];
-  XC(fn, ground_net, il) = XC(fn, ground_dn, il) * gemis;
+  XC(fn, ground_dn, col) = sol[0];
+  XC(fn, ground_net, col) = XC(fn, ground_dn, col) * gemis;
   XC(fn, roof_in, il) = bf;
   XC(fn, roof_net, il) = bf * remis;
   XC(fn, wall_in, il) = sol[1];
   XC(fn, wall_net, il) = XC(fn, wall_in, il) * wemis;
   XC(fn, top_dn, col) = 1.0;
-  XC(fn, top_net, col) = 1.0 - bf * (1.0 - remis) - (XC(fn, ground_dn, il) - XC(fn, ground_net, il)) * vgs -
+  XC(fn, top_net, col) = 1.0 - bf * (1.0 - remis) - (XC(fn, ground_dn, col) - XC(fn, ground_net, col)) * vgs -
                          (XC(fn, wall_in, il) - XC(fn, wall_net, il)) * vwg;
   if (fn.flux_dn_layer_top) {
     XC(fn, flux_dn_layer_top, il) = 1.0 - bf;
-    XC(fn, flux_up_layer_top, il) = (XC(fn, ground_dn, il) - XC(fn, ground_net, il)) * vgs +
+    XC(fn, flux_up_layer_top, il) = (XC(fn, ground_dn, col) - XC(fn, ground_net, col)) * vgs +
                                     (XC(fn, wall_in, il) - XC(fn, wall_net, il)) * vwg;
-    XC(fn, flux_dn_layer_base, il) = XC(fn, ground_dn, il);
-    XC(fn, flux_up_layer_base, il) = XC(fn, ground_dn, il) - XC(fn, ground_net, il);
+    XC(fn, flux_dn_layer_base, il) = XC(fn, ground_dn, col);
+    XC(fn, flux_up_layer_base, il) = XC(fn, ground_dn, col) - XC(fn, ground_net, col);
   }
 #undef XC
 }

@@ -50,9 +50,11 @@ def _uniform(xp, seed, field, col, lay=None):
     return lsr(x, 11).to(torch.float64) * (1.0 / 9007199254740992.0)
 
 
-def make_synthetic(config, ncol, nlay=16, col_offset=0, device=None, seed=SEED):
+def make_synthetic(config, ncol, nlay=16, col_offset=0, device=None, seed=SEED, with_temperatures=False):
     """Return (canopy_props, sw_spectral_props, lw_spectral_props) for `ncol`
-    columns starting at global column `col_offset`.  device=None: numpy host
+    columns starting at global column `col_offset` (with_temperatures=True: plus the dict of
+    temperatures the longwave emission / Planck members were made from, the inputs of
+    radsurf_fluxes / calc_simple_spectrum_lw).  device=None: numpy host
     arrays; otherwise torch tensors on that device (nlay/istartlay/i_representation
     stay numpy int32 host arrays, as the C ABI wants them)."""
     if device is None:
@@ -134,6 +136,11 @@ def make_synthetic(config, ncol, nlay=16, col_offset=0, device=None, seed=SEED):
     lw.clear_air_planck = planck
     lw.veg_planck = planck.copy() if xp is np else planck.clone()
     lw.veg_air_planck = planck.copy() if xp is np else planck.clone()
+    if with_temperatures:
+        temps = dict(ground_temperature=contiguous(t_ground), roof_temperature=flat(t_roof),
+                     wall_temperature=flat(t_wall), clear_air_temperature=flat(t_air))
+        temps["veg_temperature"] = temps["veg_air_temperature"] = temps["clear_air_temperature"]
+        return cp, sw, lw, temps
     return cp, sw, lw
 
 

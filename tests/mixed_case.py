@@ -5,7 +5,8 @@ import numpy as np
 
 from spartacus_surface_b200 import config_type
 from spartacus_surface_b200.radsurf_canopy_properties import (ITileFlat, ITileForest, ITileUrban,
-                                                              ITileVegetatedUrban)
+                                                              ITileVegetatedUrban, ITileSimpleUrban,
+                                                              ITileInfiniteStreet)
 from spartacus_surface_b200.synthetic import make_synthetic
 
 NLAY_MAX = 9
@@ -22,13 +23,13 @@ def make_mixed(cfg, ncol=300, seed=7):
     """(canopy_props, sw, lw) cut out of the regular synthetic canopy."""
     rng = np.random.default_rng(seed)
     cp, sw, lw = make_synthetic(cfg, ncol, NLAY_MAX)
-    # (the single-layer urban models are left to the single_layer fixtures: the reference indexes
-    # some of their per-column fields with the layer index, SURVEY App. B6, which only works
-    # when istartlay(j) = j)
+    # the single-layer urban models sit AFTER multi-layer columns (istartlay(j) != j): their
+    # per-column members must land in their own column (SURVEY App. B6)
     rep = np.array([ITileVegetatedUrban, ITileForest, ITileUrban, ITileFlat, ITileVegetatedUrban,
-                    ITileForest], dtype=np.int32)[np.arange(ncol) % 6]
+                    ITileForest, ITileSimpleUrban, ITileInfiniteStreet], dtype=np.int32)[np.arange(ncol) % 8]
     nlay = rng.integers(1, NLAY_MAX + 1, size=ncol).astype(np.int32)
     nlay[rep == ITileFlat] = 0
+    nlay[(rep == ITileSimpleUrban) | (rep == ITileInfiniteStreet)] = 1
     # pack the ragged layers: keep the lowest nlay[j] layers of every column
     keep = (np.arange(NLAY_MAX)[None, :] < nlay[:, None]).reshape(-1)
     for obj in (cp, sw, lw):

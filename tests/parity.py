@@ -93,13 +93,15 @@ def reference_errors(truth, *reference_fp64):
     return ref
 
 
-def check(got, truth, *reference_fp64):
-    """Returns (ok, worst err/bound, report lines)."""
+def check(got, truth, *reference_fp64, factor=REF_FACTOR):
+    """Returns (ok, worst err/bound, report lines).  `factor`: REF_FACTOR for the product path; the
+    test-only generic kernels (the reference's own operation order compiled by nvcc, i.e. one more
+    FP64 build of the reference) are held to 4."""
     err = field_errors(got, truth)
     ref = reference_errors(truth, *reference_fp64)
     lines, ok, worst = [], True, 0.0
     for key in sorted(err):
-        bound = max(REL_TOL, REF_FACTOR * ref.get(key, 0.0))
+        bound = max(REL_TOL, factor * ref.get(key, 0.0))
         worst = max(worst, err[key] / bound)
         if err[key] > bound:
             ok = False

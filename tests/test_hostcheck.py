@@ -113,3 +113,19 @@ def test_mixed_edge_case_fast_path(streams):
     _identical(run(hostcheck_lib.make_solver()), orb)
     ok, worst, lines = parity.check(run(hostcheck_lib.make_solver(fast=True)), truth, ora, orb)
     assert ok, "\n".join(lines)
+
+
+@pytest.mark.parametrize("streams", [2, 4])
+def test_degenerate_regions_fast_path(streams):
+    """Identical regions, vanishing vegetation fraction, grazing sun, optically thick layers
+    (tests/degenerate_case.py) through the register-resident bodies against the _Float128 truth."""
+    import parity
+    from degenerate_case import make_degenerate, run_all
+    cfg, cp, sw, lw = make_degenerate(streams, LG)
+    got, status = run_all(cfg, cp, sw, lw, hostcheck_lib.make_solver(fast=True))
+    assert status == 0
+    ora, _ = run_all(cfg, cp, sw, lw, oracle_lib.make_solver())
+    orb, _ = run_all(cfg, cp, sw, lw, oracle_lib.make_solver(nofma=True))
+    truth, _ = run_all(cfg, cp, sw, lw, oracle_lib.make_solver(quad=True))
+    ok, worst, lines = parity.check(got, truth, ora, orb)
+    assert ok, "\n".join(lines)
