@@ -240,6 +240,9 @@ struct Context {
   int sort_group = 512;  // ... inside groups of this many neighbouring columns
   int partition = 1;  // group layer problems by solved sub-block before the fast layer kernels
   // column-resident kernels (ssb_fused.cuh) where they exist (1 and 2 streams); 0: split path
+  // sweeps of the register-resident path at 1 and 2 streams: 0 = interface-state sweeps
+  // (ssb_fast_sweeps.cuh), 1 = record sweeps (ssb_fused.cuh MODE 1 / 2)
+  int sweep_mode = 1;
   int fused_mode = 0;  // measured on B200: 40 % fewer DRAM bytes, 28 % slower - off by default
   int fused_sort = 1;
   int fused_sort_group = 0;   // 0: the whole chunk
@@ -386,6 +389,24 @@ struct CudaBackend {
   bool fused_shape(const ssb::SolveCfg &c, bool lw, int *pe, int *oe, int *geo) {
     if (!cx.fast_mode || !cx.fused_mode || c.ns > 2) return false;
     return ssb::fused_shape(c, lw, pe, oe, geo);
+  }
+  bool records_shape(const ssb::SolveCfg &c, bool lw, int *oe) {
+    if (!cx.fast_mode || cx.sweep_mode != 1 || !cx.partition || c.ns > 2) return false;
+    int pe = 0, geo = 0;
+    return ssb::fused_shape(c, lw, &pe, oe, &geo);
+  }
+  void records_run(const ssb::ClassArgs &a, bool lw, long width) {
+    if (width <= 0 || cx.first_error != cudaSuccess) return;
+    if (!layer_was_fast && a.lmax > 0) {  // the records are built from the register-resident layer scratch
+      cx.first_error = cudaErrorNotSupported;
+      return;
+    }
+    const int fam = lw ? 3 : 1;
+    tick(fam, true);
+    ssb::records_launch(a, lw, width, cx.stream);
+    g_launches += 1;  // (check_launch counts one)
+    check_launch();
+    tick(fam, false);
   }
   int fused_slots() {
     if (cx.sm_count <= 0) {
@@ -1208,6 +1229,10 @@ int ssb200_set_option(const char *name, int64_t value) {
   }
   if (n == "pipeline_max_blocks") {
     g_ctx.pipeline_max_blocks = value < 1 ? 1 : (int)value;
+    return 0;
+  }
+  if (n == "record_sweeps") {
+    g_ctx.sweep_mode = value != 0 ? 1 : 0;
     return 0;
   }
   if (n == "fused_kernels") {  // column-resident kernels where they exist (1 and 2 streams)

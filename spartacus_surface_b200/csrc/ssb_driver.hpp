@@ -165,6 +165,8 @@ struct CallArgs {
 //   int fused_slots()                                private tiles (= resident thread blocks)
 //   int fused_flags()                                ClassArgs::fused (bit 0 set; bit 1: block-aligned phases)
 //   void fused_run(const ClassArgs&, bool lw, long width)
+//   bool records_shape(const SolveCfg&, bool lw, int *op_elems)   record sweeps available and enabled
+//   void records_run(const ClassArgs&, bool lw, long width)
 template <class Backend>
 struct Dispatcher {
   Backend &be;
@@ -185,10 +187,15 @@ struct Dispatcher {
     int f_private = 0, f_op = 0, f_geo = 0;
     const bool fused = be.fused_shape(c, lw, &f_private, &f_op, &f_geo);
     const size_t f_tiles = fused ? (size_t)be.fused_slots() * (size_t)f_private * kScratchTile : 0;
+    // record sweeps: the split layer kernels, then an upward pass that turns every layer into its
+    // down-pass operator record and a downward pass through the records (ssb_fused.cuh MODE 1 / 2)
+    int r_op = 0;
+    const bool rec = !fused && be.records_shape(c, lw, &r_op);
     // class columns are ascending: restrict to the window by binary search
     size_t pos = (size_t)(std::lower_bound(k.cols.begin(), k.cols.end(), col_lo) - k.cols.begin());
     const size_t ntot = (size_t)(std::lower_bound(k.cols.begin(), k.cols.end(), col_hi) - k.cols.begin());
     auto need_of = [&](size_t lm, size_t wd) {
+      if (rec) return scratch_doubles(el, lm, wd) + scratch_doubles((size_t)r_op, lm > 0 ? lm : 1, wd);
       return fused ? f_tiles + scratch_doubles((size_t)f_op, lm > 0 ? lm : 1, wd)
                    : scratch_doubles(el, lm, wd) + scratch_doubles(es, lm + 1, wd);
     };
@@ -229,14 +236,17 @@ struct Dispatcher {
       a.sweep = s + scratch_doubles(el, (size_t)lmax, width);
       a.ne_layer = (int)el;
       a.ne_layer_geo = (int)el - kGeoElems;
-      a.ne_sweep = (int)es;
+      a.ne_sweep = rec ? r_op : (int)es;
+      a.save_profile = (a.f1.flux_dn_layer_top || a.f2.flux_dn_layer_top) ? 1 : 0;
       if (lmax > 0) {
         if (lw)
           be.template layer_lw<NS>(a, (long)width * lmax);
         else
           be.template layer_sw<NS>(a, (long)width * lmax);
       }
-      if (lw)
+      if (rec)
+        be.records_run(a, lw, (long)width);
+      else if (lw)
         be.template sweeps_lw<NS>(a, (long)width);
       else
         be.template sweeps_sw<NS>(a, (long)width);

@@ -45,7 +45,9 @@ SSB_FAST_HOOK(fast_sweeps_lw)
   bool fused_shape_sw_ns##k(const SolveCfg &, int *, int *, int *);                     \
   bool fused_shape_lw_ns##k(const SolveCfg &, int *, int *, int *);                     \
   bool fused_sw_ns##k(const ClassArgs &, long, int, cudaStream_t);                      \
-  bool fused_lw_ns##k(const ClassArgs &, long, int, cudaStream_t);
+  bool fused_lw_ns##k(const ClassArgs &, long, int, cudaStream_t);                      \
+  bool records_sw_ns##k(const ClassArgs &, long, cudaStream_t);                         \
+  bool records_lw_ns##k(const ClassArgs &, long, cudaStream_t);
 SSB_FUSED_DECL(1)
 SSB_FUSED_DECL(2)
 #undef SSB_FUSED_DECL
@@ -56,5 +58,10 @@ inline bool fused_shape(const SolveCfg &c, bool lw, int *pe, int *oe, int *geo) 
 inline bool fused_launch(const ClassArgs &a, bool lw, long nt, int grid, cudaStream_t st) {
   if (lw) return a.cfg.ns == 1 ? fused_lw_ns1(a, nt, grid, st) : (a.cfg.ns == 2 ? fused_lw_ns2(a, nt, grid, st) : false);
   return a.cfg.ns == 1 ? fused_sw_ns1(a, nt, grid, st) : (a.cfg.ns == 2 ? fused_sw_ns2(a, nt, grid, st) : false);
+}
+// record sweeps (upward pass over the layer scratch -> operator records -> downward pass)
+inline bool records_launch(const ClassArgs &a, bool lw, long nt, cudaStream_t st) {
+  if (lw) return a.cfg.ns == 1 ? records_lw_ns1(a, nt, st) : (a.cfg.ns == 2 ? records_lw_ns2(a, nt, st) : false);
+  return a.cfg.ns == 1 ? records_sw_ns1(a, nt, st) : (a.cfg.ns == 2 ? records_sw_ns2(a, nt, st) : false);
 }
 }  // namespace ssb

@@ -10,6 +10,18 @@
 
 namespace ssb {
 
+// dynamic shared-memory limit of a kernel: set once per (kernel instantiation, device), not per launch
+#define SSB_SMEM_ONCE(kernel, smem)                                                                    \
+  do {                                                                                                 \
+    static int ssb_dev_done = -1;                                                                      \
+    int ssb_dev = 0;                                                                                   \
+    cudaGetDevice(&ssb_dev);                                                                           \
+    if (ssb_dev_done != ssb_dev) {                                                                     \
+      fast_note(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+      ssb_dev_done = ssb_dev;                                                                          \
+    }                                                                                                  \
+  } while (0)
+
 constexpr int kFastBlock = 128;  // sweeps: one thread per (column, interval)
 // layer kernels: block size and the resident threads per SM that the register budget is
 // set for (__launch_bounds__).  Measured on B200: aligning the warps of a block with
@@ -65,8 +77,7 @@ template <int NREG, int NS, bool LW>
 static void launch_partition_layers(const ClassArgs &a, long nt, cudaStream_t st) {
   const size_t smem = sizeof(double) * kPartitionBlock *
                       (LW ? LayerStack<1, NS>::lw_doubles : LayerStack<1, NS>::sw_doubles);
-  if (smem > 48 * 1024)
-    fast_note(cudaFuncSetAttribute(k_partition_layers<NREG, NS, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) SSB_SMEM_ONCE((k_partition_layers<NREG, NS, LW>), smem);
   fast_note(cudaMemsetAsync(a.perm_count, 0, 3 * sizeof(int), st));
   k_partition_layers<NREG, NS, LW><<<(unsigned)((nt + kPartitionBlock - 1) / kPartitionBlock), kPartitionBlock, smem, st>>>(a, nt);
   fast_note(cudaGetLastError());
@@ -87,7 +98,7 @@ template <int NREG, int NS, int SEG>
 static void launch_fast_layer_sw_seg(const ClassArgs &a, long nt, unsigned grid, cudaStream_t st) {
   constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
   const size_t smem = sizeof(double) * LayerStack<NR, NS>::sw_doubles * kLayerBlock;
-  fast_note(cudaFuncSetAttribute(k_fast_layer_sw_seg<NREG, NS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SSB_SMEM_ONCE((k_fast_layer_sw_seg<NREG, NS, SEG>), smem);
   k_fast_layer_sw_seg<NREG, NS, SEG><<<grid, kLayerBlock, smem, st>>>(a, nt);
   fast_note(cudaGetLastError());
 }
@@ -121,7 +132,7 @@ template <int NREG, int NS, bool URBAN>
 static void launch_fast_sweeps_sw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
   const size_t smem = sizeof(double) * SwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
-  fast_note(cudaFuncSetAttribute(k_fast_sweeps_sw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SSB_SMEM_ONCE((k_fast_sweeps_sw<NREG, NS, URBAN>), smem);
   k_fast_sweeps_sw<NREG, NS, URBAN><<<grid, kFastBlock, smem, st>>>(a, nt);
   fast_note(cudaGetLastError());
 }
@@ -154,7 +165,7 @@ template <int NREG, int NS, int SEG>
 static void launch_fast_layer_lw_seg(const ClassArgs &a, long nt, unsigned grid, cudaStream_t st) {
   constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
   const size_t smem = sizeof(double) * LayerStack<NR, NS>::lw_doubles * kLayerBlock;
-  fast_note(cudaFuncSetAttribute(k_fast_layer_lw_seg<NREG, NS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SSB_SMEM_ONCE((k_fast_layer_lw_seg<NREG, NS, SEG>), smem);
   k_fast_layer_lw_seg<NREG, NS, SEG><<<grid, kLayerBlock, smem, st>>>(a, nt);
   fast_note(cudaGetLastError());
 }
@@ -188,7 +199,7 @@ template <int NREG, int NS, bool URBAN>
 static void launch_fast_sweeps_lw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
   const size_t smem = sizeof(double) * LwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
-  fast_note(cudaFuncSetAttribute(k_fast_sweeps_lw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SSB_SMEM_ONCE((k_fast_sweeps_lw<NREG, NS, URBAN>), smem);
   k_fast_sweeps_lw<NREG, NS, URBAN><<<grid, kFastBlock, smem, st>>>(a, nt);
   fast_note(cudaGetLastError());
 }

@@ -58,7 +58,14 @@ SSB_HDI bool keep_rc(int seg, int ri, int rj) {
 // policy, unlike the streamed operator records).
 struct Tile {
   double *base;
-  SSB_HDI Tile(const ClassArgs &a, int q) : base(a.layer + layer_sidx(a, 0, 0, q)) {}
+  size_t lev_stride;  // 0: one private level (column-resident kernels); else the layer scratch of the split path
+  SSB_HDI Tile(const ClassArgs &a, int q)
+      : base(a.layer + layer_sidx(a, 0, 0, q)), lev_stride(a.fused ? 0 : (size_t)a.ne_layer * kScratchTile) {}
+  SSB_HDI Tile at(int lev) const {
+    Tile t = *this;
+    t.base += (size_t)lev * lev_stride;
+    return t;
+  }
   SSB_HDI double ld(int e, int) const { return base[(size_t)e * kScratchTile]; }
   SSB_HDI double ldp(int e, int, bool keep) const {  // structural zeros are not loaded
     double v = 0.0;
@@ -91,7 +98,7 @@ struct SwFused {
   static constexpr int mProf = mScal + 2;        // 2 x (n + d): sum(up_below), sum(up_above)
   static constexpr int op_elems = mProf + 2 * (n + d);
   // shared-memory slice: the layer stack during the layer solve; a_above, T, d_above in the step
-  static constexpr int sAa = 0, sT = n * n, sDa = 2 * n * n;
+  static constexpr int sAa = 0, sDa = n * n, sT = n * n + n * d;  // [a_above | d_above] = the carried state
   static constexpr int step_doubles = 2 * n * n + n * d;
   static constexpr int ls = LayerStack<NREG, NS>::sw_doubles;
   static constexpr int smem_doubles = ls > step_doubles ? ls : step_doubles;
@@ -99,7 +106,9 @@ struct SwFused {
 
 // One upward adding step of layer jl: reads the layer matrices and the state from the private
 // tile, writes the operator record of the level and the state above the next interface.
-template <int NREG, int NS, bool URBAN>
+// REC: the carried state stays in the shared-memory slice between the steps (split layer kernels
+// + record sweeps, where the tile is the layer scratch of level jl) instead of in the private tile.
+template <int NREG, int NS, bool URBAN, bool REC = false>
 SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Scr &Mo, int jl, int il, int il1,
                                     int nlay, int g, const StateMem &sm, double zcos, double sin0) {
   typedef SwFused<NREG, NS, URBAN> F;
@@ -109,10 +118,12 @@ SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Sc
   const int seg = (int)Lp.ld(Lay::oGeo + 7, 0);
   const SegKeep sk = seg_keep(seg);
   // ---- operands that every column needs, into shared memory --------------------------------
-  SSB_UNROLL
-  for (int i = 0; i < n * n; ++i) sm(F::sAa + i) = Lp.ld(F::oState + i, 0);
-  SSB_UNROLL
-  for (int i = 0; i < n * d; ++i) sm(F::sDa + i) = Lp.ld(F::oState + n * n + i, 0);
+  if (!REC) {
+    SSB_UNROLL
+    for (int i = 0; i < n * n; ++i) sm(F::sAa + i) = Lp.ld(F::oState + i, 0);
+    SSB_UNROLL
+    for (int i = 0; i < n * d; ++i) sm(F::sDa + i) = Lp.ld(F::oState + n * n + i, 0);
+  }
   SSB_UNROLL
   for (int j = 0; j < n; ++j) {
     SSB_UNROLL
@@ -358,7 +369,8 @@ SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Sc
   }
   double U[12], V[12];
   overlap_above<NREG, URBAN, false>(a, il1, nlay, jl, U, V);
-  const StateMem stt{Lp.base + (size_t)F::oState * kScratchTile, kScratchTile};
+  const StateMem stt = REC ? StateMem{&sm(F::sAa), sm.stride}
+                           : StateMem{Lp.base + (size_t)F::oState * kScratchTile, kScratchTile};
   {
     double Ab[n * n];
     SSB_UNROLL
@@ -405,8 +417,12 @@ SSB_HD inline void fused_layer_sw(const ClassArgs &a, int q, int lev, const Stat
   fast_layer_problem_sw<NREG, NS>(a, q, lev, st);
 }
 
-template <int NREG, int NS, bool URBAN>
+// MODE 0: the whole column in one thread (column-resident kernels).  MODE 1 / 2: the two halves of the
+// "record sweeps" that follow the split layer kernels - 1: upward pass over the layer scratch, writes the
+// operator records and the boundary conditions; 2: downward pass through the records, writes the fluxes.
+template <int NREG, int NS, bool URBAN, int MODE = 0>
 SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, const StateMem &st) {
+  constexpr bool REC = MODE != 0;
   typedef SwFused<NREG, NS, URBAN> F;
   constexpr int n = NREG * NS, d = NREG, NRB = URBAN ? NREG + 1 : NREG, NF = F::NF, NFD = F::NFD;
   const SolveCfg &c = a.cfg;
@@ -431,20 +447,22 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, co
   }
   const bool own = (g == itransp);
   const bool live = active && (cos_sza > 0.0);
-  if (active && !live) {  // night: every member of the column is zero (radsurf_interface.F90:193-196)
+  if (MODE != 2 && active && !live) {  // night: every member of the column is zero (radsurf_interface.F90:193-196)
     zero_column(fdir, nspec, g, col, il1, nlay, own);
     zero_column(fdif, nspec, g, col, il1, nlay, own);
   }
   if (!live) {
-    if (a.fused & 2)
+    if (!REC && (a.fused & 2))
       for (int jl = 0; jl < a.lmax; ++jl) {
         phase_sync(a);
         phase_sync(a);
       }
     return;
   }
-  zero_unwritten_sw<NREG, URBAN>(fdir, nspec, g, col, il1, nlay, own, true);
-  zero_unwritten_sw<NREG, URBAN>(fdif, nspec, g, col, il1, nlay, own, false);
+  if (MODE != 2) {
+    zero_unwritten_sw<NREG, URBAN>(fdir, nspec, g, col, il1, nlay, own, true);
+    zero_unwritten_sw<NREG, URBAN>(fdif, nspec, g, col, il1, nlay, own, false);
+  }
   const double zcos = URBAN ? dmax(cos_sza, 1.0e-6) : cos_sza;
   const double sin0 = URBAN ? sqrt(1.0 - zcos * zcos) : 0.0;
   double hw[NS], tang[NS];
@@ -455,45 +473,61 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, co
   }
   const Tile Lp(a, q);
   const Scr Mo(a.sweep, a.lmax, a.ne_sweep, q);
-  // ---- upward: state = [a_above | d_above] in the private tile ------------------------------
-  {
+  // ---- upward: state = [a_above | d_above] in the private tile (REC: in the shared-memory slice) ----
+  double talb_diff = 0.0, talb_dir = 0.0;
+  if (MODE != 2) {
+    // element e of the carried state
+    auto state_st = [&](int e, double v) {
+      if (REC)
+        st(F::sAa + e) = v;
+      else
+        Lp.st(F::oState + e, 0, v);
+    };
+    auto state_ld = [&](int e) -> double { return REC ? st(F::sAa + e) : Lp.ld(F::oState + e, 0); };
     const double galb = a.sw.ground_albedo[(size_t)g + (size_t)nspec * col];
     const double galb_dir =
         (a.use_sw_direct_albedo ? a.sw.ground_albedo_dir : a.sw.ground_albedo)[(size_t)g + (size_t)nspec * col];
     SSB_UNROLL
-    for (int i = 0; i < n * n + n * d; ++i) Lp.st(F::oState + i, 0, 0.0);
+    for (int i = 0; i < n * n + n * d; ++i) state_st(i, 0.0);
     SSB_UNROLL
     for (int r = 0; r < NREG; ++r) {
       SSB_UNROLL
       for (int jt = 0; jt < NS; ++jt) {
-        Lp.st(F::oState + n * n + (jt + r * NS) + n * r, 0, zcos * galb_dir * hw[jt]);
+        state_st(n * n + (jt + r * NS) + n * r, zcos * galb_dir * hw[jt]);
         SSB_UNROLL
-        for (int jf = 0; jf < NS; ++jf) Lp.st(F::oState + (jt + r * NS) + n * (jf + r * NS), 0, galb * hw[jt]);
+        for (int jf = 0; jf < NS; ++jf) state_st((jt + r * NS) + n * (jf + r * NS), galb * hw[jt]);
       }
     }
-  }
-  const int nloop = (a.fused & 2) ? a.lmax : nlay;
-  for (int jl = 0; jl < nloop; ++jl) {
-    phase_sync(a);
-    if (jl < nlay) fused_layer_sw<NREG, NS>(a, q, jl, st);
-    phase_sync(a);
-    if (jl < nlay) fused_up_step_sw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st, zcos, sin0);
-  }
-  double talb_diff = 0.0, talb_dir = 0.0;
-  {
+    if (REC) {
+      for (int jl = 0; jl < nlay; ++jl)
+        fused_up_step_sw<NREG, NS, URBAN, REC>(a, Lp.at(jl), Mo, jl, il1 + jl, il1, nlay, g, st, zcos, sin0);
+    } else {
+      const int nloop = (a.fused & 2) ? a.lmax : nlay;
+      for (int jl = 0; jl < nloop; ++jl) {
+        phase_sync(a);
+        if (jl < nlay) fused_layer_sw<NREG, NS>(a, q, jl, st);
+        phase_sync(a);
+        if (jl < nlay) fused_up_step_sw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st, zcos, sin0);
+      }
+    }
     SSB_UNROLL
     for (int i = 0; i < NS; ++i) {
       double s = 0.0;
       SSB_UNROLL
-      for (int j = 0; j < NS; ++j) s = fma(Lp.ld(F::oState + i + n * j, 0), hw[j], s);
+      for (int j = 0; j < NS; ++j) s = fma(state_ld(i + n * j), hw[j], s);
       talb_diff += s;
     }
     double s = 0.0;
     SSB_UNROLL
-    for (int js = 0; js < NS; ++js) s += Lp.ld(F::oState + n * n + js, 0);
+    for (int js = 0; js < NS; ++js) s += state_ld(n * n + js);
     talb_dir = s / zcos;
     a.bc.sw_albedo[(size_t)g + (size_t)nspec * col] = talb_diff;
     a.bc.sw_albedo_dir[(size_t)g + (size_t)nspec * col] = talb_dir;
+  }
+  if (MODE == 1) return;
+  if (MODE == 2) {
+    talb_diff = a.bc.sw_albedo[(size_t)g + (size_t)nspec * col];
+    talb_dir = a.bc.sw_albedo_dir[(size_t)g + (size_t)nspec * col];
   }
   // ---- downward: direct (suffix d) and diffuse (suffix f) sources through the records --------
   double dir_above[d], xa_d[n], xa_f[n];
@@ -742,13 +776,13 @@ struct LwFused {
   static constexpr int mScal = mP0 + n;        // segment
   static constexpr int mProf = mScal + 1;      // 2 x (n + 1)
   static constexpr int op_elems = mProf + 2 * (n + 1);
-  static constexpr int sAa = 0, sT = n * n, sSa = 2 * n * n;
+  static constexpr int sAa = 0, sSa = n * n, sT = n * n + n;  // [a_above | source_above] = the carried state
   static constexpr int step_doubles = 2 * n * n + n;
   static constexpr int ls = LayerStack<NREG, NS>::lw_doubles;
   static constexpr int smem_doubles = ls > step_doubles ? ls : step_doubles;
 };
 
-template <int NREG, int NS, bool URBAN>
+template <int NREG, int NS, bool URBAN, bool REC = false>
 SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Scr &Mo, int jl, int il, int il1,
                                     int nlay, int g, const StateMem &sm) {
   typedef LwFused<NREG, NS, URBAN> F;
@@ -757,10 +791,12 @@ SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Sc
   const int nspec = a.cfg.nspec;
   const int seg = (int)Lp.ld(Lay::oGeo + 7, 0);
   const SegKeep sk = seg_keep(seg);
-  SSB_UNROLL
-  for (int i = 0; i < n * n; ++i) sm(F::sAa + i) = Lp.ld(F::oState + i, 0);
-  SSB_UNROLL
-  for (int i = 0; i < n; ++i) sm(F::sSa + i) = Lp.ld(F::oState + n * n + i, 0);
+  if (!REC) {
+    SSB_UNROLL
+    for (int i = 0; i < n * n; ++i) sm(F::sAa + i) = Lp.ld(F::oState + i, 0);
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) sm(F::sSa + i) = Lp.ld(F::oState + n * n + i, 0);
+  }
   SSB_UNROLL
   for (int j = 0; j < n; ++j) {
     SSB_UNROLL
@@ -958,7 +994,8 @@ SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Sc
   }
   double U[12], V[12];
   overlap_above<NREG, URBAN, true>(a, il1, nlay, jl, U, V);
-  const StateMem stt{Lp.base + (size_t)F::oState * kScratchTile, kScratchTile};
+  const StateMem stt = REC ? StateMem{&sm(F::sAa), sm.stride}
+                           : StateMem{Lp.base + (size_t)F::oState * kScratchTile, kScratchTile};
   {
     double Ab[n * n];
     SSB_UNROLL
@@ -990,8 +1027,9 @@ SSB_HD inline void fused_layer_lw(const ClassArgs &a, int q, int lev, const Stat
   fast_layer_problem_lw<NREG, NS>(a, q, lev, st);
 }
 
-template <int NREG, int NS, bool URBAN>
+template <int NREG, int NS, bool URBAN, int MODE = 0>
 SSB_HD inline void fused_column_lw(const ClassArgs &a, int q_in, bool active, const StateMem &st) {
+  constexpr bool REC = MODE != 0;
   typedef LwFused<NREG, NS, URBAN> F;
   constexpr int n = NREG * NS, NRB = URBAN ? NREG + 1 : NREG, NF = F::NF;
   const SolveCfg &c = a.cfg;
@@ -1002,15 +1040,17 @@ SSB_HD inline void fused_column_lw(const ClassArgs &a, int q_in, bool active, co
   const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
   const ssb200_canopy_flux &fint = a.f1, &fnorm = a.f2;
   if (!active) {
-    if (a.fused & 2)
+    if (!REC && (a.fused & 2))
       for (int jl = 0; jl < a.lmax; ++jl) {
         phase_sync(a);
         phase_sync(a);
       }
     return;
   }
-  zero_unwritten_lw<NREG, URBAN>(fint, nspec, g, col, il1, nlay);
-  zero_unwritten_lw<NREG, URBAN>(fnorm, nspec, g, col, il1, nlay);
+  if (MODE != 2) {
+    zero_unwritten_lw<NREG, URBAN>(fint, nspec, g, col, il1, nlay);
+    zero_unwritten_lw<NREG, URBAN>(fnorm, nspec, g, col, il1, nlay);
+  }
   double hw[NS], tang[NS];
   SSB_UNROLL
   for (int js = 0; js < NS; ++js) {
@@ -1027,38 +1067,55 @@ SSB_HD inline void fused_column_lw(const ClassArgs &a, int q_in, bool active, co
     region_fractions(c, URBAN ? a.cp.building_fraction[il1] : 0.0,
                      (veg && a.cp.veg_fraction) ? a.cp.veg_fraction[il1] : 0.0, frac0);
   }
-  SSB_UNROLL
-  for (int i = 0; i < n * n + n; ++i) Lp.st(F::oState + i, 0, 0.0);
-  SSB_UNROLL
-  for (int r = 0; r < NREG; ++r) {
+  double top_emissivity = 0.0, top_emission = 0.0;
+  if (MODE != 2) {
+    auto state_st = [&](int e, double v) {
+      if (REC)
+        st(F::sAa + e) = v;
+      else
+        Lp.st(F::oState + e, 0, v);
+    };
+    auto state_ld = [&](int e) -> double { return REC ? st(F::sAa + e) : Lp.ld(F::oState + e, 0); };
     SSB_UNROLL
-    for (int jt = 0; jt < NS; ++jt) {
+    for (int i = 0; i < n * n + n; ++i) state_st(i, 0.0);
+    SSB_UNROLL
+    for (int r = 0; r < NREG; ++r) {
       SSB_UNROLL
-      for (int jf = 0; jf < NS; ++jf) Lp.st(F::oState + (jt + r * NS) + n * (jf + r * NS), 0, (1.0 - gemis) * hw[jt]);
-      Lp.st(F::oState + n * n + jt + r * NS, 0, (hw[jt] * frac0[r]) * gemission);
+      for (int jt = 0; jt < NS; ++jt) {
+        SSB_UNROLL
+        for (int jf = 0; jf < NS; ++jf) state_st((jt + r * NS) + n * (jf + r * NS), (1.0 - gemis) * hw[jt]);
+        state_st(n * n + jt + r * NS, (hw[jt] * frac0[r]) * gemission);
+      }
     }
-  }
-  const int nloop = (a.fused & 2) ? a.lmax : nlay;
-  for (int jl = 0; jl < nloop; ++jl) {
-    phase_sync(a);
-    if (jl < nlay) fused_layer_lw<NREG, NS>(a, q, jl, st);
-    phase_sync(a);
-    if (jl < nlay) fused_up_step_lw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st);
-  }
-  double top_emissivity, top_emission = 0.0;
-  {
+    if (REC) {
+      for (int jl = 0; jl < nlay; ++jl)
+        fused_up_step_lw<NREG, NS, URBAN, REC>(a, Lp.at(jl), Mo, jl, il1 + jl, il1, nlay, g, st);
+    } else {
+      const int nloop = (a.fused & 2) ? a.lmax : nlay;
+      for (int jl = 0; jl < nloop; ++jl) {
+        phase_sync(a);
+        if (jl < nlay) fused_layer_lw<NREG, NS>(a, q, jl, st);
+        phase_sync(a);
+        if (jl < nlay) fused_up_step_lw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st);
+      }
+    }
     double sAll = 0.0;
     SSB_UNROLL
     for (int i = 0; i < NS; ++i) {
       double s = 0.0;
       SSB_UNROLL
-      for (int j = 0; j < NS; ++j) s = fma(Lp.ld(F::oState + i + n * j, 0), hw[j], s);
+      for (int j = 0; j < NS; ++j) s = fma(state_ld(i + n * j), hw[j], s);
       sAll += s;
-      top_emission += Lp.ld(F::oState + n * n + i, 0);
+      top_emission += state_ld(n * n + i);
     }
     top_emissivity = 1.0 - sAll;
     a.bc.lw_emissivity[(size_t)g + (size_t)nspec * col] = top_emissivity;
     a.bc.lw_emission[(size_t)g + (size_t)nspec * col] = top_emission;
+  }
+  if (MODE == 1) return;
+  if (MODE == 2) {
+    top_emissivity = a.bc.lw_emissivity[(size_t)g + (size_t)nspec * col];
+    top_emission = a.bc.lw_emission[(size_t)g + (size_t)nspec * col];
   }
   // ---- downward: internal emission (suffix i) and incoming flux (suffix f) through the records ---
   double xa_i[n], xa_f[n];

@@ -13,6 +13,9 @@
 namespace ssb {
 
 constexpr int kFusedBlock = kScratchTile;  // one thread per problem of a tile
+#ifndef SSB_REC_DOWN_BLOCKS
+#define SSB_REC_DOWN_BLOCKS 4  // resident blocks per SM the downward record kernel is compiled for
+#endif
 
 #ifdef SSB_KIND_SW
 template <int NREG, int NS, bool URBAN>
@@ -69,6 +72,47 @@ bool SSB_CAT(fused_sw_ns, SSB_NS)(const ClassArgs &a, long nt, int grid, cudaStr
     default: return false;
   }
 }
+// ---- record sweeps after the split layer kernels (ssb_fused.cuh, MODE 1 / 2) ----------------
+template <int NREG, int NS, bool URBAN>
+__global__ void __launch_bounds__(kFusedBlock, 2) k_rec_up_sw(ClassArgs a, long nt) {
+  extern __shared__ double ssb_stack[];
+  const long q = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (q >= nt) return;
+  const StateMem st{ssb_stack + threadIdx.x, kFusedBlock};
+  fused_column_sw<NREG, NS, URBAN, 1>(a, (int)q, true, st);
+}
+template <int NREG, int NS, bool URBAN>
+__global__ void __launch_bounds__(kFusedBlock, SSB_REC_DOWN_BLOCKS) k_rec_down_sw(ClassArgs a, long nt) {
+  const long q = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (q >= nt) return;
+  fused_column_sw<NREG, NS, URBAN, 2>(a, (int)q, true, StateMem{nullptr, 0});
+}
+template <int NREG, int NS, bool URBAN>
+static void launch_records_sw(const ClassArgs &a, long nt, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = sizeof(double) * SwFused<NREG, NS, URBAN>::step_doubles * kFusedBlock;
+  if (!configured) {
+    fast_note(cudaFuncSetAttribute(k_rec_up_sw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const unsigned grid = (unsigned)((nt + kFusedBlock - 1) / kFusedBlock);
+  k_rec_up_sw<NREG, NS, URBAN><<<grid, kFusedBlock, smem, st>>>(a, nt);
+  fast_note(cudaGetLastError());
+  k_rec_down_sw<NREG, NS, URBAN><<<grid, kFusedBlock, 0, st>>>(a, nt);
+  fast_note(cudaGetLastError());
+}
+bool SSB_CAT(records_sw_ns, SSB_NS)(const ClassArgs &a, long nt, cudaStream_t st) {
+  if (a.cfg.ns != SSB_NS || a.fused) return false;
+  switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
+    case 2: launch_records_sw<1, SSB_NS, false>(a, nt, st); return true;
+    case 3: launch_records_sw<1, SSB_NS, true>(a, nt, st); return true;
+    case 4: launch_records_sw<2, SSB_NS, false>(a, nt, st); return true;
+    case 5: launch_records_sw<2, SSB_NS, true>(a, nt, st); return true;
+    case 6: launch_records_sw<3, SSB_NS, false>(a, nt, st); return true;
+    case 7: launch_records_sw<3, SSB_NS, true>(a, nt, st); return true;
+    default: return false;
+  }
+}
 #endif
 
 #ifdef SSB_KIND_LW
@@ -122,6 +166,47 @@ bool SSB_CAT(fused_lw_ns, SSB_NS)(const ClassArgs &a, long nt, int grid, cudaStr
     case 5: launch_fused_lw<2, SSB_NS, true>(a, nt, grid, st); return true;
     case 6: launch_fused_lw<3, SSB_NS, false>(a, nt, grid, st); return true;
     case 7: launch_fused_lw<3, SSB_NS, true>(a, nt, grid, st); return true;
+    default: return false;
+  }
+}
+// ---- record sweeps after the split layer kernels (ssb_fused.cuh, MODE 1 / 2) ----------------
+template <int NREG, int NS, bool URBAN>
+__global__ void __launch_bounds__(kFusedBlock, 2) k_rec_up_lw(ClassArgs a, long nt) {
+  extern __shared__ double ssb_stack[];
+  const long q = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (q >= nt) return;
+  const StateMem st{ssb_stack + threadIdx.x, kFusedBlock};
+  fused_column_lw<NREG, NS, URBAN, 1>(a, (int)q, true, st);
+}
+template <int NREG, int NS, bool URBAN>
+__global__ void __launch_bounds__(kFusedBlock, SSB_REC_DOWN_BLOCKS) k_rec_down_lw(ClassArgs a, long nt) {
+  const long q = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (q >= nt) return;
+  fused_column_lw<NREG, NS, URBAN, 2>(a, (int)q, true, StateMem{nullptr, 0});
+}
+template <int NREG, int NS, bool URBAN>
+static void launch_records_lw(const ClassArgs &a, long nt, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = sizeof(double) * LwFused<NREG, NS, URBAN>::step_doubles * kFusedBlock;
+  if (!configured) {
+    fast_note(cudaFuncSetAttribute(k_rec_up_lw<NREG, NS, URBAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const unsigned grid = (unsigned)((nt + kFusedBlock - 1) / kFusedBlock);
+  k_rec_up_lw<NREG, NS, URBAN><<<grid, kFusedBlock, smem, st>>>(a, nt);
+  fast_note(cudaGetLastError());
+  k_rec_down_lw<NREG, NS, URBAN><<<grid, kFusedBlock, 0, st>>>(a, nt);
+  fast_note(cudaGetLastError());
+}
+bool SSB_CAT(records_lw_ns, SSB_NS)(const ClassArgs &a, long nt, cudaStream_t st) {
+  if (a.cfg.ns != SSB_NS || a.fused) return false;
+  switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
+    case 2: launch_records_lw<1, SSB_NS, false>(a, nt, st); return true;
+    case 3: launch_records_lw<1, SSB_NS, true>(a, nt, st); return true;
+    case 4: launch_records_lw<2, SSB_NS, false>(a, nt, st); return true;
+    case 5: launch_records_lw<2, SSB_NS, true>(a, nt, st); return true;
+    case 6: launch_records_lw<3, SSB_NS, false>(a, nt, st); return true;
+    case 7: launch_records_lw<3, SSB_NS, true>(a, nt, st); return true;
     default: return false;
   }
 }

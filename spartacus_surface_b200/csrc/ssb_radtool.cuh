@@ -15,6 +15,139 @@
 
 namespace ssb {
 
+// ---------------------------------------------------------------------------
+// Eigen-systems of the generic kernels ON THE DEVICE: the same symmetrisation as the
+// register-resident path (ssb_layer_math.cuh), written with run-time orders.
+//   * P = D S with D = Gamma1-Gamma2, S = Gamma1+Gamma2 both "N-symmetric" (X diag(ninv) is
+//     symmetric, ninv_i = weight_js mu_js frac_r: detailed balance of exchange and scattering):
+//     -N D = L L^T (Cholesky), Y = L^T K L with K = -S diag(ninv) is symmetric with the spectrum
+//     of P; cyclic Jacobi gives Y = U diag(ev) U^T and the eigenvectors of P are V = diag(ninv) L U.
+//   * Gamma0 diag(frac) is symmetric: Y0 = diag(1/sqrt f) Gamma0 diag(sqrt f), G0 = diag(sqrt f) U0.
+// Every output of calc_matrices_* is invariant to the scaling and order of the eigenvectors
+// (SURVEY App. A.3), so this replaces the reference's nonsymmetric QR solver
+// (radtool_eigen_decomposition.F90:51-828) without changing what is computed.  The QR scheme
+// (ssb_math.cuh: eigen_real) remains for the HOST check only, where it pins the generic bodies
+// bit for bit against the oracle; no device code path reaches it.
+// ---------------------------------------------------------------------------
+#if !defined(__CUDA_ARCH__)
+inline bool &host_generic_jacobi() {
+  static bool flag = false;  // host check: false = reference-order QR solver (bit-identity test)
+  return flag;
+}
+#endif
+SSB_HDI bool generic_uses_jacobi() {
+#if defined(__CUDA_ARCH__)
+  return true;
+#else
+  return host_generic_jacobi();
+#endif
+}
+
+// cyclic Jacobi on a dense symmetric matrix Y (n x n, both triangles kept), eigenvectors in U;
+// scaled stopping criterion |y_pq|^2 <= tol^2 |y_pp y_qq| (relative accuracy of small eigenvalues).
+// Returns 0, or 1 when 40 sweeps did not reach it (cf. nerror, radtool_eigen_decomposition.F90:92-100).
+SSB_HD inline int jacobi_sym_dense(int n, double *Y, double *U) {
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) U[i + n * j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep <= 40; ++sweep) {
+    bool conv = true;
+    for (int p = 0; p < n && conv; ++p)
+      for (int q = p + 1; q < n; ++q)
+        if (!(Y[q + n * p] * Y[q + n * p] <= 1.0e-31 * fabs(Y[p + n * p] * Y[q + n * q]))) {
+          conv = false;
+          break;
+        }
+    if (conv) return 0;
+    if (sweep == 40) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double beta = Y[q + n * p];
+        const double app = Y[p + n * p], aqq = Y[q + n * q];
+        const double alpha = 0.5 * (aqq - app);
+        const double h2 = alpha * alpha + beta * beta;
+        if (!(beta * beta > 1.0e-40 * h2)) continue;
+        const double h = sqrt(h2);
+        const double c2 = 0.5 + 0.5 * fabs(alpha) / h;
+        const double c = sqrt(c2);
+        const double s = (alpha < 0.0 ? -0.5 : 0.5) * beta / (h * c);
+        const double t = s / c;
+        Y[p + n * p] = app - t * beta;
+        Y[q + n * q] = aqq + t * beta;
+        Y[q + n * p] = Y[p + n * q] = 0.0;
+        for (int k = 0; k < n; ++k) {
+          if (k != p && k != q) {
+            const double akp = Y[k + n * p], akq = Y[k + n * q];
+            const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+            Y[k + n * p] = Y[p + n * k] = np_;
+            Y[k + n * q] = Y[q + n * k] = nq_;
+          }
+          const double ukp = U[k + n * p], ukq = U[k + n * q];
+          U[k + n * p] = c * ukp - s * ukq;
+          U[k + n * q] = s * ukp + c * ukq;
+        }
+      }
+  }
+  return 1;
+}
+
+// eigenvalues `ev` and eigenvectors V of P = D S (see above); L, Y, U: n x n work arrays
+SSB_HD inline int eigen_sym_ds(int n, const double *D, const double *S, const double *ninv, double *ev, double *V,
+                               double *L, double *Y, double *U) {
+  // Cholesky of A = -diag(1/ninv) D (lower triangle)
+  for (int j = 0; j < n; ++j) {
+    double dj = -D[j + n * j] / ninv[j];
+    for (int k = 0; k < j; ++k) dj -= L[j + n * k] * L[j + n * k];
+    const double l = sqrt(dj);
+    L[j + n * j] = l;
+    for (int i = 0; i < j; ++i) L[i + n * j] = 0.0;
+    for (int i = j + 1; i < n; ++i) {
+      double sij = -D[i + n * j] / ninv[i];
+      for (int k = 0; k < j; ++k) sij -= L[i + n * k] * L[j + n * k];
+      L[i + n * j] = sij / l;
+    }
+  }
+  // Y = L^T K L, K = -S diag(ninv) (symmetrised from its lower triangle); U serves as K L
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) {
+      double sum = 0.0;
+      for (int k = j; k < n; ++k) {
+        const double kik = (i >= k) ? -S[i + n * k] * ninv[k] : -S[k + n * i] * ninv[i];
+        sum += kik * L[k + n * j];
+      }
+      U[i + n * j] = sum;
+    }
+  for (int j = 0; j < n; ++j)
+    for (int i = j; i < n; ++i) {
+      double sum = 0.0;
+      for (int k = i; k < n; ++k) sum += L[k + n * i] * U[k + n * j];
+      Y[i + n * j] = Y[j + n * i] = sum;
+    }
+  const int nerr = jacobi_sym_dense(n, Y, U);
+  for (int k = 0; k < n; ++k) {
+    ev[k] = Y[k + n * k];
+    for (int i = 0; i < n; ++i) {
+      double sum = 0.0;
+      for (int j = 0; j <= i; ++j) sum += L[i + n * j] * U[j + n * k];
+      V[i + n * k] = ninv[i] * sum;
+    }
+  }
+  return nerr;
+}
+
+// eigenvalues eps and eigenvectors G0 of Gamma0 (d <= 3) through diag(sqrt(frac))
+SSB_HD inline int eigen_sym_g0(int d, const double *g0, const double *frac, double *eps, double *G0) {
+  double sq[3], Y0[9], U0[9];
+  for (int r = 0; r < d; ++r) sq[r] = sqrt(frac[r]);
+  for (int j = 0; j < d; ++j)
+    for (int i = j; i < d; ++i) Y0[i + d * j] = Y0[j + d * i] = g0[i + d * j] * sq[j] / sq[i];
+  const int nerr = jacobi_sym_dense(d, Y0, U0);
+  for (int k = 0; k < d; ++k) {
+    eps[k] = Y0[k + d * k];
+    for (int i = 0; i < d; ++i) G0[i + d * k] = sq[i] * U0[i + d * k];
+  }
+  return nerr;
+}
+
 template <int NC>
 struct RadtoolWork {
   static constexpr int NN = NC * NC;
@@ -24,6 +157,7 @@ struct RadtoolWork {
   double cp[NBIG * 3];
   double lam[NC], elz[NC], wk[2 * NC + 1], col[NC], rhs[NC], g4c[NC];
   double g3[NC * 3], g4[NC * 3], g3g0[NC * 3];
+  double ninv[NC], frac[3];  // symmetrisers of the solved block (device eigen-systems), set by the caller
 };
 
 // Steps common to SW and LW (sw_eig:180-221, lw_eig:142-180): on return
@@ -39,9 +173,14 @@ SSB_HD inline int diffuse_part(int n, double dz, const double *g1, const double 
     gdiff[i] = g1[i] - g2[i];
     w.b3[i] = g1[i] + g2[i];
   }
-  mat_mul(n, n, n, gdiff, w.b3, P);
   double ev[NC];
-  int nerr = eigen_real(n, P, ev, V, w.wk);
+  int nerr;
+  if (generic_uses_jacobi()) {
+    nerr = eigen_sym_ds(n, gdiff, w.b3, w.ninv, ev, V, w.b4, w.b5, w.b6);
+  } else {
+    mat_mul(n, n, n, gdiff, w.b3, P);
+    nerr = eigen_real(n, P, ev, V, w.wk);
+  }
   for (int i = 0; i < n; ++i) {
     w.lam[i] = sqrt(dmax(0.0, ev[i]));
     w.elz[i] = exp(-w.lam[i] * dz);
@@ -95,7 +234,10 @@ SSB_HD inline int calc_matrices_sw(int n, int d, double dz, const double *g0, co
   // Section 3 (:225-229): E = G0 diag(exp(eps dz)) G0^-1
   double g0c[9], G0[9], G0i[9], eps[3], e0[3], t9[9], wk0[7];
   for (int i = 0; i < d * d; ++i) g0c[i] = g0[i];
-  nerr += eigen_real(d, g0c, eps, G0, wk0);
+  if (generic_uses_jacobi())
+    nerr += eigen_sym_g0(d, g0c, w.frac, eps, G0);
+  else
+    nerr += eigen_real(d, g0c, eps, G0, wk0);
   for (int i = 0; i < d * d; ++i) t9[i] = G0[i];
   invert(d, t9, G0i);
   for (int i = 0; i < d; ++i) e0[i] = exp(eps[i] * dz);

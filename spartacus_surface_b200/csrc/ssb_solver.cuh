@@ -232,6 +232,10 @@ SSB_HD inline void layer_problem_sw(const ClassArgs &a, int q, int lev) {
 
   double R[NC * NC], T[NC * NC], Idiff[NC * NC], Sup[NC * 3], Sdn[NC * 3], Idd[NC * 3], E[9], Idir[9];
   RadtoolWork<NC> w;
+  for (int r = 0; r < nr; ++r) {
+    w.frac[r] = gm.frac[r0 + r];
+    for (int js = 0; js < ns; ++js) w.ninv[js + r * ns] = a.lg.weight[js] * a.lg.mu[js] * gm.frac[r0 + r];
+  }
   const int nfail = calc_matrices_sw<NC>(nn, nr, a.cp.dz[il], g0, g1, g2, g3, R, T, Sup, Sdn, E, Idir, Idiff,
                                          Idd, w);
   count_failure(a.status, nfail);
@@ -404,6 +408,10 @@ SSB_HD inline void layer_problem_lw(const ClassArgs &a, int q, int lev) {
 
   double R[NC * NC], T[NC * NC], IF[NC * NC], src[NC], isrc[NC];
   RadtoolWork<NC> w;
+  for (int r = 0; r < nr; ++r) {
+    w.frac[r] = gm.frac[r0 + r];
+    for (int js = 0; js < ns; ++js) w.ninv[js + r * ns] = a.lg.weight[js] * a.lg.mu[js] * gm.frac[r0 + r];
+  }
   const int nfail = calc_matrices_lw<NC>(nn, a.cp.dz[il], g1, g2, brate, R, T, src, IF, isrc, w);
   count_failure(a.status, nfail);
 

@@ -1,6 +1,10 @@
-"""Equivalent of the offline driver program (driver/spartacus_surface_driver.F90:20-300)
-without the netCDF output stage: read namelists + input file, allocate the
-flux objects, prepare the LW emission, call radsurf, then scale and sum.
+"""Equivalent of the offline driver program (driver/spartacus_surface_driver.F90:20-300):
+read namelists + input file, allocate the flux objects, prepare the LW emission, call radsurf,
+scale and sum, optionally write the netCDF output file (radsurf_save.save_canopy_fluxes).
+
+    python -m spartacus_surface_b200.driver.spartacus_surface_driver config.nam input.nc output.nc
+
+is the counterpart of `bin/spartacus_surface config.nam input.nc output.nc`.
 
 `solver` is the radsurf implementation; it defaults to the product library.
 Tests pass the CPU oracle through the same code to obtain reference results.
@@ -76,9 +80,28 @@ def scale_and_sum(r):
 
 
 def run_case(namelist_path, input_path, solver=None, radsurf_overrides=None, driver_overrides=None,
-             legendre_gauss_init=None, do_scale=True):
+             legendre_gauss_init=None, do_scale=True, output_path=None):
     r = setup_case(namelist_path, input_path, radsurf_overrides, driver_overrides, legendre_gauss_init)
     r.status = run_radsurf(r, solver)
     if do_scale:
         scale_and_sum(r)
+    if output_path is not None:
+        if not do_scale:
+            raise ValueError("the output file holds the scaled and summed fluxes")
+        from ..radsurf_save import save_canopy_fluxes
+        save_canopy_fluxes(output_path, r.config, r.canopy_props, r.sw_flux, r.lw_flux)
     return r
+
+
+def main(argv=None):
+    import sys
+    argv = sys.argv[1:] if argv is None else argv
+    if len(argv) != 3:
+        raise SystemExit("usage: spartacus_surface_driver config.nam input.nc output.nc")
+    r = run_case(argv[0], argv[1], output_path=argv[2])
+    if r.status:
+        raise SystemExit(f"radsurf flagged {r.status} layer problems")
+
+
+if __name__ == "__main__":
+    main()

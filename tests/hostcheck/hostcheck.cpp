@@ -79,6 +79,46 @@ struct HostBackend {
     if (a.cfg.ns == 1) fused_run_ns<1>(a, lw, width);
     else fused_run_ns<2>(a, lw, width);
   }
+  // record sweeps after the register-resident layer bodies (mode 3)
+  bool records = false;
+  bool records_shape(const ssb::SolveCfg &c, bool lw, int *oe) {
+    if (!records || !fast || c.ns > 2) return false;
+    int pe = 0, geo = 0;
+    return c.ns == 1 ? fused_shape_ns<1>(c, lw, &pe, oe, &geo) : fused_shape_ns<2>(c, lw, &pe, oe, &geo);
+  }
+  template <int NSA, int NREG, bool URBAN>
+  void record_cols(const ssb::ClassArgs &a, bool lw, long width) {
+    double stack[512];
+    const ssb::StateMem st{stack, 1};
+    for (long t = 0; t < width; ++t) {
+      if (lw)
+        ssb::fused_column_lw<NREG, NSA, URBAN, 1>(a, (int)t, true, st);
+      else
+        ssb::fused_column_sw<NREG, NSA, URBAN, 1>(a, (int)t, true, st);
+    }
+    for (long t = 0; t < width; ++t) {
+      if (lw)
+        ssb::fused_column_lw<NREG, NSA, URBAN, 2>(a, (int)t, true, ssb::StateMem{nullptr, 0});
+      else
+        ssb::fused_column_sw<NREG, NSA, URBAN, 2>(a, (int)t, true, ssb::StateMem{nullptr, 0});
+    }
+  }
+  template <int NSA>
+  void records_run_ns(const ssb::ClassArgs &a, bool lw, long width) {
+    switch (a.cfg.nreg * 2 + (a.cfg.urban ? 1 : 0)) {
+      case 2: record_cols<NSA, 1, false>(a, lw, width); break;
+      case 3: record_cols<NSA, 1, true>(a, lw, width); break;
+      case 4: record_cols<NSA, 2, false>(a, lw, width); break;
+      case 5: record_cols<NSA, 2, true>(a, lw, width); break;
+      case 6: record_cols<NSA, 3, false>(a, lw, width); break;
+      case 7: record_cols<NSA, 3, true>(a, lw, width); break;
+      default: break;
+    }
+  }
+  void records_run(const ssb::ClassArgs &a, bool lw, long width) {
+    if (a.cfg.ns == 1) records_run_ns<1>(a, lw, width);
+    else records_run_ns<2>(a, lw, width);
+  }
   size_t budget = (size_t)1 << 22;  // small on purpose: exercises the chunk loop
   const int *dev_cols(const ssb::Plan &p, size_t off) { return p.all_cols.data() + off; }
   // reversed column order inside every chunk: results must not depend on it
@@ -220,7 +260,11 @@ extern "C" int hostcheck_radsurf(const ssb200_config *config, const ssb200_canop
   be.plan = &plan;
   if (budget_doubles > 0) be.budget = (size_t)budget_doubles;
   be.fast = fast != 0;
+  // fast == 4: generic bodies with the symmetrised Jacobi eigen-systems, as on the device
+  ssb::host_generic_jacobi() = (fast == 4);
+  if (fast == 4) be.fast = false;
   be.fused = fast == 2;
+  be.records = fast == 3;
   ssb::Dispatcher<HostBackend> disp(be);
   rc = disp.run(ca, plan, err);
   if (rc) {
