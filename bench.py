@@ -40,7 +40,9 @@ NLAY = 16
 FULL_COLUMNS = 1 << 20
 UNIT = "column*g*layers/s"
 METRIC = "column_g_layers_per_s_SW+LW"
-FAMILIES = ["sw_layer", "sw_sweep", "lw_layer", "lw_sweep", "surface"]
+# kernel families timed by the library (CUDA events on the launch stream); the last one holds the surface
+# kernels (flat / single-layer tiles) and the gather / scatter passes of the level-major staging
+FAMILIES = ["sw_layer", "sw_sweep", "lw_layer", "lw_sweep", "surface_and_staging"]
 FLUX_NAMES = ("sw_norm_dir", "sw_norm_diff", "lw_internal", "lw_norm")
 
 # Compulsory HBM bytes per (column, layer): 25 input + 40 output doubles + per-column terms

@@ -233,16 +233,20 @@ struct Context {
   int fast_mode = 1;
   size_t l2_set_aside = 0;
   long lay2col_generation = -1;
-  // order the columns of a launch by their segment pattern (fast kernels).  Measured on B200
-  // (256k columns, S2): layer kernels 10.1 -> 8.8 ms (full-sector scratch writes), sweeps
-  // 9.1 -> 10.7 ms (fewer bytes but longer load latency): off by default.
-  int sort_columns = 0;
-  int sort_group = 512;  // ... inside groups of this many neighbouring columns
+  // order the columns of a launch by their segment pattern (fast kernels): warps then take one code
+  // path per layer, the segment kernels write and the sweeps skip whole 32-byte sectors.  Measured on
+  // B200 (1 M columns, S2) TOGETHER with the level-major staging below, which makes the column order
+  // irrelevant for the per-layer inputs and outputs: 59.8 -> 50.9 ms per step (without the staging the
+  // ordering made the sweeps slower: round 1).
+  int sort_columns = 1;
+  int sort_group = 4096;  // ... inside groups of this many neighbouring columns (0: the whole chunk)
   int partition = 1;  // group layer problems by solved sub-block before the fast layer kernels
   // column-resident kernels (ssb_fused.cuh) where they exist (1 and 2 streams); 0: split path
   // sweeps of the register-resident path at 1 and 2 streams: 0 = interface-state sweeps
   // (ssb_fast_sweeps.cuh), 1 = record sweeps (ssb_fused.cuh MODE 1 / 2)
-  int sweep_mode = 1;
+  int sweep_mode = 0;  // measured on B200: the record sweeps move fewer bytes and are 6 % slower
+  // level-major staging of the per-layer arrays of a chunk (ssb_stage.cuh)
+  int stage_layers = 1;
   int fused_mode = 0;  // measured on B200: 40 % fewer DRAM bytes, 28 % slower - off by default
   int fused_sort = 1;
   int fused_sort_group = 0;   // 0: the whole chunk
@@ -343,6 +347,10 @@ struct CudaBackend {
       tick(0, false);
       if (done) return;
     }
+    if (a.lstride) {  // staged arrays are only understood by the register-resident kernels
+      if (cx.first_error == cudaSuccess) cx.first_error = cudaErrorNotSupported;
+      return;
+    }
     launch(ssb::launch_layer_sw<NS>, a, nt, 0);
   }
   template <int NS>
@@ -361,6 +369,10 @@ struct CudaBackend {
       tick(2, false);
       if (done) return;
     }
+    if (a.lstride) {
+      if (cx.first_error == cudaSuccess) cx.first_error = cudaErrorNotSupported;
+      return;
+    }
     launch(ssb::launch_layer_lw<NS>, a, nt, 2);
   }
   template <int NS>
@@ -373,6 +385,10 @@ struct CudaBackend {
       tick(1, false);
       if (done) return;
     }
+    if (a.lstride) {
+      if (cx.first_error == cudaSuccess) cx.first_error = cudaErrorNotSupported;
+      return;
+    }
     launch(ssb::launch_sweeps_sw<NS>, a, nt, 1);
   }
   template <int NS>
@@ -384,11 +400,30 @@ struct CudaBackend {
       tick(3, false);
       if (done) return;
     }
+    if (a.lstride) {
+      if (cx.first_error == cudaSuccess) cx.first_error = cudaErrorNotSupported;
+      return;
+    }
     launch(ssb::launch_sweeps_lw<NS>, a, nt, 3);
   }
   bool fused_shape(const ssb::SolveCfg &c, bool lw, int *pe, int *oe, int *geo) {
     if (!cx.fast_mode || !cx.fused_mode || c.ns > 2) return false;
     return ssb::fused_shape(c, lw, pe, oe, geo);
+  }
+  bool stage_supported(const ssb::SolveCfg &c) {
+    return cx.fast_mode && cx.partition && cx.stage_layers && c.ns <= 4 && c.nspec <= 1024;
+  }
+  void stage(const ssb::StageArgs &s, bool scatter, bool lw) {
+    if (cx.first_error != cudaSuccess) return;
+    const int fam = 4;  // booked with the surface kernels ("surface" family of ssb200_last_kernel_times_ms)
+    (void)lw;
+    tick(fam, true);
+    long n = 0;
+    ssb::stage_launch(s, scatter, cx.stream, &n);
+    g_launches += n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && cx.first_error == cudaSuccess) cx.first_error = e;
+    tick(fam, false);
   }
   bool records_shape(const ssb::SolveCfg &c, bool lw, int *oe) {
     if (!cx.fast_mode || cx.sweep_mode != 1 || !cx.partition || c.ns > 2) return false;
@@ -1229,6 +1264,10 @@ int ssb200_set_option(const char *name, int64_t value) {
   }
   if (n == "pipeline_max_blocks") {
     g_ctx.pipeline_max_blocks = value < 1 ? 1 : (int)value;
+    return 0;
+  }
+  if (n == "stage_layers") {
+    g_ctx.stage_layers = value != 0;
     return 0;
   }
   if (n == "record_sweeps") {

@@ -16,8 +16,80 @@
 #include <vector>
 
 #include "ssb_solver.cuh"
+#include "ssb_stage.cuh"
 
 namespace ssb {
+
+// Lists the per-layer arrays of a pass and redirects the members of `b` to their level-major staging
+// buffers (ssb_stage.cuh), carved from `cursor` (NULL: only count).  Returns doubles per (level, column).
+inline size_t stage_plan(ClassArgs &b, bool lw, size_t per_elem, double *cursor, StageList *in, StageList *out) {
+  size_t elems = 0;
+  auto add = [&](StageList *list, double *&member, int ns) {
+    if (!member) return;
+    elems += (size_t)ns;
+    if (!cursor) return;
+    list->ref[list->n] = member;
+    list->staged[list->n] = cursor;
+    list->nspec[list->n] = ns;
+    ++list->n;
+    member = cursor;
+    cursor += (size_t)ns * per_elem;
+  };
+  auto cin = [&](const double *&member, int ns) { add(in, const_cast<double *&>(member), ns); };
+  if (in) in->n = 0;
+  if (out) out->n = 0;
+  const int ns = b.cfg.nspec;
+  cin(b.cp.dz, 1);
+  cin(b.cp.building_fraction, 1);
+  cin(b.cp.building_scale, 1);
+  cin(b.cp.veg_fraction, 1);
+  cin(b.cp.veg_scale, 1);
+  cin(b.cp.veg_ext, 1);
+  cin(b.cp.veg_fsd, 1);
+  cin(b.cp.veg_contact_fraction, 1);
+  if (lw) {
+    cin(b.lw.air_ext, ns);
+    cin(b.lw.air_ssa, ns);
+    cin(b.lw.clear_air_planck, ns);
+    cin(b.lw.veg_ssa, ns);
+    cin(b.lw.veg_planck, ns);
+    cin(b.lw.veg_air_planck, ns);
+    cin(b.lw.roof_emissivity, ns);
+    cin(b.lw.wall_emissivity, ns);
+    cin(b.lw.roof_emission, ns);
+    cin(b.lw.wall_emission, ns);
+  } else {
+    cin(b.sw.air_ext, ns);
+    cin(b.sw.air_ssa, ns);
+    cin(b.sw.veg_ssa, ns);
+    cin(b.sw.roof_albedo, ns);
+    cin(b.sw.wall_albedo, ns);
+    cin(b.sw.wall_specular_frac, ns);
+    cin(b.sw.roof_albedo_dir, ns);
+  }
+  for (ssb200_canopy_flux *f : {&b.f1, &b.f2}) {
+    add(out, f->roof_in, ns);
+    add(out, f->roof_net, ns);
+    add(out, f->wall_in, ns);
+    add(out, f->wall_net, ns);
+    add(out, f->roof_in_dir, ns);
+    add(out, f->wall_in_dir, ns);
+    add(out, f->clear_air_abs, ns);
+    add(out, f->veg_abs, ns);
+    add(out, f->veg_air_abs, ns);
+    add(out, f->veg_abs_dir, ns);
+    add(out, f->flux_dn_layer_top, ns);
+    add(out, f->flux_up_layer_top, ns);
+    add(out, f->flux_dn_layer_base, ns);
+    add(out, f->flux_up_layer_base, ns);
+    add(out, f->flux_dn_dir_layer_top, ns);
+    add(out, f->flux_dn_dir_layer_base, ns);
+    add(out, f->roof_sunlit_frac, 1);
+    add(out, f->wall_sunlit_frac, 1);
+    add(out, f->veg_sunlit_frac, 1);
+  }
+  return elems;
+}
 
 struct ColumnClass {
   int urban, nreg;
@@ -167,6 +239,8 @@ struct CallArgs {
 //   void fused_run(const ClassArgs&, bool lw, long width)
 //   bool records_shape(const SolveCfg&, bool lw, int *op_elems)   record sweeps available and enabled
 //   void records_run(const ClassArgs&, bool lw, long width)
+//   bool stage_supported(const SolveCfg&)            level-major staging of per-layer arrays enabled for this class
+//   void stage(const StageArgs&, bool scatter, bool lw)   gather (inputs -> staging) / scatter (staging -> outputs)
 template <class Backend>
 struct Dispatcher {
   Backend &be;
@@ -191,13 +265,21 @@ struct Dispatcher {
     // down-pass operator record and a downward pass through the records (ssb_fused.cuh MODE 1 / 2)
     int r_op = 0;
     const bool rec = !fused && be.records_shape(c, lw, &r_op);
+    // level-major staging of the per-layer arrays (ssb_stage.cuh): register-resident kernels only
+    const bool stage = !fused && be.stage_supported(c);
+    size_t stage_elems = 0;
+    if (stage) {
+      ClassArgs probe = a;
+      stage_elems = stage_plan(probe, lw, 0, nullptr, nullptr, nullptr);
+    }
     // class columns are ascending: restrict to the window by binary search
     size_t pos = (size_t)(std::lower_bound(k.cols.begin(), k.cols.end(), col_lo) - k.cols.begin());
     const size_t ntot = (size_t)(std::lower_bound(k.cols.begin(), k.cols.end(), col_hi) - k.cols.begin());
     auto need_of = [&](size_t lm, size_t wd) {
-      if (rec) return scratch_doubles(el, lm, wd) + scratch_doubles((size_t)r_op, lm > 0 ? lm : 1, wd);
+      const size_t staging = stage_elems * lm * (wd / (size_t)c.nspec);
+      if (rec) return scratch_doubles(el, lm, wd) + scratch_doubles((size_t)r_op, lm > 0 ? lm : 1, wd) + staging;
       return fused ? f_tiles + scratch_doubles((size_t)f_op, lm > 0 ? lm : 1, wd)
-                   : scratch_doubles(el, lm, wd) + scratch_doubles(es, lm + 1, wd);
+                   : scratch_doubles(el, lm, wd) + scratch_doubles(es, lm + 1, wd) + staging;
     };
     while (pos < ntot) {
       // grow the chunk while its scratch (sized by the tallest column) fits the budget
@@ -238,18 +320,35 @@ struct Dispatcher {
       a.ne_layer_geo = (int)el - kGeoElems;
       a.ne_sweep = rec ? r_op : (int)es;
       a.save_profile = (a.f1.flux_dn_layer_top || a.f2.flux_dn_layer_top) ? 1 : 0;
+      // b: what the kernels see - the caller's arrays, or (staged) the chunk's level-major copies
+      ClassArgs b = a;
+      StageArgs sin, sout;
+      const bool staged = stage && lmax > 0;
+      if (staged) {
+        double *cursor = a.sweep + (rec ? scratch_doubles((size_t)r_op, (size_t)lmax, width)
+                                        : scratch_doubles(es, (size_t)lmax + 1, width));
+        stage_plan(b, lw, (size_t)lmax * cnt, cursor, &sin.list, &sout.list);
+        b.lstride = (int)cnt;
+        sin.cols = sout.cols = a.cols;
+        sin.nlay = sout.nlay = a.nlay;
+        sin.istartlay = sout.istartlay = a.istartlay;
+        sin.ncols = sout.ncols = (int)cnt;
+        sin.lmax = sout.lmax = lmax;
+        be.stage(sin, false, lw);
+      }
       if (lmax > 0) {
         if (lw)
-          be.template layer_lw<NS>(a, (long)width * lmax);
+          be.template layer_lw<NS>(b, (long)width * lmax);
         else
-          be.template layer_sw<NS>(a, (long)width * lmax);
+          be.template layer_sw<NS>(b, (long)width * lmax);
       }
       if (rec)
-        be.records_run(a, lw, (long)width);
+        be.records_run(b, lw, (long)width);
       else if (lw)
-        be.template sweeps_lw<NS>(a, (long)width);
+        be.template sweeps_lw<NS>(b, (long)width);
       else
-        be.template sweeps_sw<NS>(a, (long)width);
+        be.template sweeps_sw<NS>(b, (long)width);
+      if (staged) be.stage(sout, true, lw);
       pos += cnt;
     }
   }

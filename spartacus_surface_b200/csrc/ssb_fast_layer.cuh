@@ -109,7 +109,7 @@ SSB_HDI bool fast_sw_prepare(const ClassArgs &a, int q, int lev, LayerGeom &gm, 
   if (lev >= a.nlay[col]) return false;
   op.cos_sza = a.cp.cos_sza[col];
   if (!(op.cos_sza > 0.0)) return false;
-  const int il = a.istartlay[col] - 1 + lev;
+  const int il = layer_index(a, ic, col, lev);
   op.zcos = c.urban ? dmax(op.cos_sza, 1.0e-6) : op.cos_sza;
   op.sin0 = 0.0;
   if (c.urban) {
@@ -196,7 +196,7 @@ SSB_HDI void fast_layer_problem_lw_impl(const ClassArgs &a, int q, int lev, cons
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
   if (lev >= a.nlay[col]) return;
-  const int il = a.istartlay[col] - 1 + lev;
+  const int il = layer_index(a, ic, col, lev);
   LayerOptics op;
   op.dz = a.cp.dz[il];
   LayerGeom gm;
@@ -296,10 +296,10 @@ SSB_HDI unsigned column_segment_key(const ClassArgs &a, int col) {
 // sub-block of regions it solves), -1 when there is none.
 SSB_HDI int fast_prepare_level(const ClassArgs &a, int q, int k) {
   const SolveCfg &c = a.cfg;
-  const int col = a.cols[q / c.nspec];
+  const int ic = q / c.nspec, col = a.cols[ic];
   if (k >= a.nlay[col]) return -1;
   if (!c.lw && !(a.cp.cos_sza[col] > 0.0)) return -1;
-  const int il = a.istartlay[col] - 1 + k;
+  const int il = layer_index(a, ic, col, k);
   double bf, bs, vf, vs, ve, vcf, vfsd;
   load_geometry_inputs(a, il, bf, bs, vf, vs, ve, vcf, vfsd);
   LayerGeom gm;

@@ -174,15 +174,16 @@ SSB_HDI void adding_core(const StateMem &st, const Scr &L, const Scr &W, int jl,
 template <int NREG, bool URBAN, bool LW>
 SSB_HDI void overlap_above(const ClassArgs &a, int il1, int nlay, int jl, double *U, double *V) {
   const bool veg = NREG > 1 || !URBAN;
+  const int ls = layer_step(a);
   double fb[3] = {0.0, 0.0, 0.0}, fa[3] = {0.0, 0.0, 0.0};
   {
-    const int il = il1 + jl;
+    const int il = il1 + jl * ls;
     region_fractions_t<NREG, URBAN, LW>(URBAN ? a.cp.building_fraction[il] : 0.0,
                                         (veg && a.cp.veg_fraction) ? a.cp.veg_fraction[il] : 0.0, fb);
   }
   const bool top = jl + 1 >= nlay;
   if (!top) {
-    const int il = il1 + jl + 1;
+    const int il = il1 + (jl + 1) * ls;
     region_fractions_t<NREG, URBAN, LW>(URBAN ? a.cp.building_fraction[il] : 0.0,
                                         (veg && a.cp.veg_fraction) ? a.cp.veg_fraction[il] : 0.0, fa);
   }
@@ -230,14 +231,14 @@ SSB_HDI void overlap_matrix(const double *Ab, const double *rb, const double *U,
 // diffuse object) are cleared here (radsurf_canopy_flux.F90:286-341).
 template <int NREG, bool URBAN>
 SSB_HDI void zero_unwritten_sw(const ssb200_canopy_flux &f, int nspec, int g, int col, int il1, int nlay, bool own,
-                               bool direct) {
+                               bool direct, int ls = 1) {
   auto zl = [&](double *p) {
     if (p)
-      for (int l = 0; l < nlay; ++l) p[(size_t)g + (size_t)nspec * (il1 + l)] = 0.0;
+      for (int l = 0; l < nlay; ++l) p[(size_t)g + (size_t)nspec * (il1 + l * ls)] = 0.0;
   };
   auto zs = [&](double *p) {
     if (p && own)
-      for (int l = 0; l < nlay; ++l) p[il1 + l] = 0.0;
+      for (int l = 0; l < nlay; ++l) p[il1 + l * ls] = 0.0;
   };
   if (!URBAN) {
     zl(f.roof_in);
@@ -268,10 +269,10 @@ SSB_HDI void zero_unwritten_sw(const ssb200_canopy_flux &f, int nspec, int g, in
   }
 }
 template <int NREG, bool URBAN>
-SSB_HDI void zero_unwritten_lw(const ssb200_canopy_flux &f, int nspec, int g, int col, int il1, int nlay) {
+SSB_HDI void zero_unwritten_lw(const ssb200_canopy_flux &f, int nspec, int g, int col, int il1, int nlay, int ls = 1) {
   auto zl = [&](double *p) {
     if (p)
-      for (int l = 0; l < nlay; ++l) p[(size_t)g + (size_t)nspec * (il1 + l)] = 0.0;
+      for (int l = 0; l < nlay; ++l) p[(size_t)g + (size_t)nspec * (il1 + l * ls)] = 0.0;
   };
   if (!URBAN) {
     zl(f.roof_in);
@@ -294,9 +295,9 @@ SSB_HDI void zero_unwritten_lw(const ssb200_canopy_flux &f, int nspec, int g, in
   if (g == 0) {
     if (f.ground_sunlit_frac) f.ground_sunlit_frac[col] = 0.0;
     for (int l = 0; l < nlay; ++l) {
-      if (f.roof_sunlit_frac) f.roof_sunlit_frac[il1 + l] = 0.0;
-      if (f.wall_sunlit_frac) f.wall_sunlit_frac[il1 + l] = 0.0;
-      if (f.veg_sunlit_frac) f.veg_sunlit_frac[il1 + l] = 0.0;
+      if (f.roof_sunlit_frac) f.roof_sunlit_frac[il1 + l * ls] = 0.0;
+      if (f.wall_sunlit_frac) f.wall_sunlit_frac[il1 + l * ls] = 0.0;
+      if (f.veg_sunlit_frac) f.veg_sunlit_frac[il1 + l * ls] = 0.0;
     }
   }
 }
@@ -323,7 +324,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   const int nspec = c.nspec;
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
-  const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
+  const int nlay = a.nlay[col], il1 = layer_index(a, ic, col, 0), ls = layer_step(a);
   const ssb200_canopy_flux &fdir = a.f1, &fdif = a.f2;
   const double cos_sza = a.cp.cos_sza[col];
   int itransp = 0;
@@ -331,7 +332,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
     double best = 0.0;
     for (int gg = 0; gg < nspec; ++gg) {
       double od = 0.0;
-      for (int l = 0; l < nlay; ++l) od += a.sw.air_ext[(size_t)gg + (size_t)nspec * (il1 + l)] * a.cp.dz[il1 + l];
+      for (int l = 0; l < nlay; ++l) od += a.sw.air_ext[(size_t)gg + (size_t)nspec * (il1 + l * ls)] * a.cp.dz[il1 + l * ls];
       if (gg == 0 || od < best) {
         best = od;
         itransp = gg;
@@ -340,12 +341,12 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   }
   const bool own = (g == itransp);
   if (!(cos_sza > 0.0)) {  // night: every member of the column is zero (radsurf_interface.F90:193-196)
-    zero_column(fdir, nspec, g, col, il1, nlay, own);
-    zero_column(fdif, nspec, g, col, il1, nlay, own);
+    zero_column(fdir, nspec, g, col, il1, nlay, own, ls);
+    zero_column(fdif, nspec, g, col, il1, nlay, own, ls);
     return;
   }
-  zero_unwritten_sw<NREG, URBAN>(fdir, nspec, g, col, il1, nlay, own, true);
-  zero_unwritten_sw<NREG, URBAN>(fdif, nspec, g, col, il1, nlay, own, false);
+  zero_unwritten_sw<NREG, URBAN>(fdir, nspec, g, col, il1, nlay, own, true, ls);
+  zero_unwritten_sw<NREG, URBAN>(fdif, nspec, g, col, il1, nlay, own, false, ls);
   const double zcos = URBAN ? dmax(cos_sza, 1.0e-6) : cos_sza;
   const double sin0 = URBAN ? sqrt(1.0 - zcos * zcos) : 0.0;
   const double galb = a.sw.ground_albedo[(size_t)g + (size_t)nspec * col];
@@ -376,7 +377,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   SSB_UNROLL
   for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, 0, st(i));
   for (int jl = 0; jl < nlay; ++jl) {
-    const int il = il1 + jl;
+    const int il = il1 + jl * ls;
     const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
     double X[n * n], Wd[n * d];
     {
@@ -494,10 +495,10 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   SSB_FC(fdif, top_dn_dir) = 0.0;
   SSB_FC(fdif, top_dn) = 1.0;
   SSB_FC(fdif, top_net) = 1.0 - talb_diff;
-  if (URBAN && own && fdir.roof_sunlit_frac && nlay > 0) fdir.roof_sunlit_frac[il1 + nlay - 1] = 1.0;
+  if (URBAN && own && fdir.roof_sunlit_frac && nlay > 0) fdir.roof_sunlit_frac[il1 + (nlay - 1) * ls] = 1.0;
   double flux_dn_dir_clear = 1.0 / zcos;
   for (int jl = nlay - 1; jl >= 0; --jl) {
-    const int il = il1 + jl;
+    const int il = il1 + jl * ls;
     const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
     double f_wall[3], od_scaling[3];
     SSB_UNROLL
@@ -707,9 +708,9 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
       // spectrally independent sunlit fractions from the most transparent interval (urban_sw:805-848)
       const double nonb_here = URBAN ? 1.0 - bf : 1.0;
       double nonb_above = 1.0;
-      if (URBAN && jl + 1 < nlay) nonb_above = 1.0 - a.cp.building_fraction[il + 1];
+      if (URBAN && jl + 1 < nlay) nonb_above = 1.0 - a.cp.building_fraction[il + ls];
       if (URBAN) {
-        const double roof_fraction = (jl == nlay - 1) ? bf : dmax(0.0, bf - a.cp.building_fraction[il + 1]);
+        const double roof_fraction = (jl == nlay - 1) ? bf : dmax(0.0, bf - a.cp.building_fraction[il + ls]);
         if (own && fdir.roof_sunlit_frac)
           fdir.roof_sunlit_frac[il] = SSB_FL(fdir, roof_in_dir, il) * nonb_above /
                                       (zcos * flux_dn_dir_clear * dmax(c.min_bld, roof_fraction));
@@ -783,10 +784,10 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   const int nspec = c.nspec;
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
-  const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
+  const int nlay = a.nlay[col], il1 = layer_index(a, ic, col, 0), ls = layer_step(a);
   const ssb200_canopy_flux &fint = a.f1, &fnorm = a.f2;
-  zero_unwritten_lw<NREG, URBAN>(fint, nspec, g, col, il1, nlay);
-  zero_unwritten_lw<NREG, URBAN>(fnorm, nspec, g, col, il1, nlay);
+  zero_unwritten_lw<NREG, URBAN>(fint, nspec, g, col, il1, nlay, ls);
+  zero_unwritten_lw<NREG, URBAN>(fnorm, nspec, g, col, il1, nlay, ls);
   double hw[NS], mu_inv[NS], tang[NS];
   SSB_UNROLL
   for (int js = 0; js < NS; ++js) {
@@ -822,7 +823,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   SSB_UNROLL
   for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, 0, st(i));
   for (int jl = 0; jl < nlay; ++jl) {
-    const int il = il1 + jl;
+    const int il = il1 + jl * ls;
     const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
     double X[n * n], v1[n];
     {
@@ -855,7 +856,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
     for (int js = 0; js < NS; ++js) rb[js] = rs[js] = 0.0;
     if (URBAN) {
       const double bfj = a.cp.building_fraction[il];
-      const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + 1]) : bfj;
+      const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + ls]) : bfj;
       const double remis = SSB_LAY(a.lw.roof_emissivity, g, il), remission = SSB_LAY(a.lw.roof_emission, g, il);
       SSB_UNROLL
       for (int js = 0; js < NS; ++js) {
@@ -907,7 +908,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   SSB_FC(fnorm, top_dn) = 1.0;
   SSB_FC(fnorm, top_net) = top_emissivity;
   for (int jl = nlay - 1; jl >= 0; --jl) {
-    const int il = il1 + jl;
+    const int il = il1 + jl * ls;
     const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
     double f_wall[3], od_scaling[3];
     SSB_UNROLL
@@ -973,7 +974,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
     smv2<n, n, 0, NS>(L, Lay::oT, jl, z1_i, z1_f, ub_i, ub_f, sk);
     if (URBAN) {
       const double bfj = a.cp.building_fraction[il];
-      const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + 1]) : bfj;
+      const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + ls]) : bfj;
       const double remis = SSB_LAY(a.lw.roof_emissivity, g, il), remission = SSB_LAY(a.lw.roof_emission, g, il);
       double sroof_i = 0.0, sroof_f = 0.0, rup_i = 0.0, rup_f = 0.0;
       SSB_UNROLL

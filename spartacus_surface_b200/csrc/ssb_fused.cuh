@@ -34,6 +34,19 @@
 #pragma once
 #include "ssb_fast_sweeps.cuh"
 
+// unroll factor of the per-column loops of the upward steps (1 = rolled: smallest code; 2 or 3 let
+// the two triangular solves of neighbouring columns overlap)
+#ifndef SSB_REC_UNROLL
+#define SSB_REC_UNROLL 1
+#endif
+#if defined(__CUDACC__)
+#define SSB_PRAGMA_(x) _Pragma(#x)
+#define SSB_PRAGMA(x) SSB_PRAGMA_(x)
+#define SSB_REC_LOOP SSB_PRAGMA(unroll SSB_REC_UNROLL)
+#else
+#define SSB_REC_LOOP
+#endif
+
 namespace ssb {
 
 // Phase alignment of the warps of a block (device only; a.fused bit 1): the loop body of a column
@@ -111,6 +124,7 @@ struct SwFused {
 template <int NREG, int NS, bool URBAN, bool REC = false>
 SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Scr &Mo, int jl, int il, int il1,
                                     int nlay, int g, const StateMem &sm, double zcos, double sin0) {
+  const int ls = layer_step(a);
   typedef SwFused<NREG, NS, URBAN> F;
   typedef SwSweepLayout<NREG, NS, URBAN> Lay;
   constexpr int n = NREG * NS, d = NREG, NRB = URBAN ? NREG + 1 : NREG, NF = F::NF, NFD = F::NFD;
@@ -204,7 +218,7 @@ SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Sc
   const bool prof = a.save_profile != 0;
   // ---- columns of the direct part (first: they read all of R, which the diffuse columns then
   //      overwrite with a_below, column by column) ----------------------------------------------
-  SSB_ROLLED
+  SSB_REC_LOOP
   for (int j = 0; j < d; ++j) {
     if (!region_solved(seg, j)) {
       SSB_UNROLL
@@ -289,7 +303,7 @@ SSB_HD inline void fused_up_step_sw(const ClassArgs &a, const Tile &Lp, const Sc
     for (int f = 0; f < NFD; ++f) Mo.st(F::mFd + f + NFD * j, jl, fd[f]);
   }
   // ---- columns of the diffuse part (rolled: the same code for every column) -----------------
-  SSB_ROLLED
+  SSB_REC_LOOP
   for (int j = 0; j < n; ++j) {
     const int rj = j / NS;
     if (!region_solved(seg, rj)) {
@@ -430,7 +444,7 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, co
   const int q = active ? q_in : 0;  // (idle threads of the last tile only keep the barriers company)
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
-  const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
+  const int nlay = a.nlay[col], il1 = layer_index(a, ic, col, 0), ls = layer_step(a);
   const ssb200_canopy_flux &fdir = a.f1, &fdif = a.f2;
   const double cos_sza = a.cp.cos_sza[col];
   int itransp = 0;
@@ -438,7 +452,7 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, co
     double best = 0.0;
     for (int gg = 0; gg < nspec; ++gg) {
       double od = 0.0;
-      for (int l = 0; l < nlay; ++l) od += a.sw.air_ext[(size_t)gg + (size_t)nspec * (il1 + l)] * a.cp.dz[il1 + l];
+      for (int l = 0; l < nlay; ++l) od += a.sw.air_ext[(size_t)gg + (size_t)nspec * (il1 + l * ls)] * a.cp.dz[il1 + l * ls];
       if (gg == 0 || od < best) {
         best = od;
         itransp = gg;
@@ -448,8 +462,8 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, co
   const bool own = (g == itransp);
   const bool live = active && (cos_sza > 0.0);
   if (MODE != 2 && active && !live) {  // night: every member of the column is zero (radsurf_interface.F90:193-196)
-    zero_column(fdir, nspec, g, col, il1, nlay, own);
-    zero_column(fdif, nspec, g, col, il1, nlay, own);
+    zero_column(fdir, nspec, g, col, il1, nlay, own, ls);
+    zero_column(fdif, nspec, g, col, il1, nlay, own, ls);
   }
   if (!live) {
     if (!REC && (a.fused & 2))
@@ -460,8 +474,8 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, co
     return;
   }
   if (MODE != 2) {
-    zero_unwritten_sw<NREG, URBAN>(fdir, nspec, g, col, il1, nlay, own, true);
-    zero_unwritten_sw<NREG, URBAN>(fdif, nspec, g, col, il1, nlay, own, false);
+    zero_unwritten_sw<NREG, URBAN>(fdir, nspec, g, col, il1, nlay, own, true, ls);
+    zero_unwritten_sw<NREG, URBAN>(fdif, nspec, g, col, il1, nlay, own, false, ls);
   }
   const double zcos = URBAN ? dmax(cos_sza, 1.0e-6) : cos_sza;
   const double sin0 = URBAN ? sqrt(1.0 - zcos * zcos) : 0.0;
@@ -500,14 +514,14 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, co
     }
     if (REC) {
       for (int jl = 0; jl < nlay; ++jl)
-        fused_up_step_sw<NREG, NS, URBAN, REC>(a, Lp.at(jl), Mo, jl, il1 + jl, il1, nlay, g, st, zcos, sin0);
+        fused_up_step_sw<NREG, NS, URBAN, REC>(a, Lp.at(jl), Mo, jl, il1 + jl * ls, il1, nlay, g, st, zcos, sin0);
     } else {
       const int nloop = (a.fused & 2) ? a.lmax : nlay;
       for (int jl = 0; jl < nloop; ++jl) {
         phase_sync(a);
         if (jl < nlay) fused_layer_sw<NREG, NS>(a, q, jl, st);
         phase_sync(a);
-        if (jl < nlay) fused_up_step_sw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st, zcos, sin0);
+        if (jl < nlay) fused_up_step_sw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl * ls, il1, nlay, g, st, zcos, sin0);
       }
     }
     SSB_UNROLL
@@ -544,12 +558,12 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, co
   SSB_FC(fdif, top_dn_dir) = 0.0;
   SSB_FC(fdif, top_dn) = 1.0;
   SSB_FC(fdif, top_net) = 1.0 - talb_diff;
-  if (URBAN && own && fdir.roof_sunlit_frac && nlay > 0) fdir.roof_sunlit_frac[il1 + nlay - 1] = 1.0;
+  if (URBAN && own && fdir.roof_sunlit_frac && nlay > 0) fdir.roof_sunlit_frac[il1 + (nlay - 1) * ls] = 1.0;
   double flux_dn_dir_clear = 1.0 / zcos;
   double ua_sum_d = 0.0, ua_sum_f = 0.0, vt_d = 0.0, vt_f = 0.0;  // at the ground, from the last record
   const bool prof = a.save_profile != 0;
   for (int jl = nlay - 1; jl >= 0; --jl) {
-    const int il = il1 + jl;
+    const int il = il1 + jl * ls;
     const int seg = (int)Mo.ld(F::mScal + 1, jl);
     const double f_wall_dir_clear = Mo.ld(F::mScal, jl);
     const bool veg = NREG > 1 || !URBAN;
@@ -688,9 +702,9 @@ SSB_HD inline void fused_column_sw(const ClassArgs &a, int q_in, bool active, co
       // spectrally independent sunlit fractions from the most transparent interval (urban_sw:805-848)
       const double nonb_here = URBAN ? 1.0 - bf : 1.0;
       double nonb_above = 1.0;
-      if (URBAN && jl + 1 < nlay) nonb_above = 1.0 - a.cp.building_fraction[il + 1];
+      if (URBAN && jl + 1 < nlay) nonb_above = 1.0 - a.cp.building_fraction[il + ls];
       if (URBAN) {
-        const double roof_fraction = (jl == nlay - 1) ? bf : dmax(0.0, bf - a.cp.building_fraction[il + 1]);
+        const double roof_fraction = (jl == nlay - 1) ? bf : dmax(0.0, bf - a.cp.building_fraction[il + ls]);
         if (own && fdir.roof_sunlit_frac)
           fdir.roof_sunlit_frac[il] = (zcos * dir_below[NREG]) * nonb_above /
                                       (zcos * flux_dn_dir_clear * dmax(c.min_bld, roof_fraction));
@@ -785,6 +799,7 @@ struct LwFused {
 template <int NREG, int NS, bool URBAN, bool REC = false>
 SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Scr &Mo, int jl, int il, int il1,
                                     int nlay, int g, const StateMem &sm) {
+  const int ls = layer_step(a);
   typedef LwFused<NREG, NS, URBAN> F;
   typedef LwSweepLayout<NREG, NS, URBAN> Lay;
   constexpr int n = NREG * NS, d = NREG, NRB = URBAN ? NREG + 1 : NREG, NF = F::NF;
@@ -919,7 +934,7 @@ SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Sc
       Mo.st(F::mProf + (n + 1) + n, jl, sua);
     }
   }
-  SSB_ROLLED
+  SSB_REC_LOOP
   for (int j = 0; j < n; ++j) {
     const int rj = j / NS;
     if (!region_solved(seg, rj)) {
@@ -984,7 +999,7 @@ SSB_HD inline void fused_up_step_lw(const ClassArgs &a, const Tile &Lp, const Sc
   }
   if (URBAN) {
     const double bfj = a.cp.building_fraction[il];
-    const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + 1]) : bfj;
+    const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + ls]) : bfj;
     const double remis = SSB_LAY(a.lw.roof_emissivity, g, il), remission = SSB_LAY(a.lw.roof_emission, g, il);
     SSB_UNROLL
     for (int js = 0; js < NS; ++js) {
@@ -1037,7 +1052,7 @@ SSB_HD inline void fused_column_lw(const ClassArgs &a, int q_in, bool active, co
   const int q = active ? q_in : 0;
   const int ic = q / nspec, g = q % nspec;
   const int col = a.cols[ic];
-  const int nlay = a.nlay[col], il1 = a.istartlay[col] - 1;
+  const int nlay = a.nlay[col], il1 = layer_index(a, ic, col, 0), ls = layer_step(a);
   const ssb200_canopy_flux &fint = a.f1, &fnorm = a.f2;
   if (!active) {
     if (!REC && (a.fused & 2))
@@ -1048,8 +1063,8 @@ SSB_HD inline void fused_column_lw(const ClassArgs &a, int q_in, bool active, co
     return;
   }
   if (MODE != 2) {
-    zero_unwritten_lw<NREG, URBAN>(fint, nspec, g, col, il1, nlay);
-    zero_unwritten_lw<NREG, URBAN>(fnorm, nspec, g, col, il1, nlay);
+    zero_unwritten_lw<NREG, URBAN>(fint, nspec, g, col, il1, nlay, ls);
+    zero_unwritten_lw<NREG, URBAN>(fnorm, nspec, g, col, il1, nlay, ls);
   }
   double hw[NS], tang[NS];
   SSB_UNROLL
@@ -1089,14 +1104,14 @@ SSB_HD inline void fused_column_lw(const ClassArgs &a, int q_in, bool active, co
     }
     if (REC) {
       for (int jl = 0; jl < nlay; ++jl)
-        fused_up_step_lw<NREG, NS, URBAN, REC>(a, Lp.at(jl), Mo, jl, il1 + jl, il1, nlay, g, st);
+        fused_up_step_lw<NREG, NS, URBAN, REC>(a, Lp.at(jl), Mo, jl, il1 + jl * ls, il1, nlay, g, st);
     } else {
       const int nloop = (a.fused & 2) ? a.lmax : nlay;
       for (int jl = 0; jl < nloop; ++jl) {
         phase_sync(a);
         if (jl < nlay) fused_layer_lw<NREG, NS>(a, q, jl, st);
         phase_sync(a);
-        if (jl < nlay) fused_up_step_lw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl, il1, nlay, g, st);
+        if (jl < nlay) fused_up_step_lw<NREG, NS, URBAN>(a, Lp, Mo, jl, il1 + jl * ls, il1, nlay, g, st);
       }
     }
     double sAll = 0.0;
@@ -1129,7 +1144,7 @@ SSB_HD inline void fused_column_lw(const ClassArgs &a, int q_in, bool active, co
   SSB_FC(fnorm, top_net) = top_emissivity;
   const bool prof = a.save_profile != 0;
   for (int jl = nlay - 1; jl >= 0; --jl) {
-    const int il = il1 + jl;
+    const int il = il1 + jl * ls;
     const int seg = (int)Mo.ld(F::mScal, jl);
     double xb_i[NRB * NS], xb_f[NRB * NS];
     {
@@ -1177,7 +1192,7 @@ SSB_HD inline void fused_column_lw(const ClassArgs &a, int q_in, bool active, co
     }
     if (URBAN) {
       const double bfj = a.cp.building_fraction[il];
-      const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + 1]) : bfj;
+      const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + ls]) : bfj;
       const double remis = SSB_LAY(a.lw.roof_emissivity, g, il), remission = SSB_LAY(a.lw.roof_emission, g, il);
       double sroof_i = 0.0, sroof_f = 0.0, rup_i = 0.0, rup_f = 0.0;
       SSB_UNROLL

@@ -171,6 +171,14 @@ SSB_HDI bool sm_jacobi_sym(double *Y, double *U, int max_sweeps) {
         const double alpha = 0.5 * (aqq - app);
         const double h2 = fma(alpha, alpha, beta * beta);
         const bool skip = converged || !(beta * beta > 1.0e-40 * h2);
+        // a rotation that is the identity for every problem of the warp is not executed at all (late
+        // sweeps: most pairs are already below the threshold).  Executing it would leave the same bits
+        // - c = 1, s = 0 reproduce every entry exactly and only zero y_pq - so a problem's result does
+        // not depend on its warp neighbours either way.
+        if (all_lanes(skip)) {
+          Y[q + N * p] = 0.0;
+          continue;
+        }
         const double rh = rsqrt_pos(skip ? 1.0 : h2);
         const double x = fma(0.5 * fabs(alpha), rh, 0.5);
         const double rc = rsqrt_pos(x);

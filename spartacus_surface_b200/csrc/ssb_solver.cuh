@@ -60,7 +60,20 @@ struct ClassArgs {
   // `sweep` holds the per-level down-pass operator records (ssb_fused.cuh)
   int fused;
   int save_profile;           // flux profiles requested (decides whether their operator rows are formed)
+  // Level-major staging of the per-layer arrays (register-resident path; ssb_driver.hpp): 0 = the
+  // per-layer members of cp / sw / lw / f1 / f2 are the caller's arrays in the reference layout
+  // (packed ragged layers, istartlay); > 0 = they are the chunk's staging buffers, where layer `lev`
+  // of chunk column ic sits at index ic + lev * lstride (lstride = columns of the chunk), so that the
+  // threads of a warp (neighbouring columns, one level) touch consecutive addresses.
+  int lstride;
 };
+
+// index of layer `lev` of chunk column ic (global column col) in the per-layer arrays, and the index
+// distance between vertically adjacent layers of a column (see ClassArgs::lstride)
+SSB_HDI int layer_index(const ClassArgs &a, int ic, int col, int lev) {
+  return a.lstride ? ic + lev * a.lstride : a.istartlay[col] - 1 + lev;
+}
+SSB_HDI int layer_step(const ClassArgs &a) { return a.lstride ? a.lstride : 1; }
 
 constexpr int kScratchTile = 128;
 SSB_HDI size_t sidx(int e, int lev, int nlev, int nelem, int q) {
@@ -500,13 +513,13 @@ SSB_HDI double vsum(const double *v, int i0, int cnt) {
 // radsurf_canopy_flux.F90:286-341); the non-spectral members are zeroed by the
 // thread that owns them (`own_scalars`).
 SSB_HD inline void zero_column(const ssb200_canopy_flux &f, int nspec, int g, int col, int il1, int nlay,
-                               bool own_scalars) {
+                               bool own_scalars, int ls = 1) {
   auto zc = [&](double *p) {
     if (p) p[(size_t)g + (size_t)nspec * col] = 0.0;
   };
   auto zl = [&](double *p) {
     if (p)
-      for (int l = 0; l < nlay; ++l) p[(size_t)g + (size_t)nspec * (il1 + l)] = 0.0;
+      for (int l = 0; l < nlay; ++l) p[(size_t)g + (size_t)nspec * (il1 + l * ls)] = 0.0;
   };
   zc(f.ground_dn);
   zc(f.ground_net);
@@ -534,9 +547,9 @@ SSB_HD inline void zero_column(const ssb200_canopy_flux &f, int nspec, int g, in
   if (own_scalars) {
     if (f.ground_sunlit_frac) f.ground_sunlit_frac[col] = 0.0;
     for (int l = 0; l < nlay; ++l) {
-      if (f.roof_sunlit_frac) f.roof_sunlit_frac[il1 + l] = 0.0;
-      if (f.wall_sunlit_frac) f.wall_sunlit_frac[il1 + l] = 0.0;
-      if (f.veg_sunlit_frac) f.veg_sunlit_frac[il1 + l] = 0.0;
+      if (f.roof_sunlit_frac) f.roof_sunlit_frac[il1 + l * ls] = 0.0;
+      if (f.wall_sunlit_frac) f.wall_sunlit_frac[il1 + l * ls] = 0.0;
+      if (f.veg_sunlit_frac) f.veg_sunlit_frac[il1 + l * ls] = 0.0;
     }
   }
 }

@@ -79,6 +79,10 @@ struct HostBackend {
     if (a.cfg.ns == 1) fused_run_ns<1>(a, lw, width);
     else fused_run_ns<2>(a, lw, width);
   }
+  // level-major staging of the per-layer arrays (ssb_stage.cuh), with the register-resident bodies
+  bool stage_layers = true;
+  bool stage_supported(const ssb::SolveCfg &c) { return fast && stage_layers && c.ns <= 4; }
+  void stage(const ssb::StageArgs &s, bool scatter, bool) { ssb::stage_host(s, scatter); }
   // record sweeps after the register-resident layer bodies (mode 3)
   bool records = false;
   bool records_shape(const ssb::SolveCfg &c, bool lw, int *oe) {
@@ -259,6 +263,8 @@ extern "C" int hostcheck_radsurf(const ssb200_config *config, const ssb200_canop
   HostBackend be;
   be.plan = &plan;
   if (budget_doubles > 0) be.budget = (size_t)budget_doubles;
+  be.stage_layers = (fast & 8) == 0;  // bit 3: the caller's arrays in place (no level-major staging)
+  fast &= 7;
   be.fast = fast != 0;
   // fast == 4: generic bodies with the symmetrised Jacobi eigen-systems, as on the device
   ssb::host_generic_jacobi() = (fast == 4);

@@ -39,17 +39,18 @@ def load():
     return _lib
 
 
-def make_solver(budget_doubles=0, fast=False, fused=False, records=False, generic_jacobi=False):
+def make_solver(budget_doubles=0, fast=False, fused=False, records=False, generic_jacobi=False, stage=True):
     """fast: register-resident bodies (split layer / sweeps kernels); fused: the column-resident
     bodies where they exist (1 and 2 streams), register-resident elsewhere; records: register-resident
     layer bodies followed by the record sweeps (1 and 2 streams) - what the device runs by default;
     generic_jacobi: the generic bodies with the symmetrised Jacobi eigen-systems the DEVICE build of the
-    generic kernels uses (the default host build keeps the reference-order QR solver: bit-identity test)."""
+    generic kernels uses (the default host build keeps the reference-order QR solver: bit-identity test); stage=False: the register-resident bodies read and write the
+    caller's arrays in place instead of the level-major staging buffers of the chunk (csrc/ssb_stage.cuh)."""
     def solver(config, canopy_props, sw, lw, bc_out, istartcol=None, iendcol=None,
                sw_norm_dir=None, sw_norm_diff=None, lw_internal=None, lw_norm=None):
         structs = marshal(config, canopy_props, sw, lw, bc_out, sw_norm_dir, sw_norm_diff, lw_internal, lw_norm)
         rc = call_radsurf(load().hostcheck_radsurf, structs, istartcol, iendcol,
-                          extra=(C.c_int64(budget_doubles), C.c_int32(4 if generic_jacobi else (3 if records else (2 if fused else (1 if fast else 0))))))
+                          extra=(C.c_int64(budget_doubles), C.c_int32((4 if generic_jacobi else (3 if records else (2 if fused else (1 if fast else 0)))) | (0 if stage else 8))))
         if rc < 0:
             raise RuntimeError(f"hostcheck_radsurf failed rc={rc}")
         return rc

@@ -70,7 +70,8 @@ def test_column_range_leaves_other_columns_untouched():
             assert np.all(outside == 7.0), (name, k)
 
 
-MODES = {"interface_sweeps": dict(fast=True), "record_sweeps": dict(records=True)}
+MODES = {"interface_sweeps": dict(fast=True), "record_sweeps": dict(records=True),
+         "interface_sweeps_unstaged": dict(fast=True, stage=False)}
 # the generic kernels as the device builds them (symmetrised Jacobi eigen-systems instead of the
 # reference-order QR solver, which stays host-only): every stream count incl. 8
 GENERIC = dict(generic_jacobi=True)
@@ -153,3 +154,16 @@ def test_generic_device_formulation_vs_truth(case):
     if not ok and parity.max_err(ora, truth) > 1e-2:
         pytest.skip("reference arithmetic order has no correct digit on this fixture (LU without pivoting)")
     assert ok, "\n".join(lines)
+
+
+@pytest.mark.parametrize("case", ["simple_surfaces.npz", "urban_2stream.npz", "rami5_HET07_JPS_SUM-00-direct.npz",
+                                  "single_layer_exp.npz", "rami4pilps_vis-snw-0.3-2-4.npz"])
+def test_staging_is_invisible(case):
+    """Level-major staging of the per-layer arrays (csrc/ssb_stage.cuh) changes where the kernels
+    read and write, not what: bit-identical outputs, untouched entries stay untouched."""
+    _, a = _run(case, hostcheck_lib.make_solver(fast=True, stage=True))
+    _, b = _run(case, hostcheck_lib.make_solver(fast=True, stage=False))
+    _identical(a, b)
+    _, c = _run(case, hostcheck_lib.make_solver(records=True, stage=True), cols=(2, 3))
+    _, d = _run(case, hostcheck_lib.make_solver(records=True, stage=False), cols=(2, 3))
+    _identical(c, d)
