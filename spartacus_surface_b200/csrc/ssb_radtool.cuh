@@ -52,11 +52,14 @@ SSB_HD inline int jacobi_sym_dense(int n, double *Y, double *U) {
   for (int sweep = 0; sweep <= 40; ++sweep) {
     bool conv = true;
     for (int p = 0; p < n && conv; ++p)
-      for (int q = p + 1; q < n; ++q)
-        if (!(Y[q + n * p] * Y[q + n * p] <= 1.0e-31 * fabs(Y[p + n * p] * Y[q + n * q]))) {
+      for (int q = p + 1; q < n; ++q) {
+        const double b2 = Y[q + n * p] * Y[q + n * p], al = 0.5 * (Y[q + n * q] - Y[p + n * p]);
+        // (second clause: the rotation of this pair would be the identity, see sm_jacobi_sym)
+        if (!(b2 <= 1.0e-31 * fabs(Y[p + n * p] * Y[q + n * q]) || !(b2 > 1.0e-40 * (al * al + b2)))) {
           conv = false;
           break;
         }
+      }
     if (conv) return 0;
     if (sweep == 40) break;
     for (int p = 0; p < n - 1; ++p)
