@@ -223,6 +223,72 @@ int ssb200_radsurf_fluxes(const ssb200_config *config,
                           int32_t istartcol, int32_t iendcol,
                           ssb200_canopy_flux *sw_flux, ssb200_canopy_flux *lw_flux);
 
+/* Single-precision storage variant: what a `-DSINGLE_PRECISION` build of the reference
+ * (jprb = real32, utilities/parkind1.F90:45-49; Makefile:41-45) passes.  Same members as the
+ * double-precision structs with `float` arrays (the config struct, whose reals are scalars, is
+ * shared: the shim widens them).  The arrays cross PCIe as float (half the bytes), are widened on
+ * the device, the solve runs in FP64 exactly as ssb200_radsurf does - a superset of the
+ * reference's rule that only the eigen-decomposition works in double
+ * (radtool/radtool_eigen_decomposition.F90:55-58) - and every output is the FP64 result rounded
+ * to nearest float.  HOST pointers; same return convention as ssb200_radsurf. */
+typedef struct ssb200_canopy_properties_sp {
+  int32_t ncol, ntotlay;
+  const int32_t *nlay, *istartlay, *i_representation;
+  const float *cos_sza;
+  const float *dz;
+  const float *building_fraction, *building_scale;
+  const float *veg_fraction, *veg_scale, *veg_ext;
+  const float *veg_fsd, *veg_contact_fraction;
+} ssb200_canopy_properties_sp;
+typedef struct ssb200_sw_spectral_properties_sp {
+  int32_t nspec, pad_;
+  const float *air_ext, *air_ssa;
+  const float *veg_ssa;
+  const float *ground_albedo;
+  const float *roof_albedo, *wall_albedo, *wall_specular_frac;
+  const float *ground_albedo_dir;
+  const float *roof_albedo_dir;
+} ssb200_sw_spectral_properties_sp;
+typedef struct ssb200_lw_spectral_properties_sp {
+  int32_t nspec, pad_;
+  const float *air_ext, *air_ssa, *clear_air_planck;
+  const float *veg_ssa, *veg_planck, *veg_air_planck;
+  const float *ground_emissivity, *ground_emission;
+  const float *roof_emissivity, *wall_emissivity;
+  const float *roof_emission, *wall_emission;
+} ssb200_lw_spectral_properties_sp;
+typedef struct ssb200_canopy_flux_sp {
+  int32_t nspec, ncol, ntotlay, pad_;
+  float *ground_dn, *ground_net, *ground_vertical_diff, *top_dn, *top_net;
+  float *ground_dn_dir, *top_dn_dir;
+  float *ground_sunlit_frac;
+  float *roof_in, *roof_net, *wall_in, *wall_net;
+  float *roof_in_dir, *wall_in_dir;
+  float *roof_sunlit_frac, *wall_sunlit_frac;
+  float *clear_air_abs;
+  float *veg_abs, *veg_air_abs;
+  float *veg_abs_dir;
+  float *veg_sunlit_frac;
+  float *flux_dn_layer_top, *flux_up_layer_top;
+  float *flux_dn_layer_base, *flux_up_layer_base;
+  float *flux_dn_dir_layer_top, *flux_dn_dir_layer_base;
+} ssb200_canopy_flux_sp;
+typedef struct ssb200_boundary_conds_out_sp {
+  float *sw_albedo, *sw_albedo_dir;
+  float *lw_emissivity, *lw_emission;
+} ssb200_boundary_conds_out_sp;
+
+int ssb200_radsurf_sp(const ssb200_config *config,
+                      const ssb200_canopy_properties_sp *canopy_props,
+                      const ssb200_sw_spectral_properties_sp *sw_spectral_props,
+                      const ssb200_lw_spectral_properties_sp *lw_spectral_props,
+                      ssb200_boundary_conds_out_sp *bc_out,
+                      int32_t istartcol, int32_t iendcol,
+                      ssb200_canopy_flux_sp *sw_norm_dir,
+                      ssb200_canopy_flux_sp *sw_norm_diff,
+                      ssb200_canopy_flux_sp *lw_internal,
+                      ssb200_canopy_flux_sp *lw_norm);
+
 /* Device-resident variant.  The three per-column index arrays of
  * `canopy_props` (nlay, istartlay, i_representation) stay HOST pointers (they
  * define the launch plan, which is cached between calls while they do not

@@ -39,7 +39,7 @@ def main(path, columns=None):
         if columns:
             sc = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
             ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            b = float(r[ir]) * sc[units[ir]] + float(r[iw]) * sc[units[iw]]
+            b = float(r[ir]) * sc[units[ir]] + float(r[iw]) * sc[units[iw]]  # (the two columns may carry different units)
             print(f"  dram bytes per (column, layer) at {columns} columns x 16 layers: {b / (int(columns) * 16):.0f}")
 
 

@@ -24,7 +24,9 @@ def dptr(a):
         import torch
         assert a.dtype == torch.float64 and a.is_contiguous()
         return C.cast(a.data_ptr(), _dp)
-    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "float64 C-contiguous array required"
+    # float32 members are the single-precision storage variant (radsurf_interface.radsurf_sp): the
+    # address is carried in the same struct slot (the _sp structs of the header are layout-identical)
+    assert a.dtype in (np.float64, np.float32) and a.flags["C_CONTIGUOUS"], "C-contiguous real array required"
     return a.ctypes.data_as(_dp)
 
 

@@ -33,6 +33,8 @@ def _declare(lib):
                     P(_abi.CanopyFlux), P(_abi.CanopyFlux), P(_abi.CanopyFlux), P(_abi.CanopyFlux)]
     lib.ssb200_radsurf.argtypes = radsurf_args
     lib.ssb200_radsurf.restype = C.c_int
+    lib.ssb200_radsurf_sp.argtypes = radsurf_args  # (the _sp structs are layout-identical)
+    lib.ssb200_radsurf_sp.restype = C.c_int
     lib.ssb200_radsurf_device.argtypes = radsurf_args + [C.c_void_p, P(C.c_int32)]
     lib.ssb200_radsurf_device.restype = C.c_int
     lib.ssb200_radsurf_fluxes.argtypes = (radsurf_args[:4] + [P(_abi.DriverInputs)] + radsurf_args[4:7]

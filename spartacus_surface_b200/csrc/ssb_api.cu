@@ -124,6 +124,16 @@ __global__ void k_sigma_t4(double *out, const double *emissivity, const double *
   out[(size_t)nspec * i] = emissivity ? (sb * emissivity[(size_t)nspec * i]) * (t2 * t2) : sb * (t2 * t2);
 }
 
+// ---- single-precision storage variant: float <-> double on the device (ssb200_radsurf_sp) ----
+__global__ void k_f2d(double *dst, const float *src, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
+__global__ void k_d2f(float *dst, const double *src, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];  // round to nearest even
+}
+
 // ---- stages around radsurf for ssb200_radsurf_fluxes ----------------------------------------
 __global__ void k_fill(double *p, double v, long i0, long i1) {
   const long i = i0 + blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -667,13 +677,17 @@ struct Stager {
   int next = 0;
   int rc = 0;
   struct Arr {
-    double *host;
+    double *host;    // (sp: really float *)
     double *dev;
+    float *dev32;    // sp: device copy in the caller's precision
     size_t width;    // doubles per column (per_layer = false) or per packed layer (true)
     bool per_layer, upload, download;
   };
   std::vector<Arr> arrs;
-  Stager(Context &c, cudaStream_t s) : cx(c), stream(s) {}
+  // single-precision storage (ssb200_radsurf_sp): the caller's arrays hold float; they cross PCIe as
+  // float and are widened / rounded on the device, the kernels see double mirrors as always
+  bool sp = false;
+  Stager(Context &c, cudaStream_t s, bool sp_ = false) : cx(c), stream(s), sp(sp_) {}
   // device mirror of `host` (total = rows * width doubles); copies are issued per window
   double *mirror(const double *host, size_t rows, size_t width, bool per_layer, bool upload, bool download) {
     if (!host || rc) return nullptr;
@@ -685,8 +699,19 @@ struct Stager {
       rc = fail(SSB200_ERR_CUDA, std::string("staging allocation: ") + cudaGetErrorString(e));
       return nullptr;
     }
-    arrs.push_back(Arr{const_cast<double *>(host), (double *)b.p, width, per_layer, upload, download});
-    return (double *)b.p;
+    float *d32 = nullptr;
+    if (sp) {
+      if ((size_t)next >= cx.stage.size()) cx.stage.resize((size_t)next + 16);
+      DevBuf &b32 = cx.stage[next++];
+      e = b32.reserve((total > 0 ? total : 1) * sizeof(float));
+      if (e != cudaSuccess) {
+        rc = fail(SSB200_ERR_CUDA, std::string("staging allocation: ") + cudaGetErrorString(e));
+        return nullptr;
+      }
+      d32 = (float *)b32.p;
+    }
+    arrs.push_back(Arr{const_cast<double *>(host), (double *)cx.stage[next - (sp ? 2 : 1)].p, d32, width, per_layer, upload, download});
+    return arrs.back().dev;
   }
   // device-only array (no host counterpart: never copied)
   double *device_only(size_t total) {
@@ -706,8 +731,23 @@ struct Stager {
       if (to_device ? !a.upload : !a.download) continue;
       const size_t off = (a.per_layer ? l0 : c0) * a.width, cnt = ((a.per_layer ? l1 : c1) * a.width) - off;
       if (cnt == 0) continue;
-      cudaError_t e = to_device ? cudaMemcpyAsync(a.dev + off, a.host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, st)
-                                : cudaMemcpyAsync(a.host + off, a.dev + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaError_t e;
+      if (sp) {
+        float *h32 = reinterpret_cast<float *>(a.host);
+        const unsigned blocks = (unsigned)((cnt + 255) / 256);
+        if (to_device) {
+          e = cudaMemcpyAsync(a.dev32 + off, h32 + off, cnt * sizeof(float), cudaMemcpyHostToDevice, st);
+          k_f2d<<<blocks, 256, 0, st>>>(a.dev + off, a.dev32 + off, cnt);
+        } else {
+          k_d2f<<<blocks, 256, 0, st>>>(a.dev32 + off, a.dev + off, cnt);
+          e = cudaMemcpyAsync(h32 + off, a.dev32 + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, st);
+        }
+        ++g_launches;
+        if (e == cudaSuccess) e = cudaGetLastError();
+      } else {
+        e = to_device ? cudaMemcpyAsync(a.dev + off, a.host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, st)
+                      : cudaMemcpyAsync(a.host + off, a.dev + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, st);
+      }
       if (e != cudaSuccess)
         return fail(SSB200_ERR_CUDA, std::string(to_device ? "H2D copy: " : "D2H copy: ") + cudaGetErrorString(e));
     }
@@ -830,7 +870,7 @@ static int radsurf_host(const ssb200_config *config, const ssb200_canopy_propert
                         const ssb200_driver_inputs *drv, ssb200_boundary_conds_out *bc, int32_t istartcol,
                         int32_t iendcol, ssb200_canopy_flux *sw_dir, ssb200_canopy_flux *sw_diff,
                         ssb200_canopy_flux *lw_int, ssb200_canopy_flux *lw_norm, ssb200_canopy_flux *sw_flux,
-                        ssb200_canopy_flux *lw_flux) {
+                        ssb200_canopy_flux *lw_flux, bool sp = false) {
   int rc = ensure_device();
   if (rc) return rc;
   std::lock_guard<std::mutex> lock(g_mutex);
@@ -875,7 +915,7 @@ static int radsurf_host(const ssb200_config *config, const ssb200_canopy_propert
   const size_t cO = (size_t)(c1 - 1), cN = (size_t)(c2 - c1 + 1), lN = l2 - l1;
   if (drv && !contiguous)
     return fail(SSB200_ERR_UNSUPPORTED, "radsurf_fluxes needs the packed layers of the selected columns to be contiguous");
-  Stager sg(cx, st);
+  Stager sg(cx, st, sp);
   ssb200_canopy_properties dcp = *cp;
   auto lay1 = [&](const double *h) { return (const double *)sg.mirror(h, ntot, 1, true, true, false); };
   dcp.cos_sza = sg.mirror(cp->cos_sza, ncol, 1, false, true, false);
@@ -1217,6 +1257,28 @@ int ssb200_radsurf_fluxes(const ssb200_config *config, const ssb200_canopy_prope
   if (!drv) return fail(SSB200_ERR_ARG, "driver_inputs must not be NULL");
   return radsurf_host(config, cp, sw, lw, drv, bc, istartcol, iendcol, nullptr, nullptr, nullptr, nullptr, sw_flux,
                       lw_flux);
+}
+
+// Single-precision storage variant (-DSINGLE_PRECISION builds of the reference: jprb = real32,
+// utilities/parkind1.F90:45-49).  The _sp structs are layout-identical to the double ones (pointers
+// and 32-bit integers only), so the body is shared; the Stager widens / rounds on the device.
+int ssb200_radsurf_sp(const ssb200_config *config, const ssb200_canopy_properties_sp *cp,
+                      const ssb200_sw_spectral_properties_sp *sw, const ssb200_lw_spectral_properties_sp *lw,
+                      ssb200_boundary_conds_out_sp *bc, int32_t istartcol, int32_t iendcol, ssb200_canopy_flux_sp *sw_dir,
+                      ssb200_canopy_flux_sp *sw_diff, ssb200_canopy_flux_sp *lw_int, ssb200_canopy_flux_sp *lw_norm) {
+  static_assert(sizeof(ssb200_canopy_properties_sp) == sizeof(ssb200_canopy_properties) &&
+                    sizeof(ssb200_sw_spectral_properties_sp) == sizeof(ssb200_sw_spectral_properties) &&
+                    sizeof(ssb200_lw_spectral_properties_sp) == sizeof(ssb200_lw_spectral_properties) &&
+                    sizeof(ssb200_canopy_flux_sp) == sizeof(ssb200_canopy_flux) &&
+                    sizeof(ssb200_boundary_conds_out_sp) == sizeof(ssb200_boundary_conds_out),
+                "single-precision structs must mirror the double-precision ones");
+  return radsurf_host(config, reinterpret_cast<const ssb200_canopy_properties *>(cp),
+                      reinterpret_cast<const ssb200_sw_spectral_properties *>(sw),
+                      reinterpret_cast<const ssb200_lw_spectral_properties *>(lw), nullptr,
+                      reinterpret_cast<ssb200_boundary_conds_out *>(bc), istartcol, iendcol,
+                      reinterpret_cast<ssb200_canopy_flux *>(sw_dir), reinterpret_cast<ssb200_canopy_flux *>(sw_diff),
+                      reinterpret_cast<ssb200_canopy_flux *>(lw_int), reinterpret_cast<ssb200_canopy_flux *>(lw_norm), nullptr,
+                      nullptr, true);
 }
 
 int64_t ssb200_kernel_launch_count(void) { return (int64_t)g_launches; }

@@ -93,7 +93,13 @@ module radsurf_interface
   interface
     function ssb200_radsurf(config, canopy_props, sw_spectral_props, lw_spectral_props, bc_out, &
          &  istartcol, iendcol, sw_norm_dir, sw_norm_diff, lw_internal, lw_norm) &
+#ifdef SINGLE_PRECISION
+         ! jprb = real32: the arrays behind the c_ptr members hold float; the library widens them on the
+         ! device, solves in double precision and rounds the outputs (include/spartacus_b200.h)
+         &  bind(C, name='ssb200_radsurf_sp') result(status)
+#else
          &  bind(C, name='ssb200_radsurf') result(status)
+#endif
       import
       type(ssb200_config),                 intent(in) :: config
       type(ssb200_canopy_properties),      intent(in) :: canopy_props
@@ -142,10 +148,6 @@ contains
     type(c_ptr) :: p_sw, p_lw, p_f1, p_f2, p_f3, p_f4
     integer(c_int32_t) :: icol1, icol2
     integer(c_int) :: status
-
-#ifdef SINGLE_PRECISION
-    call radiation_abort('libspartacus_b200 is double precision only: build without -DSINGLE_PRECISION')
-#endif
 
     ! Column range: absent optionals select every column (reference :86-96).
     ! The reference driver's serial branch passes uninitialised values

@@ -92,3 +92,43 @@ def radsurf_fluxes(config, canopy_props, sw_spectral_props, lw_spectral_props, b
     if rc < 0:
         raise RadsurfError(f"ssb200_radsurf_fluxes failed (rc={rc}): {last_error()}")
     return rc
+
+
+def _real_members(*objs):
+    import numpy as np
+    for o in objs:
+        if o is None:
+            continue
+        for v in vars(o).values():
+            if isinstance(v, np.ndarray) and v.dtype.kind == "f":
+                yield v
+
+
+def to_single(obj):
+    """Copy of an API object with every float64 numpy member converted to float32 (what a
+    -DSINGLE_PRECISION build of the reference holds: jprb = real32, utilities/parkind1.F90:45-49)."""
+    import copy
+    import numpy as np
+    out = copy.copy(obj)
+    for k, v in vars(obj).items():
+        if isinstance(v, np.ndarray) and v.dtype == np.float64:
+            setattr(out, k, np.ascontiguousarray(v.astype(np.float32)))
+    return out
+
+
+def radsurf_sp(config, canopy_props, sw_spectral_props, lw_spectral_props, bc_out,
+               istartcol=None, iendcol=None, sw_norm_dir=None, sw_norm_diff=None,
+               lw_internal=None, lw_norm=None):
+    """radsurf for single-precision (float32) host arrays: ssb200_radsurf_sp.  The arrays cross PCIe
+    as float32, the solve runs in FP64 on the device, outputs are the FP64 results rounded to float32."""
+    import numpy as np
+    lib = load()
+    objs = (canopy_props, sw_spectral_props, lw_spectral_props, bc_out, sw_norm_dir, sw_norm_diff, lw_internal, lw_norm)
+    if not all(v.dtype == np.float32 for v in _real_members(*objs)):
+        raise RadsurfError("radsurf_sp: every real array member must be float32")
+    structs = marshal(config, canopy_props, sw_spectral_props, lw_spectral_props, bc_out,
+                      sw_norm_dir, sw_norm_diff, lw_internal, lw_norm)
+    rc = call_radsurf(lib.ssb200_radsurf_sp, structs, istartcol, iendcol)
+    if rc < 0:
+        raise RadsurfError(f"ssb200_radsurf_sp failed (rc={rc}): {last_error()}")
+    return rc

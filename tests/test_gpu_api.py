@@ -356,3 +356,52 @@ def test_radsurf_fluxes_equals_radsurf_scale_sum():
                 assert np.array_equal(a, b), (name, k, float(np.abs(a - b).max()))
     for k in golden_io.BC_FIELDS:
         assert np.array_equal(getattr(bc, k), getattr(bc2, k)), k
+
+
+def test_single_precision_storage_entry():
+    """ssb200_radsurf_sp (float32 arrays of a -DSINGLE_PRECISION build): the arrays
+    cross PCIe as float32, the solve runs in FP64, and every output is the FP64 result rounded to nearest
+    float32 - i.e. bit-equal to ssb200_radsurf on the widened inputs followed by a cast.  Checked on the
+    synthetic canopy (pipelined path: several blocks) and on the mixed-tile case (ragged layers, night
+    columns, several spectral intervals, untouched entries)."""
+    from mixed_case import mixed_config, make_mixed
+    from spartacus_surface_b200.radsurf_interface import radsurf_sp, to_single
+    from spartacus_surface_b200.radsurf_canopy_flux import ALL_FIELDS
+
+    def both(cfg, cp, sw, lw, nsw, nlw):
+        cp32, sw32, lw32 = to_single(cp), to_single(sw), to_single(lw)
+        widen = lambda o: type("W", (), {})
+        def wide(o):
+            import copy
+            w = copy.copy(o)
+            for k, v in vars(o).items():
+                if isinstance(v, np.ndarray) and v.dtype == np.float32:
+                    setattr(w, k, np.ascontiguousarray(v.astype(np.float64)))
+            return w
+        def outs(single):
+            bc = boundary_conds_out_type().allocate(cp.ncol, nsw, nlw)
+            fl = [canopy_flux_type().allocate(cfg, cp.ncol, cp.ntotlay, n, use_direct=d)
+                  for n, d in ((nsw, True), (nsw, True), (nlw, False), (nlw, False))]
+            for o in [bc] + fl:
+                for k, v in vars(o).items():
+                    if isinstance(v, np.ndarray) and v.dtype == np.float64:
+                        v[...] = 7.0
+            return (to_single(bc), [to_single(f) for f in fl]) if single else (bc, fl)
+        bc32, fl32 = outs(True)
+        assert radsurf_sp(cfg, cp32, sw32, lw32, bc32, None, None, *fl32) == 0
+        bc64, fl64 = outs(False)
+        assert radsurf(cfg, wide(cp32), wide(sw32), wide(lw32), bc64, None, None, *fl64) == 0
+        n = 0
+        for a, b in zip(fl32 + [bc32], fl64 + [bc64]):
+            for k, v in vars(a).items():
+                if isinstance(v, np.ndarray) and v.dtype == np.float32:
+                    assert np.array_equal(v, getattr(b, k).astype(np.float32)), k
+                    n += 1
+        assert n > 40
+
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, 70000, 4)
+    both(cfg, cp, sw, lw, 1, 1)
+    cfgm = mixed_config(2).consolidate()
+    cpm, swm, lwm = make_mixed(cfgm, ncol=400)
+    both(cfgm, cpm, swm, lwm, cfgm.nsw, cfgm.nlw)
