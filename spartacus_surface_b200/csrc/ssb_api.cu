@@ -43,10 +43,17 @@ __global__ void k_surface(ssb::SurfaceArgs s, int nsw_threads, int nlw_threads) 
 // sort keys of the columns of one launch chunk (column_segment_key)
 // (columns are ordered inside groups of `group` neighbours only: a warp then still touches
 // neighbouring lines of the per-column input and output arrays)
-__global__ void k_column_keys(ssb::ClassArgs a, unsigned long long *keys, int group) {
+// The key is packed into as few bits as it needs - `lbits` for the segment pattern (one bit per
+// layer; night-time columns get the largest value) below the group index - so that the radix sort
+// runs 3 passes instead of 8: at 131,072 columns per GPU (8-GPU sharding) the sort is latency, not
+// bandwidth.
+__global__ void k_column_keys(ssb::ClassArgs a, unsigned long long *keys, int group, int lbits) {
   const int ic = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ic < a.ncols)
-    keys[ic] = ((unsigned long long)(ic / group) << 32) | ssb::column_segment_key(a, a.cols[ic]);
+  if (ic >= a.ncols) return;
+  const unsigned long long all = (1ull << lbits) - 1ull;
+  const unsigned pattern = ssb::column_segment_key(a, a.cols[ic]);
+  const unsigned long long k = (pattern == 0xffffffffu) ? all : ((unsigned long long)pattern & (all >> 1));
+  keys[ic] = ((unsigned long long)(ic / group) << lbits) | k;
 }
 
 // ---------------------------------------------------------------------------
@@ -254,6 +261,10 @@ struct Context {
   // column-resident kernels (ssb_fused.cuh) where they exist (1 and 2 streams); 0: split path
   // sweeps of the register-resident path at 1 and 2 streams: 0 = interface-state sweeps
   // (ssb_fast_sweeps.cuh), 1 = record sweeps (ssb_fused.cuh MODE 1 / 2)
+  // shortwave and longwave pass of a call on two streams (separate scratch; no effect while profiling)
+  int concurrent_passes = 1;
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int sweep_mode = 0;  // measured on B200: the record sweeps move fewer bytes and are 6 % slower
   // level-major staging of the per-layer arrays of a chunk (ssb_stage.cuh)
   int stage_layers = 1;
@@ -270,10 +281,41 @@ Context g_ctx;
 struct CudaBackend {
   Context &cx;
   int lane;
+  int pass_lane;            // scratch / perm / sort buffers of the pass being dispatched
+  cudaStream_t main_stream; // the stream of the call; the longwave pass may run on cx.aux_stream
+  bool forked = false;
   size_t budget;
   bool layer_was_fast = false;  // the chunk's layer kernels were the register-resident ones
   explicit CudaBackend(Context &c, int lane_ = 0, size_t budget_ = 0)
-      : cx(c), lane(lane_), budget(budget_ ? budget_ : c.budget_doubles) {}
+      : cx(c), lane(lane_), pass_lane(lane_), main_stream(c.stream), budget(budget_ ? budget_ : c.budget_doubles) {}
+  // Shortwave pass on the stream of the call, longwave pass on an auxiliary stream with its own
+  // scratch (lane 2): the tails of one pass's launches are filled by the other's blocks, and the
+  // memory-bound sweeps of one overlap the FP64-bound layer kernels of the other.
+  void fork_passes() {
+    if (!cx.concurrent_passes || cx.profiling || cx.first_error != cudaSuccess) return;
+    if (!cx.aux_stream && cudaStreamCreateWithFlags(&cx.aux_stream, cudaStreamNonBlocking) != cudaSuccess) return;
+    if (!cx.ev_fork) {
+      if (cudaEventCreateWithFlags(&cx.ev_fork, cudaEventDisableTiming) != cudaSuccess) return;
+      if (cudaEventCreateWithFlags(&cx.ev_join, cudaEventDisableTiming) != cudaSuccess) return;
+    }
+    cudaEventRecord(cx.ev_fork, main_stream);
+    cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0);
+    forked = true;
+  }
+  void begin_pass(bool lw) {
+    if (!forked) return;
+    cx.stream = lw ? cx.aux_stream : main_stream;
+    pass_lane = lw ? 2 : lane;
+  }
+  void end_passes() {
+    if (forked) {
+      cudaEventRecord(cx.ev_join, cx.aux_stream);
+      cudaStreamWaitEvent(main_stream, cx.ev_join, 0);
+      forked = false;
+    }
+    cx.stream = main_stream;
+    pass_lane = lane;
+  }
   const int *dev_cols(const ssb::Plan &, size_t off) { return (const int *)cx.d_cols.p + off; }
   // columns of the chunk ordered by their segment pattern (device radix sort, stable)
   // (always for the column-resident kernels: a thread walks the layers of its column, so the
@@ -288,17 +330,22 @@ struct CudaBackend {
     cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const Key *)nullptr, (Key *)nullptr, (const int *)nullptr,
                                     (int *)nullptr, (int)n, 0, 64, cx.stream);
     temp_bytes = (temp_bytes + 255) & ~(size_t)255;
-    if (cx.d_sort[lane].reserve(temp_bytes + pad * (2 * sizeof(Key) + sizeof(int))) != cudaSuccess) {
+    if (cx.d_sort[pass_lane].reserve(temp_bytes + pad * (2 * sizeof(Key) + sizeof(int))) != cudaSuccess) {
       cudaGetLastError();
       return a.cols;
     }
-    char *base = (char *)cx.d_sort[lane].p;
+    char *base = (char *)cx.d_sort[pass_lane].p;
     Key *keys = (Key *)(base + temp_bytes), *keys_out = keys + pad;
     int *cols_out = (int *)(keys_out + pad);
     const int group = a.fused ? (cx.fused_sort_group > 0 ? cx.fused_sort_group : 0x7fffffff)
                               : (cx.sort_group > 0 ? cx.sort_group : 0x7fffffff);
-    k_column_keys<<<(unsigned)((n + 127) / 128), 128, 0, cx.stream>>>(a, keys, group);
-    cub::DeviceRadixSort::SortPairs(base, temp_bytes, keys, keys_out, a.cols, cols_out, (int)n, 0, 64, cx.stream);
+    const int lbits = (a.lmax < 31 ? a.lmax : 31) + 1;
+    int gbits = 0;
+    for (size_t ngroups = (n + (size_t)group - 1) / (size_t)group; ((size_t)1 << gbits) < ngroups; ++gbits) {
+    }
+    k_column_keys<<<(unsigned)((n + 127) / 128), 128, 0, cx.stream>>>(a, keys, group, lbits);
+    cub::DeviceRadixSort::SortPairs(base, temp_bytes, keys, keys_out, a.cols, cols_out, (int)n, 0, lbits + gbits,
+                                    cx.stream);
     g_launches += 2;
     check_launch();
     return cols_out;
@@ -309,9 +356,9 @@ struct CudaBackend {
   int *dev_status() { return (int *)cx.d_status.p; }
   size_t scratch_budget_doubles() { return budget; }
   double *scratch(size_t n) {
-    cudaError_t e = cx.d_scratch[lane].reserve(n * sizeof(double));
+    cudaError_t e = cx.d_scratch[pass_lane].reserve(n * sizeof(double));
     if (e != cudaSuccess && cx.first_error == cudaSuccess) cx.first_error = e;
-    return (double *)cx.d_scratch[lane].p;
+    return (double *)cx.d_scratch[pass_lane].p;
   }
   void tick(int family, bool start) {
     if (!cx.profiling) return;
@@ -346,8 +393,8 @@ struct CudaBackend {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(0, true);
       ssb::ClassArgs b = a;
-      if (cx.partition && cx.d_perm[lane].reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
-        b.perm_count = (int *)cx.d_perm[lane].p;
+      if (cx.partition && cx.d_perm[pass_lane].reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
+        b.perm_count = (int *)cx.d_perm[pass_lane].p;
         b.perm = b.perm_count + 4;
       }
       const bool done = ssb::fast_layer_sw<NS>(b, nt, cx.stream);
@@ -368,8 +415,8 @@ struct CudaBackend {
     if (cx.fast_mode && nt > 0 && cx.first_error == cudaSuccess) {
       tick(2, true);
       ssb::ClassArgs b = a;
-      if (cx.partition && cx.d_perm[lane].reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
-        b.perm_count = (int *)cx.d_perm[lane].p;
+      if (cx.partition && cx.d_perm[pass_lane].reserve(sizeof(int) * (3 * (size_t)nt + 4)) == cudaSuccess) {
+        b.perm_count = (int *)cx.d_perm[pass_lane].p;
         b.perm = b.perm_count + 4;
       }
       const bool done = ssb::fast_layer_lw<NS>(b, nt, cx.stream);
@@ -575,7 +622,8 @@ int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, i
   if (cx.budget_doubles == 0) {
     size_t free_b = 0, total_b = 0;
     SSB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t b = (free_b + cx.d_scratch[0].bytes + cx.d_scratch[1].bytes + cx.d_scratch[2].bytes) / 2;
+    // per scratch lane (two lanes are live when the SW and LW passes run concurrently)
+    size_t b = (free_b + cx.d_scratch[0].bytes + cx.d_scratch[1].bytes + cx.d_scratch[2].bytes) / 4;
     const size_t cap = (size_t)24 << 30;
     if (b > cap) b = cap;
     cx.budget_doubles = b / sizeof(double);
@@ -1155,7 +1203,10 @@ static int radsurf_host(const ssb200_config *config, const ssb200_canopy_propert
   const size_t total_work = lN + cN;
   int nblk = 1;
   if (cx.pipeline && contiguous && !cx.profiling && total_work >= ((size_t)1 << 17)) {
-    nblk = (int)(total_work >> 16);
+    // blocks of at least ~30 k columns x 16 layers: smaller launches are bound by launch latency (a rank
+    // of an 8-GPU run holds 131,072 columns: 4 blocks, not 16)
+    nblk = (int)(total_work >> 19);
+    if (nblk < 2) nblk = 2;
     if (nblk > cx.pipeline_max_blocks) nblk = cx.pipeline_max_blocks;
   }
   // three stages on three streams, chained per block by events: uploads in block order on
@@ -1326,6 +1377,10 @@ int ssb200_set_option(const char *name, int64_t value) {
   }
   if (n == "pipeline_max_blocks") {
     g_ctx.pipeline_max_blocks = value < 1 ? 1 : (int)value;
+    return 0;
+  }
+  if (n == "concurrent_passes") {
+    g_ctx.concurrent_passes = value != 0;
     return 0;
   }
   if (n == "stage_layers") {

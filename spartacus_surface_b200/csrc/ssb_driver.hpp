@@ -239,6 +239,7 @@ struct CallArgs {
 //   void fused_run(const ClassArgs&, bool lw, long width)
 //   bool records_shape(const SolveCfg&, bool lw, int *op_elems)   record sweeps available and enabled
 //   void records_run(const ClassArgs&, bool lw, long width)
+//   void fork_passes(), begin_pass(bool lw), end_passes()   optional concurrency of the SW and LW passes
 //   bool stage_supported(const SolveCfg&)            level-major staging of per-layer arrays enabled for this class
 //   void stage(const StageArgs&, bool scatter, bool lw)   gather (inputs -> staging) / scatter (staging -> outputs)
 template <class Backend>
@@ -356,10 +357,14 @@ struct Dispatcher {
   int run(const CallArgs &ca, const Plan &plan, std::string &err) {
     const ssb200_config &cfg = *ca.config;
     size_t col_offset = 0;
+    // the shortwave and the longwave pass of a class are independent (disjoint outputs, read-only
+    // inputs): the backend may run them on two streams with separate scratch (begin_pass / end_passes)
+    be.fork_passes();
     for (const ColumnClass &k : plan.classes) {
       for (int pass = 0; pass < 2; ++pass) {
         const bool lw = (pass == 1);
         if (lw ? !cfg.do_lw : !cfg.do_sw) continue;
+        be.begin_pass(lw);
         const ssb200_legendre_gauss &lgs =
             lw ? (k.urban ? cfg.lg_lw_urban : cfg.lg_lw_forest) : (k.urban ? cfg.lg_sw_urban : cfg.lg_sw_forest);
         const int cap = stream_capacity(lgs.nstream);
@@ -404,6 +409,7 @@ struct Dispatcher {
       }
       col_offset += k.cols.size();
     }
+    be.end_passes();
     const size_t s_lo = (size_t)(std::lower_bound(plan.surface_cols.begin(), plan.surface_cols.end(), col_lo) -
                                  plan.surface_cols.begin());
     const size_t s_hi = (size_t)(std::lower_bound(plan.surface_cols.begin(), plan.surface_cols.end(), col_hi) -

@@ -23,6 +23,9 @@ namespace ssb {
   } while (0)
 
 constexpr int kFastBlock = 128;  // sweeps: one thread per (column, interval)
+#ifndef SSB_SWEEP_MINB
+#define SSB_SWEEP_MINB 2  // resident blocks per SM the sweeps are compiled for (3: 168 registers, 1-1.8 KB of spills: 51.7 -> 68.4 ms)
+#endif
 // layer kernels: block size and the resident threads per SM that the register budget is
 // set for (__launch_bounds__).  Measured on B200: aligning the warps of a block with
 // barriers at phase boundaries (one 384-thread block per SM) does not pay.
@@ -119,7 +122,7 @@ bool SSB_CAT(fast_layer_sw_ns, SSB_NS)(const ClassArgs &a, long nt, cudaStream_t
   }
 }
 template <int NREG, int NS, bool URBAN>
-__global__ void __launch_bounds__(kFastBlock, 2) k_fast_sweeps_sw(ClassArgs a, long nt) {
+__global__ void __launch_bounds__(kFastBlock, SSB_SWEEP_MINB) k_fast_sweeps_sw(ClassArgs a, long nt) {
   extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
@@ -186,7 +189,7 @@ bool SSB_CAT(fast_layer_lw_ns, SSB_NS)(const ClassArgs &a, long nt, cudaStream_t
   }
 }
 template <int NREG, int NS, bool URBAN>
-__global__ void __launch_bounds__(kFastBlock, 2) k_fast_sweeps_lw(ClassArgs a, long nt) {
+__global__ void __launch_bounds__(kFastBlock, SSB_SWEEP_MINB) k_fast_sweeps_lw(ClassArgs a, long nt) {
   extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;

@@ -79,6 +79,9 @@ struct HostBackend {
     if (a.cfg.ns == 1) fused_run_ns<1>(a, lw, width);
     else fused_run_ns<2>(a, lw, width);
   }
+  void fork_passes() {}
+  void begin_pass(bool) {}
+  void end_passes() {}
   // level-major staging of the per-layer arrays (ssb_stage.cuh), with the register-resident bodies
   bool stage_layers = true;
   bool stage_supported(const ssb::SolveCfg &c) { return fast && stage_layers && c.ns <= 4; }
