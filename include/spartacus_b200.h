@@ -327,17 +327,22 @@ int ssb200_last_kernel_times_ms(double out[5]);
 /* Launches per kernel family in that call (same order). */
 int ssb200_last_kernel_counts(int64_t out[5]);
 
-/* Tuning knobs: "scratch_budget_bytes" (device scratch per launch chunk;
- * 0 = automatic: half of the free memory, at most 24 GiB) and "fast_kernels"
- * (1 = use the register-resident kernels where a configuration has them, 0 = generic
- * one-thread-per-problem kernels everywhere; results agree to rounding),
- * "partition_layers" (1 = group layer problems by solved sub-block so that the
- * register-resident layer kernels run; 0 = generic layer kernels),
- * "pipeline" (1 = ssb200_radsurf uploads, solves and downloads blocks of columns as
- * three overlapping stages; effective with pinned host memory), "pipeline_max_blocks"
- * (default 16), "sort_columns" (default 0; 1 = the register-resident kernels process the columns
- * of a launch ordered by their segment pattern inside groups of "sort_group" neighbours, so
- * that warps are uniform; results do not depend on it). */
+/* Tuning knobs (results never depend on them beyond rounding; defaults in brackets):
+ *   "scratch_budget_bytes"  device scratch per launch chunk and scratch lane [0 = automatic: a quarter
+ *                           of the free memory, at most 24 GiB]
+ *   "fast_kernels"          [1] register-resident kernels where a configuration has them (1-4 streams);
+ *                           0 = the generic one-thread-per-problem kernels everywhere (TEST-ONLY: they are the
+ *                           correctness path of 8 streams, not a tuned one)
+ *   "partition_layers"      [1] group layer problems by solved sub-block (needed by the fast layer kernels)
+ *   "stage_layers"          [1] level-major staging of the per-layer arrays of a chunk (gather / scatter)
+ *   "sort_columns"          [1] process the columns of a launch ordered by their segment pattern inside groups
+ *   "sort_group"            [4096] of this many neighbours (0 = the whole chunk)
+ *   "concurrent_passes"     [1] shortwave and longwave pass on two streams with separate scratch
+ *   "pipeline"              [1] host entries upload, solve and download blocks of columns as three
+ *   "pipeline_max_blocks"   [16] overlapping stages (effective with pinned host memory)
+ *   "record_sweeps"         [0] measured alternative: operator-record sweeps (1 and 2 streams)
+ *   "fused_kernels"         [0] measured alternative: column-resident kernels (1 and 2 streams), with
+ *                           "fused_sort", "fused_sort_group", "fused_blocks_per_sm", "fused_sync", "fused_l2_persist" */
 int ssb200_set_option(const char *name, int64_t value);
 
 /* Release cached plans, scratch and pinned staging buffers. */

@@ -25,9 +25,9 @@ namespace ssb {
 //   * Gamma0 diag(frac) is symmetric: Y0 = diag(1/sqrt f) Gamma0 diag(sqrt f), G0 = diag(sqrt f) U0.
 // Every output of calc_matrices_* is invariant to the scaling and order of the eigenvectors
 // (SURVEY App. A.3), so this replaces the reference's nonsymmetric QR solver
-// (radtool_eigen_decomposition.F90:51-828) without changing what is computed.  The QR scheme
-// (ssb_math.cuh: eigen_real) remains for the HOST check only, where it pins the generic bodies
-// bit for bit against the oracle; no device code path reaches it.
+// (radtool_eigen_decomposition.F90:51-828) without changing what is computed.  The QR scheme lives in
+// the test tree (tests/hostcheck/asymtx_qr.hpp, compiled with SSB_HOSTCHECK_QR into the host check only),
+// where it pins the generic bodies bit for bit against the oracle; the library does not contain it.
 // ---------------------------------------------------------------------------
 #if !defined(__CUDA_ARCH__)
 inline bool &host_generic_jacobi() {
@@ -178,12 +178,14 @@ SSB_HD inline int diffuse_part(int n, double dz, const double *g1, const double 
   }
   double ev[NC];
   int nerr;
-  if (generic_uses_jacobi()) {
-    nerr = eigen_sym_ds(n, gdiff, w.b3, w.ninv, ev, V, w.b4, w.b5, w.b6);
-  } else {
+#if defined(SSB_HOSTCHECK_QR)  // host check only (tests/hostcheck/asymtx_qr.hpp)
+  if (!generic_uses_jacobi()) {
     mat_mul(n, n, n, gdiff, w.b3, P);
     nerr = eigen_real(n, P, ev, V, w.wk);
-  }
+  } else
+#endif
+    nerr = eigen_sym_ds(n, gdiff, w.b3, w.ninv, ev, V, w.b4, w.b5, w.b6);
+  (void)P;
   for (int i = 0; i < n; ++i) {
     w.lam[i] = sqrt(dmax(0.0, ev[i]));
     w.elz[i] = exp(-w.lam[i] * dz);
@@ -237,10 +239,13 @@ SSB_HD inline int calc_matrices_sw(int n, int d, double dz, const double *g0, co
   // Section 3 (:225-229): E = G0 diag(exp(eps dz)) G0^-1
   double g0c[9], G0[9], G0i[9], eps[3], e0[3], t9[9], wk0[7];
   for (int i = 0; i < d * d; ++i) g0c[i] = g0[i];
-  if (generic_uses_jacobi())
-    nerr += eigen_sym_g0(d, g0c, w.frac, eps, G0);
-  else
+#if defined(SSB_HOSTCHECK_QR)
+  if (!generic_uses_jacobi())
     nerr += eigen_real(d, g0c, eps, G0, wk0);
+  else
+#endif
+    nerr += eigen_sym_g0(d, g0c, w.frac, eps, G0);
+  (void)wk0;
   for (int i = 0; i < d * d; ++i) t9[i] = G0[i];
   invert(d, t9, G0i);
   for (int i = 0; i < d; ++i) e0[i] = exp(eps[i] * dz);

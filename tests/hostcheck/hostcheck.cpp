@@ -6,6 +6,8 @@
 // package loads it, and the library itself has no CPU fallback.
 #include <vector>
 
+#define SSB_HOSTCHECK_QR 1
+#include "asymtx_qr.hpp"
 #include "../../spartacus_surface_b200/csrc/ssb_driver.hpp"
 #include "../../spartacus_surface_b200/csrc/ssb_fast_layer.cuh"
 #include "../../spartacus_surface_b200/csrc/ssb_fast_sweeps.cuh"

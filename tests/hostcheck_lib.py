@@ -16,7 +16,8 @@ _lib = None
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp"))]
+    deps = [SRC, os.path.join(os.path.dirname(SRC), "asymtx_qr.hpp")]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp"))]
     deps.append(os.path.join(ROOT, "include", "spartacus_b200.h"))
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return
