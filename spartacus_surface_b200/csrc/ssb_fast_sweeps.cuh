@@ -21,6 +21,7 @@
 //    the register file.
 #pragma once
 #include "ssb_fast_layer.cuh"
+#include "ssb_sweep_blocks.cuh"
 
 namespace ssb {
 
@@ -314,6 +315,8 @@ struct SwSweepLayout {
   static constexpr int oAa = 0, oDa = n * n, oLU = oDa + n * d;  // interface scratch of the fast path
   static constexpr int NRB = URBAN ? NREG + 1 : NREG, m = NRB * NS;
   static constexpr int state_doubles = n * n + n * d;
+  // block of a layer that solves only its vegetated regions (segment 2)
+  static constexpr int vegNA = NREG > 1 ? n - NS : n, vegI0 = NREG > 1 ? NS : 0;
 };
 
 template <int NREG, int NS, bool URBAN>
@@ -378,47 +381,16 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, 0, st(i));
   for (int jl = 0; jl < nlay; ++jl) {
     const int il = il1 + jl * ls;
-    const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
-    double X[n * n], Wd[n * d];
-    {
-      double LU[n * n];
-      // Wd <- d_above E, then adding_core adds a_above Sdn and applies D^-1
-      SSB_UNROLL
-      for (int j = 0; j < d; ++j) {
-        SSB_UNROLL
-        for (int i = 0; i < n; ++i) Wd[i + n * j] = 0.0;
-        SSB_UNROLL
-        for (int k = 0; k < d; ++k) {
-          const double e = L.ldp(Lay::oE + k + d * j, jl, sk.k[seg_class<2, NS>(k, j)]);
-          SSB_UNROLL
-          for (int i = 0; i < n; ++i) Wd[i + n * j] = fma(st(Lay::oDa + i + n * k), e, Wd[i + n * j]);
-        }
-      }
-      adding_core<n, d, NS, 1>(st, L, W, jl, Lay::oR, Lay::oT, Lay::oSdn, Lay::oLU, LU, X, Wd, sk);
-    }
-    // [a_below | d_below] (street part) = [R | Sup] + T [X | Wd]
+    // the adding step on the block of regions the layer solves (ssb_sweep_blocks.cuh); with the columns
+    // of the launch ordered by segment pattern the switch is uniform per warp
+    const int seg = (int)L.ld(Lay::oGeo + 7, jl);
     double Ab[n * n], Db[n * d];
-    SSB_UNROLL
-    for (int j = 0; j < n; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) Ab[i + n * j] = L.ldp(Lay::oR + i + n * j, jl, sk.k[seg_class<0, NS>(i, j)]);
-    }
-    SSB_UNROLL
-    for (int j = 0; j < d; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) Db[i + n * j] = L.ldp(Lay::oSup + i + n * j, jl, sk.k[seg_class<1, NS>(i, j)]);
-    }
-    SSB_UNROLL
-    for (int k = 0; k < n; ++k) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        const double t = L.ldp(Lay::oT + i + n * k, jl, sk.k[seg_class<0, NS>(i, k)]);
-        SSB_UNROLL
-        for (int j = 0; j < n; ++j) Ab[i + n * j] = fma(t, X[k + n * j], Ab[i + n * j]);
-        SSB_UNROLL
-        for (int j = 0; j < d; ++j) Db[i + n * j] = fma(t, Wd[k + n * j], Db[i + n * j]);
-      }
-    }
+    if (NREG == 1 || seg == 0)
+      sw_up_block<Lay, NREG, NS, n, 0>(st, L, W, jl, Ab, Db);
+    else if (seg == 1)
+      sw_up_block<Lay, NREG, NS, NS, 0>(st, L, W, jl, Ab, Db);
+    else
+      sw_up_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0>(st, L, W, jl, Ab, Db);
     double rb[NS], rd[NS];
     SSB_UNROLL
     for (int js = 0; js < NS; ++js) rb[js] = rd[js] = 0.0;
@@ -499,7 +471,7 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   double flux_dn_dir_clear = 1.0 / zcos;
   for (int jl = nlay - 1; jl >= 0; --jl) {
     const int il = il1 + jl * ls;
-    const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
+    const int seg = (int)L.ld(Lay::oGeo + 7, jl);
     double f_wall[3], od_scaling[3];
     SSB_UNROLL
     for (int r = 0; r < 3; ++r) {
@@ -525,57 +497,19 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
         dir_below[lo] = s;
       }
     }
-    // y = T x (+ Sdn dirb) ; dir_above = E dirb ; refl = d_above dir_above
-    double y_d[n], y_f[n], refl[n], ddir[d];
+    // the step on the block of regions the layer solves (ssb_sweep_blocks.cuh)
+    double refl[n], ddir[d], ub_d[m], ub_f[m], if_d[n], if_f[n], idir[d];
+    if (NREG == 1 || seg == 0)
+      sw_down_block<Lay, NREG, NS, n, 0>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above, ddir, refl, ub_d, ub_f,
+                                         ua_d, ua_f, if_d, if_f, idir);
+    else if (seg == 1)
+      sw_down_block<Lay, NREG, NS, NS, 0>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above, ddir, refl, ub_d, ub_f,
+                                          ua_d, ua_f, if_d, if_f, idir);
+    else
+      sw_down_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above, ddir,
+                                                          refl, ub_d, ub_f, ua_d, ua_f, if_d, if_f, idir);
     SSB_UNROLL
-    for (int i = 0; i < n; ++i) y_d[i] = y_f[i] = refl[i] = 0.0;
-    smv2<n, n, 0, NS>(L, Lay::oT, jl, xb_d, xb_f, y_d, y_f, sk);
-    smv1<n, d, 1, NS>(L, Lay::oSdn, jl, dir_below, y_d, sk);
-    {
-      double da_new[d];
-      SSB_UNROLL
-      for (int i = 0; i < d; ++i) da_new[i] = 0.0;
-      smv1<d, d, 2, NS>(L, Lay::oE, jl, dir_below, da_new, sk);
-      SSB_UNROLL
-      for (int i = 0; i < d; ++i) {
-        ddir[i] = dir_below[i] - da_new[i];
-        dir_above[i] = da_new[i];
-      }
-    }
-    smv1<n, d>(W, Lay::oDa, jl, dir_above, refl);
-    // z1 = D^-1 (a_above y + refl) ; z2 = D^-1 (y + R refl) ; ub = R x (street part of up_below)
-    double z1_d[n], z1_f[n], z2_d[n], z2_f[n], ub_d[m], ub_f[m];
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      z1_d[i] = refl[i];
-      z1_f[i] = 0.0;
-      z2_d[i] = y_d[i];
-      z2_f[i] = y_f[i];
-    }
-    SSB_UNROLL
-    for (int i = 0; i < m; ++i) ub_d[i] = ub_f[i] = 0.0;
-    smv2<n, n>(W, Lay::oAa, jl, y_d, y_f, z1_d, z1_f);
-    SSB_UNROLL
-    for (int j = 0; j < n; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        const double r = L.ldp(Lay::oR + i + n * j, jl, sk.k[seg_class<0, NS>(i, j)]);
-        z2_d[i] = fma(r, refl[j], z2_d[i]);
-        ub_d[i] = fma(r, xb_d[j], ub_d[i]);
-        ub_f[i] = fma(r, xb_f[j], ub_f[i]);
-      }
-    }
-    {
-      double LU[n * n];
-      SSB_UNROLL
-      for (int i = 0; i < n * n; ++i) LU[i] = W.ld(Lay::oLU + i, jl);
-      sm_lu_solve_left<n, 1>(LU, z1_d);
-      sm_lu_solve_left<n, 1>(LU, z1_f);
-      sm_lu_solve_left<n, 1>(LU, z2_d);
-      sm_lu_solve_left<n, 1>(LU, z2_f);
-    }
-    smv2<n, n, 0, NS>(L, Lay::oT, jl, z1_d, z1_f, ub_d, ub_f, sk);
-    smv1<n, d, 1, NS>(L, Lay::oSup, jl, dir_below, ub_d, sk);
+    for (int i = n; i < m; ++i) ub_d[i] = ub_f[i] = 0.0;
     if (URBAN) {
       const double ralb = SSB_LAY(a.sw.roof_albedo, g, il);
       const double ralb_dir = a.sw.roof_albedo_dir ? SSB_LAY(a.sw.roof_albedo_dir, g, il) : ralb;
@@ -598,15 +532,6 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
       SSB_FL(fdif, roof_in, il) = sroof_f;
       SSB_FL(fdif, roof_net, il) = sroof_f - rup_f;
     }
-    // fluxes just above the base: x_above = z2 ; up_above = a_above z2 + refl
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      xa_d[i] = z2_d[i];
-      xa_f[i] = z2_f[i];
-      ua_d[i] = refl[i];
-      ua_f[i] = 0.0;
-    }
-    smv2<n, n>(W, Lay::oAa, jl, xa_d, xa_f, ua_d, ua_f);
     if (fdir.flux_dn_layer_top || fdif.flux_dn_layer_top) {
       double s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sdb = 0.0, sda = 0.0;
       SSB_UNROLL
@@ -639,22 +564,6 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
         SSB_FL(fdif, flux_up_layer_top, il) = s[6];
         SSB_FL(fdif, flux_up_layer_base, il) = s[7];
       }
-    }
-    // integrated fluxes across the layer
-    double if_d[n], if_f[n], idir[d];
-    {
-      double cv_d[n], cv_f[n];
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        cv_d[i] = xb_d[i] - xa_d[i] - ub_d[i] + ua_d[i];
-        cv_f[i] = xb_f[i] - xa_f[i] - ub_f[i] + ua_f[i];
-        if_d[i] = if_f[i] = 0.0;
-      }
-      SSB_UNROLL
-      for (int i = 0; i < d; ++i) idir[i] = 0.0;
-      smv2<n, n, 0, NS>(L, Lay::oIdiff, jl, cv_d, cv_f, if_d, if_f, sk);
-      smv1<d, d, 2, NS>(L, Lay::oIdir, jl, ddir, idir, sk);
-      smv1<n, d, 1, NS>(L, Lay::oIdd, jl, ddir, if_d, sk);
     }
     double smu_d[NREG], smu_f[NREG], stan_d[NREG], stan_f[NREG];
     SSB_UNROLL
@@ -774,6 +683,7 @@ struct LwSweepLayout {
   static constexpr int oAa = 0, oSa = n * n, oLU = oSa + n;
   static constexpr int NRB = URBAN ? NREG + 1 : NREG, m = NRB * NS;
   static constexpr int state_doubles = n * n + n;
+  static constexpr int vegNA = NREG > 1 ? n - NS : n, vegI0 = NREG > 1 ? NS : 0;
 };
 
 template <int NREG, int NS, bool URBAN>
@@ -824,33 +734,14 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, 0, st(i));
   for (int jl = 0; jl < nlay; ++jl) {
     const int il = il1 + jl * ls;
-    const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
-    double X[n * n], v1[n];
-    {
-      double LU[n * n];
-      // v1 <- source_above, then adding_core adds a_above src and applies D^-1
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) v1[i] = st(Lay::oSa + i);
-      adding_core<n, 1, NS, 3>(st, L, W, jl, Lay::oR, Lay::oT, Lay::oSrc, Lay::oLU, LU, X, v1, sk);
-    }
+    const int seg = (int)L.ld(Lay::oGeo + 7, jl);
     double Ab[n * n], Sb[n];
-    SSB_UNROLL
-    for (int j = 0; j < n; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) Ab[i + n * j] = L.ldp(Lay::oR + i + n * j, jl, sk.k[seg_class<0, NS>(i, j)]);
-    }
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) Sb[i] = L.ldp(Lay::oSrc + i, jl, sk.k[seg_class<3, NS>(i, 0)]);
-    SSB_UNROLL
-    for (int k = 0; k < n; ++k) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        const double t = L.ldp(Lay::oT + i + n * k, jl, sk.k[seg_class<0, NS>(i, k)]);
-        SSB_UNROLL
-        for (int j = 0; j < n; ++j) Ab[i + n * j] = fma(t, X[k + n * j], Ab[i + n * j]);
-        Sb[i] = fma(t, v1[k], Sb[i]);
-      }
-    }
+    if (NREG == 1 || seg == 0)
+      lw_up_block<Lay, NREG, NS, n, 0>(st, L, W, jl, Ab, Sb);
+    else if (seg == 1)
+      lw_up_block<Lay, NREG, NS, NS, 0>(st, L, W, jl, Ab, Sb);
+    else
+      lw_up_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0>(st, L, W, jl, Ab, Sb);
     double rb[NS], rs[NS];
     SSB_UNROLL
     for (int js = 0; js < NS; ++js) rb[js] = rs[js] = 0.0;
@@ -909,7 +800,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   SSB_FC(fnorm, top_net) = top_emissivity;
   for (int jl = nlay - 1; jl >= 0; --jl) {
     const int il = il1 + jl * ls;
-    const SegKeep sk = seg_keep((int)L.ld(Lay::oGeo + 7, jl));
+    const int seg = (int)L.ld(Lay::oGeo + 7, jl);
     double f_wall[3], od_scaling[3];
     SSB_UNROLL
     for (int r = 0; r < 3; ++r) {
@@ -925,53 +816,16 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       expand_down<NREG, NRB, NS>(V, xa_i, xb_i);
       expand_down<NREG, NRB, NS>(V, xa_f, xb_f);
     }
-    double src[n], sa[n];
+    double ub_i[m], ub_f[m], if_i[n], if_f[n];
+    if (NREG == 1 || seg == 0)
+      lw_down_block<Lay, NREG, NS, n, 0>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f, if_i, if_f);
+    else if (seg == 1)
+      lw_down_block<Lay, NREG, NS, NS, 0>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f, if_i, if_f);
+    else
+      lw_down_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f, if_i,
+                                                          if_f);
     SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      src[i] = L.ldp(Lay::oSrc + i, jl, sk.k[seg_class<3, NS>(i, 0)]);
-      sa[i] = W.ld(Lay::oSa + i, jl);
-    }
-    // y = T x (+ src) ; z1 = D^-1 (a_above y + sa) ; z2 = D^-1 (y + R sa) ; ub = R x + src
-    double y_i[n], y_f[n];
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      y_i[i] = src[i];
-      y_f[i] = 0.0;
-    }
-    smv2<n, n, 0, NS>(L, Lay::oT, jl, xb_i, xb_f, y_i, y_f, sk);
-    double z1_i[n], z1_f[n], z2_i[n], z2_f[n], ub_i[m], ub_f[m];
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      z1_i[i] = sa[i];
-      z1_f[i] = 0.0;
-      z2_i[i] = y_i[i];
-      z2_f[i] = y_f[i];
-    }
-    SSB_UNROLL
-    for (int i = 0; i < m; ++i) ub_i[i] = ub_f[i] = 0.0;
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) ub_i[i] = src[i];
-    smv2<n, n>(W, Lay::oAa, jl, y_i, y_f, z1_i, z1_f);
-    SSB_UNROLL
-    for (int j = 0; j < n; ++j) {
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        const double r = L.ldp(Lay::oR + i + n * j, jl, sk.k[seg_class<0, NS>(i, j)]);
-        z2_i[i] = fma(r, sa[j], z2_i[i]);
-        ub_i[i] = fma(r, xb_i[j], ub_i[i]);
-        ub_f[i] = fma(r, xb_f[j], ub_f[i]);
-      }
-    }
-    {
-      double LU[n * n];
-      SSB_UNROLL
-      for (int i = 0; i < n * n; ++i) LU[i] = W.ld(Lay::oLU + i, jl);
-      sm_lu_solve_left<n, 1>(LU, z1_i);
-      sm_lu_solve_left<n, 1>(LU, z1_f);
-      sm_lu_solve_left<n, 1>(LU, z2_i);
-      sm_lu_solve_left<n, 1>(LU, z2_f);
-    }
-    smv2<n, n, 0, NS>(L, Lay::oT, jl, z1_i, z1_f, ub_i, ub_f, sk);
+    for (int i = n; i < m; ++i) ub_i[i] = ub_f[i] = 0.0;
     if (URBAN) {
       const double bfj = a.cp.building_fraction[il];
       const double exposed = (jl < nlay - 1) ? dmax(0.0, bfj - a.cp.building_fraction[il + ls]) : bfj;
@@ -994,14 +848,6 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
       SSB_FL(fnorm, roof_in, il) = sroof_f;
       SSB_FL(fnorm, roof_net, il) = sroof_f - rup_f;
     }
-    SSB_UNROLL
-    for (int i = 0; i < n; ++i) {
-      xa_i[i] = z2_i[i];
-      xa_f[i] = z2_f[i];
-      ua_i[i] = sa[i];
-      ua_f[i] = 0.0;
-    }
-    smv2<n, n>(W, Lay::oAa, jl, xa_i, xa_f, ua_i, ua_f);
     if (fint.flux_dn_layer_top || fnorm.flux_dn_layer_top) {
       double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       SSB_UNROLL
@@ -1028,20 +874,9 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
         SSB_FL(fnorm, flux_up_layer_base, il) = s[7];
       }
     }
-    double if_i[n], if_f[n], book[3 * d + 1];
-    {
-      double tv_i[n], tv_f[n];
-      SSB_UNROLL
-      for (int i = 0; i < n; ++i) {
-        tv_i[i] = xb_i[i] + ua_i[i];
-        tv_f[i] = xb_f[i] + ua_f[i];
-        if_i[i] = L.ldp(Lay::oIsrc + i, jl, sk.k[seg_class<3, NS>(i, 0)]);
-        if_f[i] = 0.0;
-      }
-      smv2<n, n, 0, NS>(L, Lay::oIF, jl, tv_i, tv_f, if_i, if_f, sk);
-      SSB_UNROLL
-      for (int i = 0; i < 3 * d + 1; ++i) book[i] = L.ld(Lay::oBook + i, jl);
-    }
+    double book[3 * d + 1];
+    SSB_UNROLL
+    for (int i = 0; i < 3 * d + 1; ++i) book[i] = L.ld(Lay::oBook + i, jl);
     double smu_i[NREG], smu_f[NREG], stan_i[NREG], stan_f[NREG];
     SSB_UNROLL
     for (int r = 0; r < NREG; ++r) {
