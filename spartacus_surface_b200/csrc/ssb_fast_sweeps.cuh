@@ -48,6 +48,14 @@ struct Scr {
     if (keep) v = ld(e, lev);
     return v;
   }
+  SSB_HDI void prefetch(int e, int lev) const {  // into L2 (no register, no scoreboard entry)
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)lev * lev_stride + (size_t)e * kScratchTile));
+#else
+    (void)e;
+    (void)lev;
+#endif
+  }
   SSB_HDI void st(int e, int lev, double v) const {
 #if defined(__CUDA_ARCH__)
     __stcs(base + (size_t)lev * lev_stride + (size_t)e * kScratchTile, v);
@@ -74,6 +82,19 @@ SSB_HD constexpr int seg_class(int i, int j) {
                          ? 1
                          : ((KIND == 2 ? i : i / NS) > 0 && (KIND == 0 ? j / NS : j) > 0) ? 2 : 0;
 }
+
+// L2 prefetch of the NA x NA block at offset `off` (n x n layout) of level `lev`
+template <int n, int NA, int I0>
+SSB_HDI void prefetch_block(const Scr &S, int off, int lev) {
+  SSB_UNROLL
+  for (int j = 0; j < NA; ++j) {
+    SSB_UNROLL
+    for (int i = 0; i < NA; ++i) S.prefetch(off + (I0 + i) + n * (I0 + j), lev);
+  }
+}
+#ifndef SSB_SWEEP_PREFETCH
+#define SSB_SWEEP_PREFETCH 0
+#endif
 
 // (V (x) I_NS) x : below-interface vector (NRB*NS) from the above-interface one (NREG*NS)
 template <int NREG, int NRB, int NS>
@@ -384,6 +405,16 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
     // the adding step on the block of regions the layer solves (ssb_sweep_blocks.cuh); with the columns
     // of the launch ordered by segment pattern the switch is uniform per warp
     const int seg = (int)L.ld(Lay::oGeo + 7, jl);
+    if (SSB_SWEEP_PREFETCH && jl + 1 < nlay) {
+      const int sn = (int)L.ld(Lay::oGeo + 7, jl + 1);
+      if (NREG == 1 || sn == 0) {
+        prefetch_block<n, n, 0>(L, Lay::oR, jl + 1);
+        prefetch_block<n, n, 0>(L, Lay::oT, jl + 1);
+      } else if (sn == 1) {
+        prefetch_block<n, NS, 0>(L, Lay::oR, jl + 1);
+        prefetch_block<n, NS, 0>(L, Lay::oT, jl + 1);
+      }
+    }
     double Ab[n * n], Db[n * d];
     if (NREG == 1 || seg == 0)
       sw_up_block<Lay, NREG, NS, n, 0>(st, L, W, jl, Ab, Db);
@@ -495,6 +526,18 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
         SSB_UNROLL
         for (int up = 0; up < NREG; ++up) s = fma(V[lo + NRB * up], dir_above[up], s);
         dir_below[lo] = s;
+      }
+    }
+    if (SSB_SWEEP_PREFETCH && jl > 0) {
+      const int sn = (int)L.ld(Lay::oGeo + 7, jl - 1);
+      prefetch_block<n, n, 0>(W, Lay::oAa, jl - 1);
+      if (NREG == 1 || sn == 0) {
+        prefetch_block<n, n, 0>(L, Lay::oT, jl - 1);
+        prefetch_block<n, n, 0>(L, Lay::oR, jl - 1);
+        prefetch_block<n, n, 0>(W, Lay::oLU, jl - 1);
+      } else if (sn == 1) {
+        prefetch_block<n, NS, 0>(L, Lay::oT, jl - 1);
+        prefetch_block<n, NS, 0>(L, Lay::oR, jl - 1);
       }
     }
     // the step on the block of regions the layer solves (ssb_sweep_blocks.cuh)
