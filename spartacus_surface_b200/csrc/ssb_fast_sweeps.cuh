@@ -385,6 +385,9 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
   }
   const Scr L(a.layer, a.lmax, a.ne_layer, q);
   const Scr W(a.sweep, a.lmax + 1, a.ne_sweep, q);
+  // the upwelling flux outside the block a layer solves is only needed for the flux profiles (and at
+  // the ground: level 0 is always stored and read in full)
+  const bool full_ua = fdir.flux_dn_layer_top != nullptr || fdif.flux_dn_layer_top != nullptr;
 
   // ---- upward sweep: state = [a_above (n x n) | d_above (n x d)] ------------
   SSB_UNROLL
@@ -463,8 +466,19 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
         }
       }
     }
-    SSB_UNROLL
-    for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, jl + 1, st(i));
+    // the state above the top layer is the top-of-canopy albedo (used from `st` below, never re-read);
+    // a consumer layer that solves a sub-block gets only the entries it reads (interface_store_pruned)
+    if (jl + 1 < nlay) {
+      const int sn = (NREG == 1 || full_ua) ? 0 : (int)L.ld(Lay::oGeo + 7, jl + 1);
+      if (sn == 0) {
+        SSB_UNROLL
+        for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, jl + 1, st(i));
+      } else if (sn == 1) {
+        interface_store_pruned<Lay, n, NS, 0, 1, 0>(st, W, jl + 1);
+      } else {
+        interface_store_pruned<Lay, n, Lay::vegNA, Lay::vegI0, Lay::vegNA / NS, Lay::vegI0 / NS>(st, W, jl + 1);
+      }
+    }
   }
   double talb_diff = 0.0, talb_dir = 0.0;
   {
@@ -545,12 +559,21 @@ SSB_HD inline void fast_column_sweeps_sw(const ClassArgs &a, int q, const StateM
     if (NREG == 1 || seg == 0)
       sw_down_block<Lay, NREG, NS, n, 0>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above, ddir, refl, ub_d, ub_f,
                                          ua_d, ua_f, if_d, if_f, idir);
-    else if (seg == 1)
-      sw_down_block<Lay, NREG, NS, NS, 0>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above, ddir, refl, ub_d, ub_f,
-                                          ua_d, ua_f, if_d, if_f, idir);
-    else
-      sw_down_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above, ddir,
-                                                          refl, ub_d, ub_f, ua_d, ua_f, if_d, if_f, idir);
+    else if (seg == 1) {
+      if (full_ua || jl == 0)
+        sw_down_block<Lay, NREG, NS, NS, 0, true>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above, ddir, refl, ub_d,
+                                                  ub_f, ua_d, ua_f, if_d, if_f, idir);
+      else
+        sw_down_block<Lay, NREG, NS, NS, 0, false>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above, ddir, refl, ub_d,
+                                                   ub_f, ua_d, ua_f, if_d, if_f, idir);
+    } else {
+      if (full_ua || jl == 0)
+        sw_down_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0, true>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above,
+                                                                  ddir, refl, ub_d, ub_f, ua_d, ua_f, if_d, if_f, idir);
+      else
+        sw_down_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0, false>(L, W, jl, xb_d, xb_f, dir_below, xa_d, xa_f, dir_above,
+                                                                   ddir, refl, ub_d, ub_f, ua_d, ua_f, if_d, if_f, idir);
+    }
     SSB_UNROLL
     for (int i = n; i < m; ++i) ub_d[i] = ub_f[i] = 0.0;
     if (URBAN) {
@@ -750,6 +773,7 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
   }
   const Scr L(a.layer, a.lmax, a.ne_layer, q);
   const Scr W(a.sweep, a.lmax + 1, a.ne_sweep, q);
+  const bool full_ua = fint.flux_dn_layer_top != nullptr || fnorm.flux_dn_layer_top != nullptr;
   const double gemis = a.lw.ground_emissivity[(size_t)g + (size_t)nspec * col];
   const double gemission = a.lw.ground_emission[(size_t)g + (size_t)nspec * col];
 
@@ -812,8 +836,17 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
         st(Lay::oSa + u * NS + jt) = s;
       }
     }
-    SSB_UNROLL
-    for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, jl + 1, st(i));
+    if (jl + 1 < nlay) {  // (see the shortwave sweep)
+      const int sn = (NREG == 1 || full_ua) ? 0 : (int)L.ld(Lay::oGeo + 7, jl + 1);
+      if (sn == 0) {
+        SSB_UNROLL
+        for (int i = 0; i < Lay::state_doubles; ++i) W.st(i, jl + 1, st(i));
+      } else if (sn == 1) {
+        interface_store_pruned<Lay, n, NS, 0, 1, 0>(st, W, jl + 1);
+      } else {
+        interface_store_pruned<Lay, n, Lay::vegNA, Lay::vegI0, 1, 0>(st, W, jl + 1);
+      }
+    }
   }
   double top_emissivity, top_emission = 0.0;
   {
@@ -862,11 +895,19 @@ SSB_HD inline void fast_column_sweeps_lw(const ClassArgs &a, int q, const StateM
     double ub_i[m], ub_f[m], if_i[n], if_f[n];
     if (NREG == 1 || seg == 0)
       lw_down_block<Lay, NREG, NS, n, 0>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f, if_i, if_f);
-    else if (seg == 1)
-      lw_down_block<Lay, NREG, NS, NS, 0>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f, if_i, if_f);
-    else
-      lw_down_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f, if_i,
-                                                          if_f);
+    else if (seg == 1) {
+      if (full_ua || jl == 0)
+        lw_down_block<Lay, NREG, NS, NS, 0, true>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f, if_i, if_f);
+      else
+        lw_down_block<Lay, NREG, NS, NS, 0, false>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f, if_i, if_f);
+    } else {
+      if (full_ua || jl == 0)
+        lw_down_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0, true>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f,
+                                                                  if_i, if_f);
+      else
+        lw_down_block<Lay, NREG, NS, Lay::vegNA, Lay::vegI0, false>(L, W, jl, xb_i, xb_f, xa_i, xa_f, ub_i, ub_f, ua_i, ua_f,
+                                                                   if_i, if_f);
+    }
     SSB_UNROLL
     for (int i = n; i < m; ++i) ub_i[i] = ub_f[i] = 0.0;
     if (URBAN) {

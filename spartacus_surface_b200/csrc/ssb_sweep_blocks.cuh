@@ -21,6 +21,28 @@
 
 namespace ssb {
 
+// The interface state stored at level jl is consumed by layer jl alone (downward pass).  A consumer that
+// solves only the block A = [I0, I0 + NA) and does not need the upwelling flux outside it reads only the
+// rows and columns of a_above that touch A, and the A rows of the vector part of the state: NVC columns
+// starting at V0 of d_above (the direct beam of the block's regions) or source_above (NVC = 1).  The rest
+// of the state never goes to HBM (a clear-only layer at 2 streams: 22 instead of 54 doubles).
+template <class Lay, int n, int NA, int I0, int NVC, int V0, class ScrT>
+SSB_HDI void interface_store_pruned(const StateMem &st, const ScrT &W, int lev) {
+  SSB_UNROLL
+  for (int j = 0; j < n; ++j) {
+    SSB_UNROLL
+    for (int i = 0; i < n; ++i) {
+      if ((i >= I0 && i < I0 + NA) || (j >= I0 && j < I0 + NA)) W.st(Lay::oAa + i + n * j, lev, st(Lay::oAa + i + n * j));
+    }
+  }
+  constexpr int oV = n * n;  // d_above (n x d) or source_above (n) follows a_above in the state
+  SSB_UNROLL
+  for (int k = 0; k < NVC; ++k) {
+    SSB_UNROLL
+    for (int i = 0; i < NA; ++i) W.st(oV + (I0 + i) + n * (V0 + k), lev, st(oV + (I0 + i) + n * (V0 + k)));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Shortwave
 // ---------------------------------------------------------------------------------------------
@@ -108,12 +130,16 @@ SSB_HDI void sw_up_block(const StateMem &st, const ScrT &L, const ScrT &W, int j
 // downward: from the fluxes below the interface above the layer (xb_*: first n entries used, dir_below:
 // first d entries) to the fluxes just above the layer base and the integrated fluxes.
 // Suffix d: direct-source pass, f: diffuse-source pass.  Every output array is full size (n or d).
-template <class Lay, int NREG, int NS, int NA, int I0, class ScrT>
+template <class Lay, int NREG, int NS, int NA, int I0, bool FULL_UA = true, class ScrT>
 SSB_HDI void sw_down_block(const ScrT &L, const ScrT &W, int jl, const double *xb_d, const double *xb_f,
                            const double *dir_below, double *xa_d, double *xa_f, double *dir_above, double *ddir,
                            double *refl, double *ub_d, double *ub_f, double *ua_d, double *ua_f, double *if_d,
                            double *if_f, double *idir) {
   constexpr int n = NREG * NS, d = NREG, DA = NA / NS, R0 = I0 / NS;
+  // rows of the interface state outside the block are only needed for the upwelling flux outside the
+  // block (flux profiles, ground level): without FULL_UA they are neither stored nor loaded
+  // (interface_store_pruned)
+  constexpr bool all_rows = (NA == n) || FULL_UA;
   double y_d[NA], y_f[NA], z1_d[NA], z1_f[NA], z2_d[NA], z2_f[NA];
   SSB_UNROLL
   for (int i = 0; i < NA; ++i) y_d[i] = y_f[i] = 0.0;
@@ -147,7 +173,10 @@ SSB_HDI void sw_down_block(const ScrT &L, const ScrT &W, int jl, const double *x
   SSB_UNROLL
   for (int k = 0; k < DA; ++k) {
     SSB_UNROLL
-    for (int i = 0; i < n; ++i) refl[i] = fma(W.ld(Lay::oDa + i + n * (R0 + k), jl), dir_above[R0 + k], refl[i]);
+    for (int i = 0; i < n; ++i) {
+      if (all_rows || (i >= I0 && i < I0 + NA))
+        refl[i] = fma(W.ld(Lay::oDa + i + n * (R0 + k), jl), dir_above[R0 + k], refl[i]);
+    }
   }
   // z1 = D_AA^-1 (a_AA y + refl_A) ; z2 = D_AA^-1 (y + R_AA refl_A) ; ub_A = R_AA xb_A
   SSB_UNROLL
@@ -240,9 +269,11 @@ SSB_HDI void sw_down_block(const ScrT &L, const ScrT &W, int jl, const double *x
   for (int j = 0; j < n; ++j) {
     SSB_UNROLL
     for (int i = 0; i < n; ++i) {
-      const double a = W.ld(Lay::oAa + i + n * j, jl);
-      ua_d[i] = fma(a, xa_d[j], ua_d[i]);
-      ua_f[i] = fma(a, xa_f[j], ua_f[i]);
+      if (all_rows || (i >= I0 && i < I0 + NA)) {
+        const double a = W.ld(Lay::oAa + i + n * j, jl);
+        ua_d[i] = fma(a, xa_d[j], ua_d[i]);
+        ua_f[i] = fma(a, xa_f[j], ua_f[i]);
+      }
     }
   }
   // integrated fluxes across the layer (only the solved regions absorb)
@@ -349,14 +380,15 @@ SSB_HDI void lw_up_block(const StateMem &st, const ScrT &L, const ScrT &W, int j
   }
 }
 
-template <class Lay, int NREG, int NS, int NA, int I0, class ScrT>
+template <class Lay, int NREG, int NS, int NA, int I0, bool FULL_UA = true, class ScrT>
 SSB_HDI void lw_down_block(const ScrT &L, const ScrT &W, int jl, const double *xb_i, const double *xb_f, double *xa_i,
                            double *xa_f, double *ub_i, double *ub_f, double *ua_i, double *ua_f, double *if_i,
                            double *if_f) {
   constexpr int n = NREG * NS;
+  constexpr bool all_rows = (NA == n) || FULL_UA;  // see sw_down_block
   double src[NA], sa[n], y_i[NA], y_f[NA], z1_i[NA], z1_f[NA], z2_i[NA], z2_f[NA];
   SSB_UNROLL
-  for (int i = 0; i < n; ++i) sa[i] = W.ld(Lay::oSa + i, jl);
+  for (int i = 0; i < n; ++i) sa[i] = (all_rows || (i >= I0 && i < I0 + NA)) ? W.ld(Lay::oSa + i, jl) : 0.0;
   SSB_UNROLL
   for (int i = 0; i < NA; ++i) {
     src[i] = L.ld(Lay::oSrc + I0 + i, jl);
@@ -455,9 +487,11 @@ SSB_HDI void lw_down_block(const ScrT &L, const ScrT &W, int jl, const double *x
   for (int j = 0; j < n; ++j) {
     SSB_UNROLL
     for (int i = 0; i < n; ++i) {
-      const double a = W.ld(Lay::oAa + i + n * j, jl);
-      ua_i[i] = fma(a, xa_i[j], ua_i[i]);
-      ua_f[i] = fma(a, xa_f[j], ua_f[i]);
+      if (all_rows || (i >= I0 && i < I0 + NA)) {
+        const double a = W.ld(Lay::oAa + i + n * j, jl);
+        ua_i[i] = fma(a, xa_i[j], ua_i[i]);
+        ua_f[i] = fma(a, xa_f[j], ua_f[i]);
+      }
     }
   }
   // integrated fluxes: int_flux (dn_below + up_above) + int_flux_source

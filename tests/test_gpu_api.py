@@ -244,6 +244,27 @@ def test_full_size_properties():
     lib.ssb200_release()
 
 
+def test_pruned_interface_state_is_invisible():
+    """Without flux profiles (the benchmark configuration) the sweeps store and load only the part of
+    the interface state a layer that solves a sub-block of its regions reads
+    (ssb_sweep_blocks.cuh: interface_store_pruned): every member other than the profiles equals the
+    run with profiles (full interface state) bit for bit, 2 and 4 streams."""
+    lib = load()
+    for streams in (2, 4):
+        cfg = _cfg(streams)
+        cp, sw, lw = make_synthetic(cfg, 4096 if streams == 2 else 512, 16)
+        outs = []
+        for profile in (True, False):
+            bc, fl = _outputs(cfg, cp.ncol, cp.ntotlay, profile=profile)
+            assert radsurf(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+            outs.append(_as_dict(fl, bc))
+        assert "flux_dn_layer_top" in outs[0]["lw_norm"] and "flux_dn_layer_top" not in outs[1]["lw_norm"]
+        for n, f in outs[1].items():
+            for k, v in f.items():
+                assert np.array_equal(v, outs[0][n][k]), (streams, n, k, float(np.abs(v - outs[0][n][k]).max()))
+    lib.ssb200_release()
+
+
 def test_simple_spectrum_lw_on_device():
     """calc_simple_spectrum_lw through the device entry equals the host (numpy) version."""
     import copy

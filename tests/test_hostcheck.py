@@ -169,3 +169,36 @@ def test_staging_is_invisible(case):
     _, c = _run(case, hostcheck_lib.make_solver(records=True, stage=True), cols=(2, 3))
     _, d = _run(case, hostcheck_lib.make_solver(records=True, stage=False), cols=(2, 3))
     _identical(c, d)
+
+
+@pytest.mark.parametrize("streams", [1, 2, 3])
+def test_pruned_interface_state_is_invisible(streams):
+    """Without flux profiles the sweeps store and load only the part of the interface state that a
+    layer solving a sub-block of its regions reads (ssb_sweep_blocks.cuh: interface_store_pruned).
+    On the synthetic benchmark canopy (vegetation-free layers aloft) every member other than the
+    profiles must equal the run WITH profiles (full interface state) bit for bit."""
+    from spartacus_surface_b200 import config_type, canopy_flux_type, boundary_conds_out_type
+    from spartacus_surface_b200.radsurf_canopy_flux import ALL_FIELDS
+    from spartacus_surface_b200.synthetic import make_synthetic
+    cfg = config_type(n_vegetation_region_urban=2, n_vegetation_region_forest=2, n_stream_sw_urban=streams,
+                      n_stream_lw_urban=streams, n_stream_sw_forest=streams,
+                      n_stream_lw_forest=streams).consolidate(LG)
+    cp, sw, lw = make_synthetic(cfg, 48, 16)
+    solver = hostcheck_lib.make_solver(fast=True)
+
+    def run(profile):
+        bc = boundary_conds_out_type().allocate(cp.ncol, 1, 1)
+        fl = [canopy_flux_type().allocate(cfg, cp.ncol, cp.ntotlay, 1, use_direct=d, do_save_flux_profile=profile)
+              for d in (True, True, False, False)]
+        assert solver(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+        out = {n: {k: getattr(f, k) for k in ALL_FIELDS if getattr(f, k) is not None}
+               for n, f in zip(golden_io.FLUX_NAMES, fl)}
+        out["bc"] = {k: getattr(bc, k) for k in golden_io.BC_FIELDS}
+        return out
+
+    with_profiles, without = run(True), run(False)
+    assert "flux_dn_layer_top" in with_profiles["sw_norm_dir"] and "flux_dn_layer_top" not in without["sw_norm_dir"]
+    assert (cp.veg_fraction.reshape(cp.ncol, 16)[:, -1] == 0.0).all()  # clear-only layers aloft
+    for name, fields in without.items():
+        for k, v in fields.items():
+            assert np.array_equal(v, with_profiles[name][k]), (name, k, np.abs(v - with_profiles[name][k]).max())
