@@ -22,6 +22,19 @@ namespace ssb {
     }                                                                                                  \
   } while (0)
 
+
+// Where the per-thread slice lives.  Shared memory ([element][thread], conflict-free) as long as two
+// blocks of the kernel fit one SM; a slice too large for that (3 regions x 4 streams: 1.4-1.7 KB per
+// thread, one 128-thread block per SM) goes to the thread's local memory instead, which halves neither
+// the block count nor the warps that hide the latency of everything else (SSB_SLICE_LOCAL_BYTES: the
+// shared-memory bytes per block above which the local variant is used; 0 switches it off).
+#ifndef SSB_SLICE_LOCAL_BYTES
+#define SSB_SLICE_LOCAL_BYTES (112 * 1024)
+#endif
+SSB_HD constexpr bool slice_is_local(int doubles, int threads) {
+  return SSB_SLICE_LOCAL_BYTES > 0 && (long)sizeof(double) * doubles * threads > (long)SSB_SLICE_LOCAL_BYTES;
+}
+
 constexpr int kFastBlock = 128;  // sweeps: one thread per (column, interval)
 #ifndef SSB_SWEEP_MINB
 #define SSB_SWEEP_MINB 2  // resident blocks per SM the sweeps are compiled for (3: 168 registers, 1-1.8 KB of spills: 51.7 -> 68.4 ms)
@@ -94,14 +107,22 @@ __global__ void __launch_bounds__(kLayerBlock, kLayerMinB) k_fast_layer_sw_seg(C
   if (t >= a.perm_count[SEG]) return;
   const long id = a.perm[(size_t)SEG * (size_t)nt + t];
   const long width = (long)a.ncols * a.cfg.nspec;
-  const StateMem st{ssb_stack + threadIdx.x, kLayerBlock};
-  fast_layer_problem_sw_seg<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width), st);
+  constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
+  if constexpr (slice_is_local(LayerStack<NR, NS>::sw_doubles, kLayerBlock)) {
+    double slice[LayerStack<NR, NS>::sw_doubles];
+    fast_layer_problem_sw_seg<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width), StateMem{slice, 1});
+  } else {
+    const StateMem st{ssb_stack + threadIdx.x, kLayerBlock};
+    fast_layer_problem_sw_seg<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width), st);
+  }
 }
 template <int NREG, int NS, int SEG>
 static void launch_fast_layer_sw_seg(const ClassArgs &a, long nt, unsigned grid, cudaStream_t st) {
   constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
-  const size_t smem = sizeof(double) * LayerStack<NR, NS>::sw_doubles * kLayerBlock;
-  SSB_SMEM_ONCE((k_fast_layer_sw_seg<NREG, NS, SEG>), smem);
+  const size_t smem = slice_is_local(LayerStack<NR, NS>::sw_doubles, kLayerBlock)
+                          ? 0
+                          : sizeof(double) * LayerStack<NR, NS>::sw_doubles * kLayerBlock;
+  if (smem > 0) SSB_SMEM_ONCE((k_fast_layer_sw_seg<NREG, NS, SEG>), smem);
   k_fast_layer_sw_seg<NREG, NS, SEG><<<grid, kLayerBlock, smem, st>>>(a, nt);
   fast_note(cudaGetLastError());
 }
@@ -126,16 +147,23 @@ __global__ void __launch_bounds__(kFastBlock, SSB_SWEEP_MINB) k_fast_sweeps_sw(C
   extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
-  const StateMem st{ssb_state + threadIdx.x, kFastBlock};
-  fast_column_sweeps_sw<NREG, NS, URBAN>(a, (int)t, st);
+  if constexpr (slice_is_local(SwSweepLayout<NREG, NS, URBAN>::state_doubles, kFastBlock)) {
+    double slice[SwSweepLayout<NREG, NS, URBAN>::state_doubles];
+    fast_column_sweeps_sw<NREG, NS, URBAN>(a, (int)t, StateMem{slice, 1});
+  } else {
+    const StateMem st{ssb_state + threadIdx.x, kFastBlock};
+    fast_column_sweeps_sw<NREG, NS, URBAN>(a, (int)t, st);
+  }
 }
 // (3 or 4 blocks per SM at 168 / 128 registers were measured: the spills cost more than the
 // extra warps hide)
 template <int NREG, int NS, bool URBAN>
 static void launch_fast_sweeps_sw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
-  const size_t smem = sizeof(double) * SwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
-  SSB_SMEM_ONCE((k_fast_sweeps_sw<NREG, NS, URBAN>), smem);
+  const size_t smem = slice_is_local(SwSweepLayout<NREG, NS, URBAN>::state_doubles, kFastBlock)
+                          ? 0
+                          : sizeof(double) * SwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
+  if (smem > 0) SSB_SMEM_ONCE((k_fast_sweeps_sw<NREG, NS, URBAN>), smem);
   k_fast_sweeps_sw<NREG, NS, URBAN><<<grid, kFastBlock, smem, st>>>(a, nt);
   fast_note(cudaGetLastError());
 }
@@ -161,14 +189,22 @@ __global__ void __launch_bounds__(kLayerBlock, kLayerMinB) k_fast_layer_lw_seg(C
   if (t >= a.perm_count[SEG]) return;
   const long id = a.perm[(size_t)SEG * (size_t)nt + t];
   const long width = (long)a.ncols * a.cfg.nspec;
-  const StateMem st{ssb_stack + threadIdx.x, kLayerBlock};
-  fast_layer_problem_lw_impl<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width), st);
+  constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
+  if constexpr (slice_is_local(LayerStack<NR, NS>::lw_doubles, kLayerBlock)) {
+    double slice[LayerStack<NR, NS>::lw_doubles];
+    fast_layer_problem_lw_impl<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width), StateMem{slice, 1});
+  } else {
+    const StateMem st{ssb_stack + threadIdx.x, kLayerBlock};
+    fast_layer_problem_lw_impl<NREG, NS, SEG>(a, (int)(id % width), (int)(id / width), st);
+  }
 }
 template <int NREG, int NS, int SEG>
 static void launch_fast_layer_lw_seg(const ClassArgs &a, long nt, unsigned grid, cudaStream_t st) {
   constexpr int NR = (SEG == 0) ? NREG : (SEG == 1 ? 1 : (NREG > 1 ? NREG - 1 : 1));
-  const size_t smem = sizeof(double) * LayerStack<NR, NS>::lw_doubles * kLayerBlock;
-  SSB_SMEM_ONCE((k_fast_layer_lw_seg<NREG, NS, SEG>), smem);
+  const size_t smem = slice_is_local(LayerStack<NR, NS>::lw_doubles, kLayerBlock)
+                          ? 0
+                          : sizeof(double) * LayerStack<NR, NS>::lw_doubles * kLayerBlock;
+  if (smem > 0) SSB_SMEM_ONCE((k_fast_layer_lw_seg<NREG, NS, SEG>), smem);
   k_fast_layer_lw_seg<NREG, NS, SEG><<<grid, kLayerBlock, smem, st>>>(a, nt);
   fast_note(cudaGetLastError());
 }
@@ -193,16 +229,23 @@ __global__ void __launch_bounds__(kFastBlock, SSB_SWEEP_MINB) k_fast_sweeps_lw(C
   extern __shared__ double ssb_state[];  // [state element][thread]: conflict-free per-thread slices
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (t >= nt) return;
-  const StateMem st{ssb_state + threadIdx.x, kFastBlock};
-  fast_column_sweeps_lw<NREG, NS, URBAN>(a, (int)t, st);
+  if constexpr (slice_is_local(LwSweepLayout<NREG, NS, URBAN>::state_doubles, kFastBlock)) {
+    double slice[LwSweepLayout<NREG, NS, URBAN>::state_doubles];
+    fast_column_sweeps_lw<NREG, NS, URBAN>(a, (int)t, StateMem{slice, 1});
+  } else {
+    const StateMem st{ssb_state + threadIdx.x, kFastBlock};
+    fast_column_sweeps_lw<NREG, NS, URBAN>(a, (int)t, st);
+  }
 }
 // (3 or 4 blocks per SM at 168 / 128 registers were measured: the spills cost more than the
 // extra warps hide)
 template <int NREG, int NS, bool URBAN>
 static void launch_fast_sweeps_lw(const ClassArgs &a, long nt, cudaStream_t st) {
   const unsigned grid = (unsigned)((nt + kFastBlock - 1) / kFastBlock);
-  const size_t smem = sizeof(double) * LwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
-  SSB_SMEM_ONCE((k_fast_sweeps_lw<NREG, NS, URBAN>), smem);
+  const size_t smem = slice_is_local(LwSweepLayout<NREG, NS, URBAN>::state_doubles, kFastBlock)
+                          ? 0
+                          : sizeof(double) * LwSweepLayout<NREG, NS, URBAN>::state_doubles * kFastBlock;
+  if (smem > 0) SSB_SMEM_ONCE((k_fast_sweeps_lw<NREG, NS, URBAN>), smem);
   k_fast_sweeps_lw<NREG, NS, URBAN><<<grid, kFastBlock, smem, st>>>(a, nt);
   fast_note(cudaGetLastError());
 }
