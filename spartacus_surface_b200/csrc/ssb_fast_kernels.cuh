@@ -58,9 +58,14 @@ constexpr int kLayerMinB = SSB_LAYER_THREADS / SSB_LAYER_BLOCK;
 // sub-block of regions they solve, so that every warp of the layer kernels runs one code
 // path.  Warp-aggregated append: the order inside a segment is not deterministic, the results
 // are (every problem is independent).
+// resident blocks per SM the partition pass is compiled for: at 1 and 2 streams 64 registers (4 blocks) hide more
+// of its load latency than the 80 it would take (47.4 -> 47.2 ms per step); the 4-stream version needs its 128-162
+#ifndef SSB_PARTITION_MINB
+#define SSB_PARTITION_MINB (SSB_NS <= 2 ? 4 : 1)
+#endif
 constexpr int kPartitionBlock = 256;
 template <int NREG, int NS, bool LW>
-static __global__ void __launch_bounds__(kPartitionBlock) k_partition_layers(ClassArgs a, long nt) {
+static __global__ void __launch_bounds__(kPartitionBlock, SSB_PARTITION_MINB) k_partition_layers(ClassArgs a, long nt) {
   extern __shared__ double ssb_stack[];
   const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
   int seg = -1;

@@ -265,6 +265,28 @@ def test_pruned_interface_state_is_invisible():
     lib.ssb200_release()
 
 
+def test_pruned_interface_state_mixed_tiles():
+    """The same bit-identity on the mixed case (forest and urban tiles with and without vegetation, ragged
+    layers, night columns, several spectral intervals; tests/mixed_case.py), 2 and 4 streams."""
+    from mixed_case import mixed_config, make_mixed
+    for streams in (2, 4):
+        cfg = mixed_config(streams).consolidate()
+        cp, sw, lw = make_mixed(cfg, ncol=1500)
+        outs = []
+        for profile in (True, False):
+            bc = boundary_conds_out_type().allocate(cp.ncol, cfg.nsw, cfg.nlw)
+            fl = [canopy_flux_type().allocate(cfg, cp.ncol, cp.ntotlay, n, use_direct=d, do_save_flux_profile=profile)
+                  for n, d in ((cfg.nsw, True), (cfg.nsw, True), (cfg.nlw, False), (cfg.nlw, False))]
+            for f in fl:
+                f.fill(7.0)
+            assert radsurf(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+            outs.append(_as_dict(fl, bc))
+        for n, f in outs[1].items():
+            for k, v in f.items():
+                assert np.array_equal(v, outs[0][n][k]), (streams, n, k, float(np.abs(v - outs[0][n][k]).max()))
+    load().ssb200_release()
+
+
 def test_simple_spectrum_lw_on_device():
     """calc_simple_spectrum_lw through the device entry equals the host (numpy) version."""
     import copy

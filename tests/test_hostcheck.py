@@ -202,3 +202,32 @@ def test_pruned_interface_state_is_invisible(streams):
     for name, fields in without.items():
         for k, v in fields.items():
             assert np.array_equal(v, with_profiles[name][k]), (name, k, np.abs(v - with_profiles[name][k]).max())
+
+
+@pytest.mark.parametrize("streams", [2, 4])
+def test_pruned_interface_state_mixed_tiles(streams):
+    """The same bit-identity on the mixed case: forest and urban tiles with and without vegetation, ragged
+    layers, night columns, several spectral intervals, direct ground albedo (tests/mixed_case.py)."""
+    from mixed_case import mixed_config, make_mixed
+    from spartacus_surface_b200 import canopy_flux_type, boundary_conds_out_type
+    from spartacus_surface_b200.radsurf_canopy_flux import ALL_FIELDS
+    cfg = mixed_config(streams).consolidate(LG)
+    cp, sw, lw = make_mixed(cfg)
+    solver = hostcheck_lib.make_solver(fast=True)
+
+    def run(profile):
+        bc = boundary_conds_out_type().allocate(cp.ncol, cfg.nsw, cfg.nlw)
+        fl = [canopy_flux_type().allocate(cfg, cp.ncol, cp.ntotlay, n, use_direct=d, do_save_flux_profile=profile)
+              for n, d in ((cfg.nsw, True), (cfg.nsw, True), (cfg.nlw, False), (cfg.nlw, False))]
+        for f in fl:
+            f.fill(7.0)
+        assert solver(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+        out = {n: {k: getattr(f, k) for k in ALL_FIELDS if getattr(f, k) is not None}
+               for n, f in zip(golden_io.FLUX_NAMES, fl)}
+        out["bc"] = {k: getattr(bc, k) for k in golden_io.BC_FIELDS}
+        return out
+
+    with_profiles, without = run(True), run(False)
+    for name, fields in without.items():
+        for k, v in fields.items():
+            assert np.array_equal(v, with_profiles[name][k]), (name, k, np.abs(v - with_profiles[name][k]).max())
