@@ -329,14 +329,14 @@ int ssb200_last_kernel_counts(int64_t out[5]);
 
 /* Tuning knobs (results never depend on them beyond rounding; defaults in brackets):
  *   "scratch_budget_bytes"  device scratch per launch chunk and scratch lane [0 = automatic: a quarter
- *                           of the free memory, at most 24 GiB]
+ *                           of the free memory, at most 12 GiB]
  *   "fast_kernels"          [1] register-resident kernels where a configuration has them (1-4 streams);
  *                           0 = the generic one-thread-per-problem kernels everywhere (TEST-ONLY: they are the
  *                           correctness path of 8 streams, not a tuned one)
  *   "partition_layers"      [1] group layer problems by solved sub-block (needed by the fast layer kernels)
  *   "stage_layers"          [1] level-major staging of the per-layer arrays of a chunk (gather / scatter)
  *   "sort_columns"          [1] process the columns of a launch ordered by their segment pattern inside groups
- *   "sort_group"            [4096] of this many neighbours (0 = the whole chunk)
+ *   "sort_group"            [16384] of this many neighbours (0 = the whole chunk)
  *   "concurrent_passes"     [1] shortwave and longwave pass on two streams with separate scratch
  *   "pipeline"              [1] host entries upload, solve and download blocks of columns as three
  *   "pipeline_max_blocks"   [16] overlapping stages (effective with pinned host memory)

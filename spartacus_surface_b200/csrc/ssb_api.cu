@@ -256,7 +256,7 @@ struct Context {
   // irrelevant for the per-layer inputs and outputs: 59.8 -> 50.9 ms per step (without the staging the
   // ordering made the sweeps slower: round 1).
   int sort_columns = 1;
-  int sort_group = 4096;  // ... inside groups of this many neighbouring columns (0: the whole chunk)
+  int sort_group = 16384;  // ... inside groups of this many neighbouring columns (0: the whole chunk); measured 1024 .. 65536: 48.0 / 47.3 (4096) / 47.2 / 46.9 (16384) / 47.0 / 47.2 ms per step
   int partition = 1;  // group layer problems by solved sub-block before the fast layer kernels
   // column-resident kernels (ssb_fused.cuh) where they exist (1 and 2 streams); 0: split path
   // sweeps of the register-resident path at 1 and 2 streams: 0 = interface-state sweeps
@@ -624,7 +624,7 @@ int radsurf_device_locked(Context &cx, const ssb::CallArgs &ca, int istartcol, i
     SSB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     // per scratch lane (two lanes are live when the SW and LW passes run concurrently)
     size_t b = (free_b + cx.d_scratch[0].bytes + cx.d_scratch[1].bytes + cx.d_scratch[2].bytes) / 4;
-    const size_t cap = (size_t)24 << 30;
+    const size_t cap = (size_t)12 << 30;  // (more, smaller chunks overlap the two passes better: 47.0 -> 46.7 ms against 24 GiB)
     if (b > cap) b = cap;
     cx.budget_doubles = b / sizeof(double);
   }
