@@ -52,6 +52,11 @@ def _same(a, b):
             assert np.array_equal(v, b[n][k]), (n, k, float(np.abs(v - b[n][k]).max()))
 
 
+def copy_obj(obj):
+    import copy
+    return copy.copy(obj)
+
+
 def _to_device(obj):
     import copy
     import torch
@@ -284,6 +289,51 @@ def test_pruned_interface_state_mixed_tiles():
         for n, f in outs[1].items():
             for k, v in f.items():
                 assert np.array_equal(v, outs[0][n][k]), (streams, n, k, float(np.abs(v - outs[0][n][k]).max()))
+    load().ssb200_release()
+
+
+def test_argument_validation_instead_of_device_faults():
+    """Unknown tile codes and members a present tile type needs but that are not allocated are argument
+    errors with a message, not device faults (round-1 advisor findings); the context stays usable."""
+    cfg = _cfg()
+    cp, sw, lw = make_synthetic(cfg, 64, 4)
+    bc, fl = _outputs(cfg, cp.ncol, cp.ntotlay)
+    bad = copy_obj(cp)
+    bad.i_representation = cp.i_representation.copy()
+    bad.i_representation[3] = 9
+    with pytest.raises(RadsurfError, match="unknown i_representation"):
+        radsurf(cfg, bad, sw, lw, bc, None, None, *fl)
+    for obj, member in ((cp, "building_scale"), (cp, "veg_fsd"), (sw, "wall_albedo"), (lw, "ground_emission")):
+        broken = copy_obj(obj)
+        setattr(broken, member, None)
+        args = [broken if o is obj else o for o in (cp, sw, lw)]
+        with pytest.raises(RadsurfError, match=member):
+            radsurf(cfg, *args, bc, None, None, *fl)
+    assert radsurf(cfg, cp, sw, lw, bc, None, None, *fl) == 0  # the same context still solves
+
+
+def test_calls_from_two_streams_are_ordered():
+    """ssb200_radsurf_device shares one context (scratch, plan and status buffers): a call on another
+    stream than the previous one waits for it on the device, so back-to-back calls from two streams give
+    the results of the same calls made one after the other (round-1 advisor finding)."""
+    import torch
+    cfg = _cfg()
+    probs = []
+    for off in (0, 50_000):
+        cp, sw, lw = make_synthetic(cfg, 20_000, 16, col_offset=off, device="cuda:0")
+        probs.append((cp, sw, lw, _outputs(cfg, cp.ncol, cp.ntotlay, device="cuda:0", profile=False),
+                      _outputs(cfg, cp.ncol, cp.ntotlay, device="cuda:0", profile=False)))
+    torch.cuda.synchronize()
+    for cp, sw, lw, (bc, fl), _ in probs:  # one after the other, default stream
+        assert radsurf(cfg, cp, sw, lw, bc, None, None, *fl) == 0
+        torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(3):  # back to back, alternating streams, no host synchronisation in between
+        for (cp, sw, lw, _, (bc, fl)), st in zip(probs, streams):
+            assert radsurf(cfg, cp, sw, lw, bc, None, None, *fl, stream=st.cuda_stream) == 0
+    torch.cuda.synchronize()
+    for cp, sw, lw, (bc, fl), (bc2, fl2) in probs:
+        _same(_as_dict(fl, bc), _as_dict(fl2, bc2))
     load().ssb200_release()
 
 
